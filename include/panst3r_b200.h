@@ -1,0 +1,163 @@
+/* panst3r_b200 — C ABI of the Blackwell (sm_100a) PanSt3R inference hot path.
+ *
+ * Drop-in boundary for naver/panst3r's multi-view forward path.  Every entry point is plain C:
+ * raw device pointers + sizes, a CUDA stream handle, int return code (0 = ok, <0 = error, message via
+ * pst3r_last_error()).  The caller (PyTorch host code, see panst3r_b200/ops.py) owns all memory; the
+ * library never allocates device memory and never synchronises the stream.
+ *
+ * Reference interfaces replaced (paths relative to the naver/panst3r checkout):
+ *   - curope `rope_2d(tokens, positions, base, fwd)` (croco/curope, installed per README.md:67-71;
+ *     selected by 'RoPE100' at src/panst3r/model/input_mixer.py:16)            -> pst3r_rope2d
+ *   - `nn.Linear` / croco `Mlp` / `nn.MultiheadAttention` in-proj GEMMs
+ *     (model/upscalers/pixel_shuffle.py:17-27,40-54; model/mask_transformer.py:314,372,435-437;
+ *     model/input_mixer.py:14,19; upstream encoder/decoder blocks driven from engine/must3r.py:17-24,45,93)
+ *                                                                               -> pst3r_gemm_bf16
+ *   - xformers `memory_efficient_attention` / croco `Attention`,`CrossAttention` / torch MHA
+ *     (gradio_panst3r.py:25; model/blocks.py:18-19,32; model/mask_transformer.py:395-398)
+ *                                                                               -> pst3r_attention
+ *   - `torch.einsum("bqc,bnchw->bnqhw")` (model/mask_transformer.py:279-288)   -> pst3r_gemm_bf16 with
+ *     PST3R_STORE_TRANSPOSED (mask-logit planes) + pst3r_attn_mask_bits (:264-272, :172)
+ *   - `F.pixel_shuffle` (model/upscalers/pixel_shuffle.py:42,46,50)             -> PST3R_STORE_PIXSHUF2
+ *   - upstream LinearHead depth-to-space (pointmaps at engine/must3r.py:93)     -> PST3R_STORE_D2S
+ *   - `nn.LayerNorm`, `nn.GroupNorm`, sine PE, DINO preprocessing (model/dino.py:61-66), LoftUp featuriser
+ *     (model/upscalers/loftup.py:9-79)                                          -> pst3r_layernorm etc.
+ */
+#ifndef PANST3R_B200_H_
+#define PANST3R_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pst3r_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char* pst3r_last_error(void);
+int pst3r_version(void);
+/* Returns 0 if the current CUDA device is sm_100 (B200); <0 otherwise. */
+int pst3r_check_device(void);
+
+/* ---- GEMM: C[M,N] = epilogue(A[M,K] * B[N,K]^T) ---------------------------------------------
+ * A, B are bf16, K contiguous (row strides lda/ldb in elements, multiples of 8).  tcgen05 tensor cores,
+ * fp32 accumulation in TMEM, TMA-fed.  The epilogue is described by pst3r_gemm_epilogue. */
+enum {
+  PST3R_ACT_NONE = 0,
+  PST3R_ACT_GELU = 1, /* exact erf GELU (nn.GELU default) */
+  PST3R_ACT_RELU = 2
+};
+enum {
+  PST3R_STORE_PLAIN = 0,      /* out[row*ldo + col] */
+  PST3R_STORE_TRANSPOSED = 1, /* out[(row / rows_per_batch)*batch_stride + col*ldt + row % rows_per_batch] */
+  PST3R_STORE_PIXSHUF2 = 2,   /* row=(b,y,x) on grid_h x grid_w, col=4c+2i+j -> out[((b*2gh+2y+i)*2gw+2x+j)*ldo + c] */
+  PST3R_STORE_D2S = 3         /* row=(b,y,x), col=(i*P+j)*C+c -> fp32 out[((b*gh*P+y*P+i)*gw*P + x*P+j)*C + c] */
+};
+
+typedef struct pst3r_gemm_epilogue {
+  void* out;              /* bf16 or fp32 device pointer */
+  int64_t ldo;            /* row stride of out in elements (PLAIN / PIXSHUF2) */
+  int32_t out_f32;        /* 0: bf16 output, 1: fp32 output */
+  int32_t act;            /* PST3R_ACT_* (applied after bias) */
+  const float* bias;      /* [N] fp32 or NULL */
+  const float* col_scale; /* [N] fp32 or NULL (LayerScale; applied after act) */
+  const void* residual;   /* bf16 [M, ldr] or NULL (added last) */
+  int64_t ldr;
+  float alpha;            /* accumulator scale (applied first) */
+  int32_t store_mode;     /* PST3R_STORE_* */
+  int64_t rows_per_batch; /* TRANSPOSED */
+  int64_t batch_stride;   /* TRANSPOSED */
+  int64_t ldt;            /* TRANSPOSED */
+  int32_t grid_h, grid_w; /* PIXSHUF2 / D2S token grid */
+  int32_t d2s_patch;      /* D2S patch size P */
+  int32_t d2s_ch;         /* D2S channels C */
+  /* fused 2-D RoPE on the leading rope_cols columns (head_dim 64, pairs (j, j+16) in each 32-wide half;
+   * first half rotates by y, second by x) — replaces cuRoPE2D after the QKV projection */
+  const float* rope_cs;   /* [rope_maxpos][16][2] fp32 (cos, sin) or NULL */
+  const int32_t* rope_pos; /* [M][2] (y, x) */
+  int32_t rope_cols;
+  int32_t rope_maxpos;
+} pst3r_gemm_epilogue;
+
+int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
+                    const pst3r_gemm_epilogue* epi, pst3r_stream_t stream);
+
+/* ---- Attention: O = softmax(scale * Q K^T [+ mask]) V ----------------------------------------
+ * bf16 Q/K/V with head_dim 64 or 96, element strides given per (batch, token, head); head_dim contiguous.
+ * kv_batch_stride may be 0 (all batch items attend the same memory tokens: MUSt3R render pass).
+ * mask_bits (optional): uint32 words, bit (k & 31) of word [b][q][k >> 5] set => key k is BLOCKED for
+ * query q (shared by all heads, mask_transformer.py:272).
+ * O is written bf16 as [B, Nq, H*hd] with row stride ldo.
+ * workspace: fp32 scratch of pst3r_attention_workspace_bytes() bytes (split-KV partials), may be NULL when 0. */
+typedef struct pst3r_attn_args {
+  const void* q; int64_t q_sb, q_sn, q_sh;
+  const void* k; int64_t k_sb, k_sn, k_sh;
+  const void* v; int64_t v_sb, v_sn, v_sh;
+  void* o; int64_t o_sb, o_sn; /* o[b*o_sb + n*o_sn + h*hd + d] */
+  int32_t B, H, Nq, Nk, head_dim;
+  float scale;
+  const uint32_t* mask_bits; int64_t mask_sb, mask_sq; /* strides in words */
+  int32_t kv_splits;     /* 0 = auto */
+  void* workspace; int64_t workspace_bytes;
+} pst3r_attn_args;
+
+int64_t pst3r_attention_workspace_bytes(int32_t B, int32_t H, int32_t Nq, int32_t head_dim, int32_t kv_splits);
+int32_t pst3r_attention_auto_splits(int32_t B, int32_t H, int32_t Nq, int32_t Nk);
+int pst3r_attention(const pst3r_attn_args* args, pst3r_stream_t stream);
+
+/* ---- Normalisation / elementwise ------------------------------------------------------------- */
+/* y = LN(x [+ add]) * gamma + beta ; x bf16 or fp32 [rows, dim] (row stride ldx), y bf16 or fp32.
+ * If sum_out != NULL the pre-norm sum (x + add) is also written (bf16, row stride ld_sum): fused
+ * "residual add + post-norm" of the Mask2Former-style query decoder (mask_transformer.py:339-340). */
+int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const void* add, int64_t ld_add, const float* gamma,
+                    const float* beta, float eps, void* y, int32_t y_f32, int64_t ldy, void* sum_out,
+                    int64_t ld_sum, int32_t rows, int32_t dim, pst3r_stream_t stream);
+
+/* In-place 2-D RoPE, curope semantics: tokens bf16 [B, N, H, D] (D contiguous, D % 4 == 0),
+ * positions int32 [B, N, 2] = (y, x); angle = p * base^(-j/(D/4)); fwd = +1 / -1. */
+int pst3r_rope2d(void* tokens, int64_t s_b, int64_t s_n, int64_t s_h, const int32_t* pos, int32_t B, int32_t N,
+                 int32_t H, int32_t D, float base, float fwd, pst3r_stream_t stream);
+
+/* out[r, c] = a[r, c] + b[r % b_rows, c]  (bf16; pos-embedding / level-embedding adds) */
+int pst3r_add_bcast(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_rows, void* out, int64_t ldo,
+                    int32_t rows, int32_t cols, pst3r_stream_t stream);
+
+/* fp32 [rows, cols] (ld) -> bf16, and back */
+int pst3r_cast_f32_to_bf16(const float* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols,
+                           pst3r_stream_t stream);
+int pst3r_cast_bf16_to_f32(const void* x, int64_t ldx, float* y, int64_t ldy, int32_t rows, int32_t cols,
+                           pst3r_stream_t stream);
+
+/* Patchify (im2col) for the ViT patch embeddings: img fp32 [B,3,H,W] -> bf16 [B*(H/P)*(W/P), ldo] with
+ * column = c*P*P + i*P + j (Conv2d weight flattening).  Columns [3*P*P, ldo) are zero-filled. */
+int pst3r_patchify(const float* img, int32_t B, int32_t H, int32_t W, int32_t P, void* out, int64_t ldo,
+                   pst3r_stream_t stream);
+
+/* DINOv2 preprocessing fused with patchify (model/dino.py:61-66): x*0.5+0.5, ImageNet normalise, bilinear
+ * resize (align_corners=False) to (Ho, Wo), then im2col with patch P (14). */
+int pst3r_dino_preprocess_patchify(const float* img, int32_t B, int32_t H, int32_t W, int32_t Ho, int32_t Wo,
+                                   int32_t P, void* out, int64_t ldo, pst3r_stream_t stream);
+
+/* Mean of the centre 2x2 of every 8x8 cell of a pixel-major feature map: feats bf16 [B, Hm, Wm, C] ->
+ * bf16 [B, Hm/8, Wm/8, C].  The 8x bilinear downsample (align_corners=False) of the mask logits
+ * (mask_transformer.py:286) is linear in the features, so the attention mask only needs these. */
+int pst3r_center_pool8(const void* feats, int32_t B, int32_t Hm, int32_t Wm, int32_t C, void* out,
+                       pst3r_stream_t stream);
+
+/* logits_t fp32 [Q, ld] (TRANSPOSED store: row q, column = flattened key token) -> mask bits
+ * [Q, ceil(Nk/32)] with bit set iff logit < 0 (sigmoid < 0.5 => blocked); rows that would be fully blocked
+ * are cleared (mask_transformer.py:172). */
+int pst3r_attn_mask_bits(const float* logits_t, int64_t ld, int32_t Q, int32_t Nk, uint32_t* bits,
+                         pst3r_stream_t stream);
+
+/* L2-normalise rows: y = x / (||x|| + eps)  (fp32 in, bf16 or fp32 out; mask_transformer.py:227) */
+int pst3r_l2norm_rows(const float* x, int64_t ldx, void* y, int32_t y_f32, int64_t ldy, int32_t rows, int32_t cols,
+                      float eps, pst3r_stream_t stream);
+
+/* bf16 pixel-major [B, HW, C] -> fp32 channel-major [B, C, HW] (reference NCHW layout of mask_feats / fpn) */
+int pst3r_nhwc_to_nchw_f32(const void* x, int32_t B, int32_t HW, int32_t C, float* y, pst3r_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANST3R_B200_H_ */

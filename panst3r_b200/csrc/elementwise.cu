@@ -1,0 +1,414 @@
+// HBM-bound helper kernels of the PanSt3R forward path: LayerNorm (with fused residual add), 2-D RoPE,
+// broadcast adds, casts, ViT patchify (im2col), DINOv2 preprocessing, centre-2x2 pooling for the attention
+// mask, mask-bit packing, row L2 normalisation, layout transposes, LoftUp featuriser pieces.
+// All are plain coalesced / vectorised CUDA-core kernels: none of this work is GEMM shaped.
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/panst3r_b200.h"
+
+namespace pst3r {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, three cached passes (mean, centred variance, normalise).
+// ------------------------------------------------------------------------------------------------
+template <bool X_F32>
+__device__ __forceinline__ float ln_load(const void* x, long long idx) {
+  if (X_F32) return reinterpret_cast<const float*>(x)[idx];
+  return __bfloat162float(reinterpret_cast<const bf16*>(x)[idx]);
+}
+
+template <bool X_F32, bool Y_F32>
+__global__ void layernorm_kernel(const void* __restrict__ x, long long ldx, const bf16* __restrict__ add,
+                                 long long ld_add, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float eps, void* __restrict__ y, long long ldy, bf16* __restrict__ sum_out,
+                                 long long ld_sum, int rows, int dim) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const long long xo = (long long)row * ldx;
+  const long long ao = (long long)row * ld_add;
+  float s = 0.0f;
+  for (int i = lane; i < dim; i += 32) {
+    float v = ln_load<X_F32>(x, xo + i);
+    if (add) v += __bfloat162float(add[ao + i]);
+    s += v;
+  }
+  const float mean = warp_sum(s) / dim;
+  float ss = 0.0f;
+  for (int i = lane; i < dim; i += 32) {
+    float v = ln_load<X_F32>(x, xo + i);
+    if (add) v += __bfloat162float(add[ao + i]);
+    const float d = v - mean;
+    ss += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / dim + eps);
+  for (int i = lane; i < dim; i += 32) {
+    float v = ln_load<X_F32>(x, xo + i);
+    if (add) v += __bfloat162float(add[ao + i]);
+    if (sum_out) sum_out[(long long)row * ld_sum + i] = __float2bfloat16(v);
+    const float o = (v - mean) * rstd * gamma[i] + beta[i];
+    if (Y_F32)
+      reinterpret_cast<float*>(y)[(long long)row * ldy + i] = o;
+    else
+      reinterpret_cast<bf16*>(y)[(long long)row * ldy + i] = __float2bfloat16(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-D RoPE (curope semantics), in place.  One thread per (token, head, pair).
+// ------------------------------------------------------------------------------------------------
+__global__ void rope2d_kernel(bf16* __restrict__ t, long long s_b, long long s_n, long long s_h,
+                              const int* __restrict__ pos, int B, int N, int H, int D, float log2_base, float fwd) {
+  const int Q = D / 4;  // pairs per half
+  const long long total = (long long)B * N * H * 2 * Q;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = idx % Q;
+  long long r = idx / Q;
+  const int half = r % 2; r /= 2;
+  const int h = r % H; r /= H;
+  const int n = r % N;
+  const int b = r / N;
+  const int pp = pos[((long long)b * N + n) * 2 + half];
+  const float inv_freq = exp2f(-log2_base * (float)j / (float)Q);
+  float sn, cs;
+  sincosf((float)pp * inv_freq * fwd, &sn, &cs);
+  bf16* base = t + (long long)b * s_b + (long long)n * s_n + (long long)h * s_h + half * (D / 2);
+  const float u = __bfloat162float(base[j]);
+  const float v = __bfloat162float(base[j + Q]);
+  base[j] = __float2bfloat16(u * cs - v * sn);
+  base[j + Q] = __float2bfloat16(v * cs + u * sn);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void add_bcast_kernel(const bf16* __restrict__ a, long long lda, const bf16* __restrict__ b,
+                                 long long ldb, int b_rows, bf16* __restrict__ out, long long ldo, int rows,
+                                 int cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cv = cols >> 1;
+  if (idx >= (long long)rows * cv) return;
+  const int c = (idx % cv) * 2;
+  const int r = idx / cv;
+  const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + (long long)r * lda + c));
+  const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + (long long)(r % b_rows) * ldb + c));
+  *reinterpret_cast<__nv_bfloat162*>(out + (long long)r * ldo + c) = __floats2bfloat162_rn(x.x + y.x, x.y + y.y);
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                     int rows, int cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cols) return;
+  const int c = idx % cols;
+  const int r = idx / cols;
+  y[(long long)r * ldy + c] = __float2bfloat16(x[(long long)r * ldx + c]);
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ y, long long ldy,
+                                     int rows, int cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cols) return;
+  const int c = idx % cols;
+  const int r = idx / cols;
+  y[(long long)r * ldy + c] = __bfloat162float(x[(long long)r * ldx + c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Patchify: out[(b, y, x), c*P*P + i*P + j] = img[b, c, y*P + i, x*P + j]
+// ------------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const float* __restrict__ img, int B, int H, int W, int P, bf16* __restrict__ out,
+                                long long ldo) {
+  const int gh = H / P, gw = W / P;
+  const int kdim = 3 * P * P;
+  const long long total = (long long)B * gh * gw * ldo;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int col = idx % ldo;
+  const long long t = idx / ldo;
+  float v = 0.0f;
+  if (col < kdim) {
+    const int j = col % P;
+    const int i = (col / P) % P;
+    const int c = col / (P * P);
+    const int x = t % gw;
+    const int y = (t / gw) % gh;
+    const int b = t / ((long long)gw * gh);
+    v = img[(((long long)b * 3 + c) * H + (y * P + i)) * W + (x * P + j)];
+  }
+  out[idx] = __float2bfloat16(v);
+}
+
+// DINOv2: [-1,1] -> [0,1] -> ImageNet normalise -> bilinear (align_corners=False) to (Ho, Wo) -> im2col(P)
+__global__ void dino_preprocess_patchify_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int Wo,
+                                                int P, bf16* __restrict__ out, long long ldo) {
+  const int gh = Ho / P, gw = Wo / P;
+  const int kdim = 3 * P * P;
+  const long long total = (long long)B * gh * gw * ldo;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int col = idx % ldo;
+  const long long t = idx / ldo;
+  float v = 0.0f;
+  if (col < kdim) {
+    const int j = col % P;
+    const int i = (col / P) % P;
+    const int c = col / (P * P);
+    const int x = t % gw;
+    const int y = (t / gw) % gh;
+    const int b = t / ((long long)gw * gh);
+    const int oy = y * P + i, ox = x * P + j;
+    const float sy = fmaxf(((float)oy + 0.5f) * ((float)H / (float)Ho) - 0.5f, 0.0f);
+    const float sx = fmaxf(((float)ox + 0.5f) * ((float)W / (float)Wo) - 0.5f, 0.0f);
+    const int y0 = min((int)sy, H - 1), x0 = min((int)sx, W - 1);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    const float* pc = img + ((long long)b * 3 + c) * H * W;
+    const float v00 = pc[(long long)y0 * W + x0], v01 = pc[(long long)y0 * W + x1];
+    const float v10 = pc[(long long)y1 * W + x0], v11 = pc[(long long)y1 * W + x1];
+    const float raw = (1.0f - ly) * ((1.0f - lx) * v00 + lx * v01) + ly * ((1.0f - lx) * v10 + lx * v11);
+    const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+    const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+    v = ((raw * 0.5f + 0.5f) - mean) / stdv;
+  }
+  out[idx] = __float2bfloat16(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// centre 2x2 mean of every 8x8 cell (pixel-major feature map)
+// ------------------------------------------------------------------------------------------------
+__global__ void center_pool8_kernel(const bf16* __restrict__ f, int B, int Hm, int Wm, int C, bf16* __restrict__ out) {
+  const int gh = Hm / 8, gw = Wm / 8;
+  const int cv = C >> 1;
+  const long long total = (long long)B * gh * gw * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (idx % cv) * 2;
+  long long t = idx / cv;
+  const int X = t % gw; t /= gw;
+  const int Y = t % gh;
+  const int b = t / gh;
+  const bf16* base = f + (long long)b * Hm * Wm * C;
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const long long pix = (long long)(8 * Y + 3 + dy) * Wm + (8 * X + 3 + dx);
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + pix * C + c));
+      acc.x += v.x; acc.y += v.y;
+    }
+  *reinterpret_cast<__nv_bfloat162*>(out + (((long long)b * gh + Y) * gw + X) * C + c) =
+      __floats2bfloat162_rn(acc.x * 0.25f, acc.y * 0.25f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask bits: one block per query row
+// ------------------------------------------------------------------------------------------------
+__global__ void attn_mask_bits_kernel(const float* __restrict__ logits_t, long long ld, int Nk, uint32_t* __restrict__ bits,
+                                      int words_per_row) {
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float* row = logits_t + (long long)q * ld;
+  uint32_t* brow = bits + (long long)q * words_per_row;
+  int blocked = 0;
+  for (int w = warp; w < words_per_row; w += nwarps) {
+    const int k = w * 32 + lane;
+    const bool blk = (k < Nk) && (row[k] < 0.0f);
+    const uint32_t word = __ballot_sync(0xffffffffu, blk);
+    if (lane == 0) brow[w] = word;
+    blocked += __popc(word);
+  }
+  __shared__ int s_cnt[32];
+  if (lane == 0) s_cnt[warp] = blocked;
+  __syncthreads();
+  int tot = 0;
+  for (int i = 0; i < nwarps; ++i) tot += s_cnt[i];
+  if (tot == Nk) {  // every key blocked -> attend everywhere (mask_transformer.py:172)
+    for (int w = threadIdx.x; w < words_per_row; w += blockDim.x) brow[w] = 0u;
+  }
+}
+
+__global__ void l2norm_rows_kernel(const float* __restrict__ x, long long ldx, void* __restrict__ y, int y_f32,
+                                   long long ldy, int rows, int cols, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float ss = 0.0f;
+  for (int i = lane; i < cols; i += 32) {
+    const float v = x[(long long)row * ldx + i];
+    ss += v * v;
+  }
+  const float inv = 1.0f / (sqrtf(warp_sum(ss)) + eps);
+  for (int i = lane; i < cols; i += 32) {
+    const float v = x[(long long)row * ldx + i] * inv;
+    if (y_f32)
+      reinterpret_cast<float*>(y)[(long long)row * ldy + i] = v;
+    else
+      reinterpret_cast<bf16*>(y)[(long long)row * ldy + i] = __float2bfloat16(v);
+  }
+}
+
+// bf16 [B, HW, C] -> fp32 [B, C, HW]
+__global__ void nhwc_to_nchw_f32_kernel(const bf16* __restrict__ x, int HW, int C, float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const bf16* xb = x + (long long)b * HW * C;
+  float* yb = y + (long long)b * HW * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? __bfloat162float(xb[(long long)p * C + c]) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (p < HW && c < C) yb[(long long)c * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+static inline unsigned blocks_for(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+}  // namespace pst3r
+
+using namespace pst3r;
+
+extern "C" const char* pst3r_last_error(void) { return get_last_error(); }
+extern "C" int pst3r_version(void) { return 1; }
+extern "C" int pst3r_check_device(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_last_error("no CUDA device");
+    return PST3R_ERR_NODEVICE;
+  }
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+    set_last_error("cudaGetDeviceProperties failed");
+    return PST3R_ERR_NODEVICE;
+  }
+  if (p.major != 10) {
+    set_last_error("device %s is sm_%d%d; this library contains sm_100a code only", p.name, p.major, p.minor);
+    return PST3R_ERR_NODEVICE;
+  }
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const void* add, int64_t ld_add,
+                               const float* gamma, const float* beta, float eps, void* y, int32_t y_f32, int64_t ldy,
+                               void* sum_out, int64_t ld_sum, int32_t rows, int32_t dim, pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(x && gamma && beta && y && rows > 0 && dim > 0, "layernorm: bad args");
+  const int wpb = 8;
+  const unsigned grid = blocks_for(rows, wpb);
+  const bf16* a = reinterpret_cast<const bf16*>(add);
+  bf16* so = reinterpret_cast<bf16*>(sum_out);
+  if (x_f32 && y_f32)
+    layernorm_kernel<true, true><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim);
+  else if (x_f32)
+    layernorm_kernel<true, false><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim);
+  else if (y_f32)
+    layernorm_kernel<false, true><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim);
+  else
+    layernorm_kernel<false, false><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_rope2d(void* tokens, int64_t s_b, int64_t s_n, int64_t s_h, const int32_t* pos, int32_t B,
+                            int32_t N, int32_t H, int32_t D, float base, float fwd, pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(tokens && pos && B > 0 && N > 0 && H > 0 && D > 0 && (D % 4) == 0, "rope2d: bad args (D %% 4 != 0?)");
+  const long long total = (long long)B * N * H * (D / 2);
+  rope2d_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<bf16*>(tokens), s_b, s_n, s_h, pos, B, N, H, D,
+                                                       log2f(base), fwd);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_add_bcast(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_rows, void* out,
+                               int64_t ldo, int32_t rows, int32_t cols, pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(a && b && out && rows > 0 && cols > 0 && (cols % 2) == 0 && b_rows > 0 && (lda % 2) == 0 &&
+                      (ldb % 2) == 0 && (ldo % 2) == 0,
+                  "add_bcast: bad args");
+  add_bcast_kernel<<<blocks_for((long long)rows * (cols / 2), 256), 256, 0, s>>>(
+      reinterpret_cast<const bf16*>(a), lda, reinterpret_cast<const bf16*>(b), ldb, b_rows, reinterpret_cast<bf16*>(out),
+      ldo, rows, cols);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_cast_f32_to_bf16(const float* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols,
+                                      pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(x && y && rows > 0 && cols > 0, "cast: bad args");
+  cast_f32_bf16_kernel<<<blocks_for((long long)rows * cols, 256), 256, 0, s>>>(x, ldx, reinterpret_cast<bf16*>(y), ldy, rows, cols);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+extern "C" int pst3r_cast_bf16_to_f32(const void* x, int64_t ldx, float* y, int64_t ldy, int32_t rows, int32_t cols,
+                                      pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(x && y && rows > 0 && cols > 0, "cast: bad args");
+  cast_bf16_f32_kernel<<<blocks_for((long long)rows * cols, 256), 256, 0, s>>>(reinterpret_cast<const bf16*>(x), ldx, y, ldy, rows, cols);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_patchify(const float* img, int32_t B, int32_t H, int32_t W, int32_t P, void* out, int64_t ldo,
+                              pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(img && out && B > 0 && P > 0 && (H % P) == 0 && (W % P) == 0 && ldo >= 3 * P * P, "patchify: bad args");
+  const long long total = (long long)B * (H / P) * (W / P) * ldo;
+  patchify_kernel<<<blocks_for(total, 256), 256, 0, s>>>(img, B, H, W, P, reinterpret_cast<bf16*>(out), ldo);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_dino_preprocess_patchify(const float* img, int32_t B, int32_t H, int32_t W, int32_t Ho, int32_t Wo,
+                                              int32_t P, void* out, int64_t ldo, pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(img && out && B > 0 && P > 0 && (Ho % P) == 0 && (Wo % P) == 0 && ldo >= 3 * P * P,
+                  "dino_preprocess_patchify: bad args");
+  const long long total = (long long)B * (Ho / P) * (Wo / P) * ldo;
+  dino_preprocess_patchify_kernel<<<blocks_for(total, 256), 256, 0, s>>>(img, B, H, W, Ho, Wo, P,
+                                                                        reinterpret_cast<bf16*>(out), ldo);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_center_pool8(const void* feats, int32_t B, int32_t Hm, int32_t Wm, int32_t C, void* out,
+                                  pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(feats && out && B > 0 && (Hm % 8) == 0 && (Wm % 8) == 0 && (C % 2) == 0, "center_pool8: bad args");
+  const long long total = (long long)B * (Hm / 8) * (Wm / 8) * (C / 2);
+  center_pool8_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const bf16*>(feats), B, Hm, Wm, C,
+                                                            reinterpret_cast<bf16*>(out));
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_attn_mask_bits(const float* logits_t, int64_t ld, int32_t Q, int32_t Nk, uint32_t* bits,
+                                    pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(logits_t && bits && Q > 0 && Nk > 0 && ld >= Nk, "attn_mask_bits: bad args");
+  const int words = ((Nk + 127) / 128) * 4;
+  attn_mask_bits_kernel<<<Q, 256, 0, s>>>(logits_t, ld, Nk, bits, words);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_l2norm_rows(const float* x, int64_t ldx, void* y, int32_t y_f32, int64_t ldy, int32_t rows,
+                                 int32_t cols, float eps, pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(x && y && rows > 0 && cols > 0, "l2norm_rows: bad args");
+  l2norm_rows_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(x, ldx, y, y_f32, ldy, rows, cols, eps);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_nhwc_to_nchw_f32(const void* x, int32_t B, int32_t HW, int32_t C, float* y, pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(x && y && B > 0 && HW > 0 && C > 0, "nhwc_to_nchw_f32: bad args");
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  nhwc_to_nchw_f32_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const bf16*>(x), HW, C, y);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}

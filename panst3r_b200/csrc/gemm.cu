@@ -1,0 +1,441 @@
+// tcgen05 / TMA bf16 GEMM with fused epilogues:  C[M,N] = epi(A[M,K] * B[N,K]^T)
+//
+// Replaces every nn.Linear-shaped contraction on the PanSt3R forward path (QKV / proj / MLP of the
+// encoder, decoder, DINOv2, InputMixer; the v1 PixelShuffle MLP chain; the mask-logit einsum; the
+// pointmap head).  Fused epilogues: bias, GELU/ReLU, LayerScale, residual add, 2-D RoPE on q/k columns,
+// pixel_shuffle(2) store, 16x16 depth-to-space store, transposed (plane-major) fp32 store.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      : TMA producer   (A 128x64 + B BNx64 bf16 tiles, SWIZZLE_128B, STAGES-deep mbarrier ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x n x 16, fp32 accum in TMEM)
+//   warps 2..5  : epilogue (tcgen05.ld 32 lanes x 32 cols -> registers -> math -> global)
+//   TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the mainloop of tile i+1.
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/panst3r_b200.h"
+
+namespace pst3r {
+
+struct GemmEpi {
+  void* out;
+  long long ldo;
+  int out_f32;
+  int act;
+  const float* bias;
+  const float* col_scale;
+  const bf16* residual;
+  long long ldr;
+  float alpha;
+  int store_mode;
+  long long rows_per_batch, batch_stride, ldt;
+  int grid_h, grid_w;
+  int d2s_patch, d2s_ch;
+  const float2* rope_cs;
+  const int* rope_pos;
+  int rope_cols;
+  int rope_maxpos;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr uint32_t TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr uint32_t DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
+};
+
+// ---- epilogue for one 32-column chunk owned by one thread (one output row) --------------------
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32], int row, int col0, int M, int N) {
+  if (row >= M || col0 >= N) return;
+  const int ncols = min(32, N - col0);
+  const bool full = (ncols == 32);
+
+  if (ep.alpha != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= ep.alpha;
+  }
+  if (ep.bias) {
+    if (full) {
+      const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 b = __ldg(b4 + i);
+        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < ncols) v[i] += __ldg(ep.bias + col0 + i);
+    }
+  }
+  if (ep.rope_cs && col0 < ep.rope_cols) {
+    // chunk == one 32-wide half of a 64-wide head: even chunk rotates by y, odd chunk by x
+    const int half = (col0 >> 5) & 1;
+    int p = __ldg(ep.rope_pos + 2 * (long long)row + half);
+    p = max(0, min(p, ep.rope_maxpos - 1));
+    const float2* cs = ep.rope_cs + (long long)p * 16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 c = __ldg(cs + j);
+      const float a = v[j], b = v[j + 16];
+      v[j] = a * c.x - b * c.y;
+      v[j + 16] = b * c.x + a * c.y;
+    }
+  }
+  if (ep.act == PST3R_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  } else if (ep.act == PST3R_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+  }
+  if (ep.col_scale) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols) v[i] *= __ldg(ep.col_scale + col0 + i);
+  }
+  if (ep.residual) {
+    const bf16* r = ep.residual + (long long)row * ep.ldr + col0;
+    if (full && ((ep.ldr & 7) == 0)) {
+      const uint4* r4 = reinterpret_cast<const uint4*>(r);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = __ldg(r4 + i);
+        float2 f;
+        f = unpack_bf16x2(u.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+        f = unpack_bf16x2(u.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+        f = unpack_bf16x2(u.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+        f = unpack_bf16x2(u.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < ncols) v[i] += __bfloat162float(r[i]);
+    }
+  }
+
+  switch (ep.store_mode) {
+    case PST3R_STORE_PLAIN: {
+      if (ep.out_f32) {
+        float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + col0;
+        if (full && ((ep.ldo & 3) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) o[i] = v[i];
+        }
+      } else {
+        bf16* o = reinterpret_cast<bf16*>(ep.out) + (long long)row * ep.ldo + col0;
+        if (full && ((ep.ldo & 7) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+            u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            reinterpret_cast<uint4*>(o)[i] = u;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) o[i] = __float2bfloat16(v[i]);
+        }
+      }
+    } break;
+    case PST3R_STORE_TRANSPOSED: {
+      // lanes of a warp hold consecutive rows -> each per-column store is a coalesced 128 B line
+      const long long b = row / ep.rows_per_batch;
+      const long long r = row - b * ep.rows_per_batch;
+      if (ep.out_f32) {
+        float* o = reinterpret_cast<float*>(ep.out) + b * ep.batch_stride + (long long)col0 * ep.ldt + r;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) o[(long long)i * ep.ldt] = v[i];
+      } else {
+        bf16* o = reinterpret_cast<bf16*>(ep.out) + b * ep.batch_stride + (long long)col0 * ep.ldt + r;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) o[(long long)i * ep.ldt] = __float2bfloat16(v[i]);
+      }
+    } break;
+    case PST3R_STORE_PIXSHUF2: {
+      // F.pixel_shuffle(., 2): out[b, c, 2y+i, 2x+j] = in[b, 4c+2i+j, y, x]; we keep pixel-major (NHWC) output.
+      const int gw = ep.grid_w, gh = ep.grid_h;
+      const int x = row % gw;
+      const int t = row / gw;
+      const int y = t % gh;
+      const int b = t / gh;
+      const int c0 = col0 >> 2;  // 8 output channels per 32-column chunk
+      bf16* base = reinterpret_cast<bf16*>(ep.out);
+#pragma unroll
+      for (int ij = 0; ij < 4; ++ij) {
+        const int i = ij >> 1, j = ij & 1;
+        const long long orow = ((long long)(b * 2 * gh + 2 * y + i)) * (2 * gw) + 2 * x + j;
+        bf16* o = base + orow * ep.ldo + c0;
+        if (full && ((ep.ldo & 7) == 0)) {
+          uint4 u;
+          u.x = pack_bf16x2(v[0 * 4 + ij], v[1 * 4 + ij]);
+          u.y = pack_bf16x2(v[2 * 4 + ij], v[3 * 4 + ij]);
+          u.z = pack_bf16x2(v[4 * 4 + ij], v[5 * 4 + ij]);
+          u.w = pack_bf16x2(v[6 * 4 + ij], v[7 * 4 + ij]);
+          *reinterpret_cast<uint4*>(o) = u;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (4 * c + ij < ncols) o[c] = __float2bfloat16(v[4 * c + ij]);
+        }
+      }
+    } break;
+    case PST3R_STORE_D2S: {
+      // Pointmap head: weight rows were permuted on the host so that col = (i*P + j)*C + c; the output
+      // pixel (y*P+i, x*P+j) then receives C contiguous floats and a whole patch row i is one contiguous run.
+      const int gw = ep.grid_w, gh = ep.grid_h, P = ep.d2s_patch, C = ep.d2s_ch;
+      const int x = row % gw;
+      const int t = row / gw;
+      const int y = t % gh;
+      const int b = t / gh;
+      const int run = P * C;
+      float* base = reinterpret_cast<float*>(ep.out);
+      const long long Wfull = (long long)gw * P;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        if (k < ncols) {
+          const int col = col0 + k;
+          const int i = col / run;
+          const int rem = col - i * run;
+          const long long o = (((long long)(b * gh + y) * P + i) * Wfull + (long long)x * P) * C + rem;
+          base[o] = v[k];
+        }
+      }
+    } break;
+    default: break;
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmEpi ep, const int M, const int N, const int K) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m_blocks = (M + GEMM_BM - 1) / GEMM_BM;
+  const int num_n_blocks = (N + BN - 1) / BN;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m_blocks;
+        const int n_blk = tile / num_m_blocks;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          uint8_t* a_dst = smem + s * L::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + L::A_BYTES;
+          tma_load_2d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int n_blk = tile / num_m_blocks;
+        const int n_rem = N - n_blk * BN;
+        const int n_mma = n_rem >= BN ? BN : ((n_rem + 15) & ~15);
+        const uint32_t idesc = make_idesc_bf16(GEMM_BM, n_mma, 0, 0);
+        const int acc = local & 1;
+        const uint32_t acc_ph = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + L::A_BYTES;
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr, 0, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(b_addr, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // +32 B per UMMA_K step inside the 128 B swizzle span (address field is in 16 B units)
+            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ------------------------------- epilogue -----------------------------------
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int m_blk = tile % num_m_blocks;
+      const int n_blk = tile / num_m_blocks;
+      const int acc = local & 1;
+      const uint32_t acc_ph = (local >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BM + quad * 32 + lane;
+      const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      const int n_rem = N - n_blk * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c * 32 >= n_rem) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(t_base + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        epilogue_chunk(ep, v, row, n_blk * BN + c * 32, M, N);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& ep, int M, int N, int K,
+                       cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  auto kern = gemm_bf16_tn_kernel<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    PST3R_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    configured = true;
+  }
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+}  // namespace pst3r
+
+using namespace pst3r;
+
+extern "C" int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N,
+                               int32_t K, const pst3r_gemm_epilogue* e, pst3r_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PST3R_CHECK_ARG(A && B && e && e->out, "gemm: null pointer");
+  PST3R_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  PST3R_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 (lda=%lld ldb=%lld)",
+                  (long long)lda, (long long)ldb);
+  PST3R_CHECK_ARG(lda >= K && ldb >= K, "gemm: lda/ldb smaller than K");
+  if (e->store_mode == PST3R_STORE_TRANSPOSED)
+    PST3R_CHECK_ARG(e->rows_per_batch > 0 && e->ldt > 0, "gemm: TRANSPOSED store needs rows_per_batch/ldt");
+  if (e->store_mode == PST3R_STORE_PIXSHUF2)
+    PST3R_CHECK_ARG(e->grid_h > 0 && e->grid_w > 0 && (N % 4) == 0 && !e->out_f32 && (M % (e->grid_h * e->grid_w)) == 0,
+                    "gemm: PIXSHUF2 store needs grid, N%%4==0, bf16 out");
+  if (e->store_mode == PST3R_STORE_D2S)
+    PST3R_CHECK_ARG(e->grid_h > 0 && e->grid_w > 0 && e->d2s_patch > 0 && e->d2s_ch > 0 && e->out_f32 &&
+                        N == e->d2s_patch * e->d2s_patch * e->d2s_ch && (M % (e->grid_h * e->grid_w)) == 0,
+                    "gemm: D2S store needs grid/patch/channels, N == P*P*C, fp32 out");
+  if (e->rope_cs)
+    PST3R_CHECK_ARG(e->rope_pos && e->rope_cols > 0 && (e->rope_cols % 64) == 0 && e->rope_maxpos > 0,
+                    "gemm: rope epilogue needs pos, rope_cols %% 64 == 0, maxpos");
+
+  GemmEpi ep;
+  ep.out = e->out; ep.ldo = e->ldo; ep.out_f32 = e->out_f32; ep.act = e->act;
+  ep.bias = e->bias; ep.col_scale = e->col_scale;
+  ep.residual = reinterpret_cast<const bf16*>(e->residual); ep.ldr = e->ldr;
+  ep.alpha = e->alpha; ep.store_mode = e->store_mode;
+  ep.rows_per_batch = e->rows_per_batch; ep.batch_stride = e->batch_stride; ep.ldt = e->ldt;
+  ep.grid_h = e->grid_h; ep.grid_w = e->grid_w; ep.d2s_patch = e->d2s_patch; ep.d2s_ch = e->d2s_ch;
+  ep.rope_cs = reinterpret_cast<const float2*>(e->rope_cs); ep.rope_pos = e->rope_pos;
+  ep.rope_cols = e->rope_cols; ep.rope_maxpos = e->rope_maxpos;
+
+  // Tile-width heuristic: the widest BN whose tile count still fills the machine.
+  const int sms = num_sms();
+  const int mb = (M + GEMM_BM - 1) / GEMM_BM;
+  int BN = 256;
+  if (mb * ((N + 255) / 256) < sms || N <= 128) BN = 128;
+  if (BN == 128 && (mb * ((N + 127) / 128) < sms || N <= 64)) BN = 64;
+  if (N > 128 && N <= 256 && mb >= sms) BN = 256;  // e.g. mask einsum: N = 200, huge M
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[2] = {2, (uint64_t)lda * 2};
+    uint32_t box[2] = {GEMM_BK, GEMM_BM};
+    int r = encode_tmap(&tmA, A, 2, 2, dims, str, box);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[2] = {2, (uint64_t)ldb * 2};
+    uint32_t box[2] = {GEMM_BK, (uint32_t)BN};
+    int r = encode_tmap(&tmB, B, 2, 2, dims, str, box);
+    if (r) return r;
+  }
+  switch (BN) {
+    case 256: return launch_gemm<256, 4>(tmA, tmB, ep, M, N, K, stream);
+    case 128: return launch_gemm<128, 6>(tmA, tmB, ep, M, N, K, stream);
+    default: return launch_gemm<64, 8>(tmA, tmB, ep, M, N, K, stream);
+  }
+}

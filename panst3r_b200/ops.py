@@ -1,0 +1,338 @@
+"""Thin PyTorch-facing wrappers over the C ABI (include/panst3r_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every wrapper passes raw pointers,
+strides and the current CUDA stream to libpanst3r_b200.so.  No wrapper computes anything in torch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib as _l
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+STORE_PLAIN, STORE_TRANSPOSED, STORE_PIXSHUF2, STORE_D2S = 0, 1, 2, 3
+
+# launch counter (bench.py reports gpu_launches from this)
+launches = 0
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _l.Pst3rError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise _l.Pst3rError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def _rows2d(t: torch.Tensor, name: str) -> Tuple[int, int, int]:
+    """(rows, cols, ld) of a tensor viewed as a row-strided 2-D matrix with contiguous columns."""
+    if t.dim() < 2:
+        raise _l.Pst3rError(f"{name}: need >=2 dims")
+    if t.stride(-1) != 1:
+        raise _l.Pst3rError(f"{name}: last dim must be contiguous")
+    if t.dim() > 2:
+        # leading dims must collapse onto a single row stride
+        ld = t.stride(-2)
+        exp = ld * t.shape[-2]
+        for d in range(t.dim() - 3, -1, -1):
+            if t.shape[d] != 1 and t.stride(d) != exp:
+                raise _l.Pst3rError(f"{name}: leading dims are not collapsible (shape {tuple(t.shape)}, strides {t.stride()})")
+            exp *= t.shape[d]
+        rows = 1
+        for d in t.shape[:-1]:
+            rows *= d
+        return rows, t.shape[-1], ld
+    return t.shape[0], t.shape[1], t.stride(0)
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         col_scale: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, alpha: float = 1.0,
+         out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+         store_mode: int = STORE_PLAIN, rows_per_batch: int = 0, batch_stride: int = 0, ldt: int = 0,
+         grid: Tuple[int, int] = (0, 0), d2s: Tuple[int, int] = (0, 0),
+         rope: Optional[Tuple[torch.Tensor, torch.Tensor, int]] = None) -> torch.Tensor:
+    """out = epilogue(a @ w.T).  a: bf16 [..., K] (row-strided), w: bf16 [N, K]."""
+    global launches
+    lib = _l.load()
+    _need(a, torch.bfloat16, "gemm.a")
+    _need(w, torch.bfloat16, "gemm.w")
+    M, K, lda = _rows2d(a, "gemm.a")
+    N, K2, ldb = _rows2d(w, "gemm.w")
+    if K != K2:
+        raise _l.Pst3rError(f"gemm: K mismatch {K} vs {K2}")
+    e = _l.GemmEpilogue()
+    if store_mode == STORE_PLAIN:
+        if out is None:
+            out = torch.empty((*a.shape[:-1], N), device=a.device, dtype=out_dtype)
+        _, oc, ldo = _rows2d(out, "gemm.out")
+        if oc != N:
+            raise _l.Pst3rError("gemm: out has wrong number of columns")
+        e.ldo = ldo
+    else:
+        if out is None:
+            raise _l.Pst3rError("gemm: out must be given for non-plain store modes")
+        e.ldo = out.stride(-2) if out.dim() >= 2 else 0
+    e.out = out.data_ptr()
+    e.out_f32 = 1 if out.dtype == torch.float32 else 0
+    if out.dtype not in (torch.float32, torch.bfloat16):
+        raise _l.Pst3rError("gemm: out must be bf16 or fp32")
+    e.act = act
+    if bias is not None:
+        _need(bias, torch.float32, "gemm.bias")
+    if col_scale is not None:
+        _need(col_scale, torch.float32, "gemm.col_scale")
+    e.bias = _ptr(bias)
+    e.col_scale = _ptr(col_scale)
+    if residual is not None:
+        _need(residual, torch.bfloat16, "gemm.residual")
+        _, _, ldr = _rows2d(residual, "gemm.residual")
+        e.residual = residual.data_ptr()
+        e.ldr = ldr
+    e.alpha = alpha
+    e.store_mode = store_mode
+    e.rows_per_batch, e.batch_stride, e.ldt = rows_per_batch, batch_stride, ldt
+    e.grid_h, e.grid_w = grid
+    e.d2s_patch, e.d2s_ch = d2s
+    if rope is not None:
+        cs, pos, rope_cols = rope
+        _need(cs, torch.float32, "gemm.rope_cs")
+        _need(pos, torch.int32, "gemm.rope_pos")
+        e.rope_cs, e.rope_pos, e.rope_cols, e.rope_maxpos = cs.data_ptr(), pos.data_ptr(), rope_cols, cs.shape[0]
+    _l.check(lib.pst3r_gemm_bf16(a.data_ptr(), lda, w.data_ptr(), ldb, M, N, K, C.byref(e), _stream()), "pst3r_gemm_bf16")
+    launches += 1
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = t
+    return t
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None,
+              mask_bits: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              kv_splits: int = 0) -> torch.Tensor:
+    """q: bf16 [B, Nq, H, hd]; k, v: bf16 [B or 1, Nk, H, hd] (any strides, hd contiguous).
+    mask_bits: int32/uint32 [B or 1, Nq, W] words, bit set = key blocked.  Returns bf16 [B, Nq, H*hd]."""
+    global launches
+    lib = _l.load()
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _need(t, torch.bfloat16, f"attention.{n}")
+        if t.dim() != 4 or t.stride(-1) != 1:
+            raise _l.Pst3rError(f"attention.{n}: expected [B, N, H, hd] with contiguous hd")
+    B, Nq, H, hd = q.shape
+    Bk, Nk, Hk, hdk = k.shape
+    if (Hk, hdk) != (H, hd) or v.shape != k.shape or Bk not in (1, B):
+        raise _l.Pst3rError("attention: shape mismatch")
+    if out is None:
+        out = torch.empty((B, Nq, H * hd), device=q.device, dtype=torch.bfloat16)
+    a = _l.AttnArgs()
+    a.q, a.q_sb, a.q_sn, a.q_sh = q.data_ptr(), q.stride(0), q.stride(1), q.stride(2)
+    shared = (Bk == 1 and B > 1) or k.stride(0) == 0
+    a.k, a.k_sb, a.k_sn, a.k_sh = k.data_ptr(), (0 if shared else k.stride(0)), k.stride(1), k.stride(2)
+    a.v, a.v_sb, a.v_sn, a.v_sh = v.data_ptr(), (0 if shared else v.stride(0)), v.stride(1), v.stride(2)
+    if B == 1:  # batch stride is irrelevant; keep it non-zero so that K/V are not flagged shared
+        a.k_sb = a.k_sb or Nk * k.stride(1)
+        a.v_sb = a.v_sb or Nk * v.stride(1)
+    a.o, a.o_sb, a.o_sn = out.data_ptr(), out.stride(0), out.stride(1)
+    a.B, a.H, a.Nq, a.Nk, a.head_dim = B, H, Nq, Nk, hd
+    a.scale = float(scale if scale is not None else hd ** -0.5)
+    if mask_bits is not None:
+        if mask_bits.dtype not in (torch.int32, torch.uint32) or mask_bits.dim() != 3 or mask_bits.stride(-1) != 1:
+            raise _l.Pst3rError("attention.mask_bits: expected int32 [B or 1, Nq, W]")
+        a.mask_bits = mask_bits.data_ptr()
+        a.mask_sb = 0 if mask_bits.shape[0] == 1 else mask_bits.stride(0)
+        a.mask_sq = mask_bits.stride(1)
+    splits = kv_splits if kv_splits > 0 else lib.pst3r_attention_auto_splits(B, H, Nq, Nk)
+    a.kv_splits = splits
+    need = lib.pst3r_attention_workspace_bytes(B, H, Nq, hd, splits)
+    if need > 0:
+        ws = _workspace(need, q.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    _l.check(lib.pst3r_attention(C.byref(a), _stream()), "pst3r_attention")
+    launches += 1 if splits <= 1 else 2
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
+              add: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              out_dtype: torch.dtype = torch.bfloat16, sum_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global launches
+    lib = _l.load()
+    if x.dtype not in (torch.bfloat16, torch.float32) or not x.is_cuda:
+        raise _l.Pst3rError("layernorm.x: expected CUDA bf16/fp32")
+    rows, dim, ldx = _rows2d(x, "layernorm.x")
+    _need(gamma, torch.float32, "layernorm.gamma")
+    _need(beta, torch.float32, "layernorm.beta")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    _, _, ldy = _rows2d(out, "layernorm.out")
+    ld_add = 0
+    if add is not None:
+        _need(add, torch.bfloat16, "layernorm.add")
+        _, _, ld_add = _rows2d(add, "layernorm.add")
+    ld_sum = 0
+    if sum_out is not None:
+        _need(sum_out, torch.bfloat16, "layernorm.sum_out")
+        _, _, ld_sum = _rows2d(sum_out, "layernorm.sum_out")
+    _l.check(lib.pst3r_layernorm(x.data_ptr(), int(x.dtype == torch.float32), ldx, _ptr(add), ld_add, gamma.data_ptr(),
+                                 beta.data_ptr(), eps, out.data_ptr(), int(out.dtype == torch.float32), ldy,
+                                 _ptr(sum_out), ld_sum, rows, dim, _stream()), "pst3r_layernorm")
+    launches += 1
+    return out
+
+
+def rope2d_(tokens: torch.Tensor, pos: torch.Tensor, base: float = 100.0, fwd: float = 1.0) -> torch.Tensor:
+    """In-place 2-D RoPE on bf16 tokens [B, N, H, D] (D contiguous) with int32 positions [B, N, 2]."""
+    global launches
+    lib = _l.load()
+    _need(tokens, torch.bfloat16, "rope2d.tokens")
+    _need(pos, torch.int32, "rope2d.pos")
+    B, N, H, D = tokens.shape
+    if tokens.stride(-1) != 1 or not pos.is_contiguous():
+        raise _l.Pst3rError("rope2d: bad strides")
+    _l.check(lib.pst3r_rope2d(tokens.data_ptr(), tokens.stride(0), tokens.stride(1), tokens.stride(2), pos.data_ptr(),
+                              B, N, H, D, base, fwd, _stream()), "pst3r_rope2d")
+    launches += 1
+    return tokens
+
+
+def add_bcast(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = a[r] + b[r % b_rows] on bf16 row matrices."""
+    global launches
+    lib = _l.load()
+    _need(a, torch.bfloat16, "add_bcast.a")
+    _need(b, torch.bfloat16, "add_bcast.b")
+    rows, cols, lda = _rows2d(a, "add_bcast.a")
+    brows, bcols, ldb = _rows2d(b, "add_bcast.b")
+    if bcols != cols:
+        raise _l.Pst3rError("add_bcast: column mismatch")
+    if out is None:
+        out = torch.empty(a.shape, device=a.device, dtype=torch.bfloat16)
+    _, _, ldo = _rows2d(out, "add_bcast.out")
+    _l.check(lib.pst3r_add_bcast(a.data_ptr(), lda, b.data_ptr(), ldb, brows, out.data_ptr(), ldo, rows, cols, _stream()),
+             "pst3r_add_bcast")
+    launches += 1
+    return out
+
+
+def to_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global launches
+    lib = _l.load()
+    _need(x, torch.float32, "to_bf16.x")
+    rows, cols, ldx = _rows2d(x, "to_bf16.x")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _, _, ldy = _rows2d(out, "to_bf16.out")
+    _l.check(lib.pst3r_cast_f32_to_bf16(x.data_ptr(), ldx, out.data_ptr(), ldy, rows, cols, _stream()), "cast")
+    launches += 1
+    return out
+
+
+def to_f32(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global launches
+    lib = _l.load()
+    _need(x, torch.bfloat16, "to_f32.x")
+    rows, cols, ldx = _rows2d(x, "to_f32.x")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _, _, ldy = _rows2d(out, "to_f32.out")
+    _l.check(lib.pst3r_cast_bf16_to_f32(x.data_ptr(), ldx, out.data_ptr(), ldy, rows, cols, _stream()), "cast")
+    launches += 1
+    return out
+
+
+def patchify(img: torch.Tensor, P: int, ld: Optional[int] = None) -> torch.Tensor:
+    """img fp32 [B,3,H,W] -> bf16 [B*(H/P)*(W/P), ld] (Conv2d weight flattening order)."""
+    global launches
+    lib = _l.load()
+    _need(img, torch.float32, "patchify.img")
+    img = img.contiguous()
+    B, _, H, W = img.shape
+    ld = ld or 3 * P * P
+    out = torch.empty((B * (H // P) * (W // P), ld), device=img.device, dtype=torch.bfloat16)
+    _l.check(lib.pst3r_patchify(img.data_ptr(), B, H, W, P, out.data_ptr(), ld, _stream()), "pst3r_patchify")
+    launches += 1
+    return out
+
+
+def dino_preprocess_patchify(img: torch.Tensor, Ho: int, Wo: int, P: int, ld: int) -> torch.Tensor:
+    global launches
+    lib = _l.load()
+    _need(img, torch.float32, "dino_preprocess.img")
+    img = img.contiguous()
+    B, _, H, W = img.shape
+    out = torch.empty((B * (Ho // P) * (Wo // P), ld), device=img.device, dtype=torch.bfloat16)
+    _l.check(lib.pst3r_dino_preprocess_patchify(img.data_ptr(), B, H, W, Ho, Wo, P, out.data_ptr(), ld, _stream()),
+             "pst3r_dino_preprocess_patchify")
+    launches += 1
+    return out
+
+
+def center_pool8(feats: torch.Tensor) -> torch.Tensor:
+    """feats bf16 [B, Hm, Wm, C] -> bf16 [B, Hm/8, Wm/8, C] (mean of the centre 2x2 of each 8x8 cell)."""
+    global launches
+    lib = _l.load()
+    _need(feats, torch.bfloat16, "center_pool8.feats")
+    feats = feats.contiguous()
+    B, Hm, Wm, Cc = feats.shape
+    out = torch.empty((B, Hm // 8, Wm // 8, Cc), device=feats.device, dtype=torch.bfloat16)
+    _l.check(lib.pst3r_center_pool8(feats.data_ptr(), B, Hm, Wm, Cc, out.data_ptr(), _stream()), "pst3r_center_pool8")
+    launches += 1
+    return out
+
+
+def attn_mask_bits(logits_t: torch.Tensor, Nk: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """logits_t fp32 [Q, >=Nk] -> int32 [1, Q, ceil(Nk/128)*4] block mask (bit set: logit < 0)."""
+    global launches
+    lib = _l.load()
+    _need(logits_t, torch.float32, "attn_mask_bits.logits")
+    Q, _, ld = _rows2d(logits_t, "attn_mask_bits.logits")
+    words = ((Nk + 127) // 128) * 4
+    if out is None:
+        out = torch.empty((1, Q, words), device=logits_t.device, dtype=torch.int32)
+    _l.check(lib.pst3r_attn_mask_bits(logits_t.data_ptr(), ld, Q, Nk, out.data_ptr(), _stream()), "pst3r_attn_mask_bits")
+    launches += 1
+    return out
+
+
+def l2norm_rows(x: torch.Tensor, eps: float, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    global launches
+    lib = _l.load()
+    _need(x, torch.float32, "l2norm_rows.x")
+    rows, cols, ldx = _rows2d(x, "l2norm_rows.x")
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    _, _, ldy = _rows2d(out, "l2norm_rows.out")
+    _l.check(lib.pst3r_l2norm_rows(x.data_ptr(), ldx, out.data_ptr(), int(out_dtype == torch.float32), ldy, rows, cols,
+                                   eps, _stream()), "pst3r_l2norm_rows")
+    launches += 1
+    return out
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
+    """bf16 [B, HW, C] -> fp32 [B, C, HW]"""
+    global launches
+    lib = _l.load()
+    _need(x, torch.bfloat16, "nhwc_to_nchw_f32.x")
+    x = x.contiguous()
+    B, HW, Cc = x.shape
+    out = torch.empty((B, Cc, HW), device=x.device, dtype=torch.float32)
+    _l.check(lib.pst3r_nhwc_to_nchw_f32(x.data_ptr(), B, HW, Cc, out.data_ptr(), _stream()), "pst3r_nhwc_to_nchw_f32")
+    launches += 1
+    return out
