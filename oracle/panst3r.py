@@ -1,0 +1,108 @@
+"""Oracle PanSt3R façade (TEST INFRASTRUCTURE ONLY): the reference's orchestration restated over oracle modules.
+
+Follows /root/reference/src/panst3r/panst3r.py:47-86 (forward_dino / forward_must3r_encoder /
+forward_must3r_decoder), :169-284 (forward_inference_multi_ar, single aspect ratio, linspace keyframes) and
+:286-296 (forward); engine/must3r.py:28-69 (memory build loop) and :71-94 (render, unsliced branch).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .must3r import Dust3rEncoder, MUSt3R
+from .panoptic import DinoV2Encoder, InputMixer, LoftUpUpscaler, PanopticDecoder, PixelShuffleUpscaler
+
+
+class PanSt3R(nn.Module):
+    def __init__(self, must3r_encoder, must3r_decoder, dino_encoder, panoptic_decoder):
+        super().__init__()
+        self.must3r_encoder = must3r_encoder
+        self.must3r_decoder = must3r_decoder
+        self.dino_encoder = dino_encoder
+        self.panoptic_decoder = panoptic_decoder
+        self.must3r_params = dict(init_num_views=2, batch_num_views=1, render_iterations=1)
+
+    def get_must3r_mem_batches(self, n_imgs):  # panst3r.py:65-70
+        mem_batches = [self.must3r_params["init_num_views"]]
+        while (s := sum(mem_batches)) != n_imgs:
+            mem_batches.append(min(self.must3r_params["batch_num_views"], n_imgs - s))
+        return mem_batches
+
+    def forward_dino(self, imgs, true_shape):
+        B, V = imgs.shape[:2]
+        return self.dino_encoder(imgs.flatten(0, 1), true_shape.flatten(0, 1)).unflatten(0, (B, V))
+
+    def forward_must3r_encoder(self, imgs, true_shape):
+        B, V = imgs.shape[:2]
+        x, pos = self.must3r_encoder(imgs.flatten(0, 1), true_shape.flatten(0, 1))
+        return x.unflatten(0, (B, V)), pos.unflatten(0, (B, V))
+
+    def build_memory(self, x, pos, true_shape):  # engine/must3r.py:28-69
+        edges = [0] + np.cumsum(self.get_must3r_mem_batches(x.shape[1])).tolist()
+        mem = None
+        for a, b in zip(edges[:-1], edges[1:]):
+            mem, _, _ = self.must3r_decoder(x[:, a:b].contiguous(), pos[:, a:b].contiguous(),
+                                            true_shape[:, a:b].contiguous(), mem, render=False, return_feats=True)
+        return mem
+
+    def render(self, x, pos, true_shape, mem):  # engine/must3r.py:71-94
+        _, pointmaps, feats = self.must3r_decoder(x, pos, true_shape, mem, render=True, return_feats=True)
+        return pointmaps, feats[-1]
+
+    @torch.no_grad()
+    def forward(self, imgs, true_shape, classes, max_bs=None, outdevice=None):
+        x_dino = self.forward_dino(imgs, true_shape)
+        x, pos = self.forward_must3r_encoder(imgs, true_shape)
+        mem = self.build_memory(x, pos, true_shape)
+        pointmaps, y = self.render(x, pos, true_shape, mem)
+        panout = self.panoptic_decoder((x, y, x_dino), imgs, pos, true_shape, classes)
+        return panout, pointmaps
+
+    @torch.no_grad()
+    def forward_inference_multi_ar(self, imgs, true_shape, classes, num_keyframes=None, max_bs=None, outdevice=None):
+        """imgs: list of (3,H,W) tensors sharing one shape; true_shape (N,2).  Returns (pointmaps list, panout)."""
+        N = len(imgs)
+        if num_keyframes is None or num_keyframes > N:
+            num_keyframes = N
+            keyframes = list(range(N))
+        else:
+            keyframes = np.linspace(0, N - 1, num_keyframes, dtype=int).tolist()
+        not_keyframes = sorted(set(range(N)).difference(keyframes))
+        order = keyframes + not_keyframes
+        im = torch.stack([imgs[i] for i in order])[None]
+        ts = true_shape[order][None]
+        x, pos = self.forward_must3r_encoder(im, ts)
+        k = num_keyframes
+        mem = self.build_memory(x[:, :k], pos[:, :k], ts[:, :k])
+        pm_kf, y_kf = self.render(x[:, :k], pos[:, :k], ts[:, :k], mem)
+        d_kf = self.forward_dino(im[:, :k], ts[:, :k])
+        pan = self.panoptic_decoder((x[:, :k], y_kf, d_kf), im[:, :k], pos[:, :k], ts[:, :k], classes)
+        pointmaps = list(pm_kf[0])
+        masks = list(pan["pred_masks"][0])
+        for i in range(k, N):  # render-only frames reuse the keyframes' final queries (panst3r.py:127-167)
+            sl = slice(i, i + 1)
+            pm_i, y_i = self.render(x[:, sl], pos[:, sl], ts[:, sl], mem)
+            d_i = self.forward_dino(im[:, sl], ts[:, sl])
+            out_i = self.panoptic_decoder((x[:, sl], y_i, d_i), im[:, sl], pos[:, sl], ts[:, sl], classes,
+                                          memory_queries=pan["out_queries"])
+            pointmaps.append(pm_i[0, 0])
+            masks.append(out_i["pred_masks"][0, 0])
+        inv = np.argsort(order)
+        return [pointmaps[i] for i in inv], {"pred_logits": pan["pred_logits"], "pred_masks": [masks[i] for i in inv],
+                                              "out_queries": pan["out_queries"]}
+
+
+def build_panst3r(variant: str = "v1", enc_depth=24, dec_depth=12, dino_depth=24, mixer_layers=3) -> PanSt3R:
+    """Full-size widths (ViT-L encoder 1024/16 heads, decoder 768/12 heads, DINOv2-L); depths reducible for tests."""
+    enc = Dust3rEncoder(depth=enc_depth)
+    dec = MUSt3R(depth=dec_depth)
+    dino = DinoV2Encoder(depth=dino_depth)
+    if variant == "v1":
+        pd = PanopticDecoder(upscaler=PixelShuffleUpscaler(input_dim=2816))
+    elif variant == "v2":
+        pd = PanopticDecoder(input_mixer=InputMixer([512, 512], 16, 2816, 768, num_layers=mixer_layers),
+                             upscaler=LoftUpUpscaler(input_dim=768, dim=384), mask_dim=384)
+    else:
+        raise ValueError(variant)
+    return PanSt3R(enc, dec, dino, pd).eval()
