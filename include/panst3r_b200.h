@@ -48,7 +48,8 @@ enum {
   PST3R_ACT_RELU = 2
 };
 enum {
-  PST3R_STORE_PLAIN = 0,      /* out[row*ldo + col] */
+  PST3R_STORE_PLAIN = 0,      /* out[row*ldo + col]; if rows_per_batch > 0:
+                                 out[(row / rows_per_batch)*batch_stride + (row % rows_per_batch)*ldo + col] */
   PST3R_STORE_TRANSPOSED = 1, /* out[(row / rows_per_batch)*batch_stride + col*ldt + row % rows_per_batch] */
   PST3R_STORE_PIXSHUF2 = 2,   /* row=(b,y,x) on grid_h x grid_w, col=4c+2i+j -> out[((b*2gh+2y+i)*2gw+2x+j)*ldo + c] */
   PST3R_STORE_D2S = 3         /* row=(b,y,x), col=(i*P+j)*C+c -> fp32 out[((b*gh*P+y*P+i)*gw*P + x*P+j)*C + c] */
@@ -63,6 +64,7 @@ typedef struct pst3r_gemm_epilogue {
   const float* col_scale; /* [N] fp32 or NULL (LayerScale; applied after act) */
   const void* residual;   /* bf16 [M, ldr] or NULL (added last) */
   int64_t ldr;
+  int32_t res_mod_rows;   /* > 0: residual row = row % res_mod_rows (broadcast, e.g. position embeddings) */
   float alpha;            /* accumulator scale (applied first) */
   int32_t store_mode;     /* PST3R_STORE_* */
   int64_t rows_per_batch; /* TRANSPOSED */
@@ -108,10 +110,13 @@ int pst3r_attention(const pst3r_attn_args* args, pst3r_stream_t stream);
 /* ---- Normalisation / elementwise ------------------------------------------------------------- */
 /* y = LN(x [+ add]) * gamma + beta ; x bf16 or fp32 [rows, dim] (row stride ldx), y bf16 or fp32.
  * If sum_out != NULL the pre-norm sum (x + add) is also written (bf16, row stride ld_sum): fused
- * "residual add + post-norm" of the Mask2Former-style query decoder (mask_transformer.py:339-340). */
+ * "residual add + post-norm" of the Mask2Former-style query decoder (mask_transformer.py:339-340).
+ * If x_rows_per_batch > 0, input row r lives at x + (r / rpb)*x_batch_stride + (r % rpb)*ldx (used to drop the
+ * DINOv2 CLS token while normalising, model/dino.py:69). */
 int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const void* add, int64_t ld_add, const float* gamma,
                     const float* beta, float eps, void* y, int32_t y_f32, int64_t ldy, void* sum_out,
-                    int64_t ld_sum, int32_t rows, int32_t dim, pst3r_stream_t stream);
+                    int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rows_per_batch, int64_t x_batch_stride,
+                    pst3r_stream_t stream);
 
 /* In-place 2-D RoPE, curope semantics: tokens bf16 [B, N, H, D] (D contiguous, D % 4 == 0),
  * positions int32 [B, N, 2] = (y, x); angle = p * base^(-j/(D/4)); fwd = +1 / -1. */

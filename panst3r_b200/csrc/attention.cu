@@ -463,7 +463,7 @@ extern "C" int pst3r_attention(const pst3r_attn_args* a, pst3r_stream_t stream_)
   PST3R_CHECK_ARG((a->k_sb == 0) == (a->v_sb == 0), "attention: k and v must both be batch-shared or neither");
   PST3R_CHECK_ARG((a->o_sn % 8) == 0 && (a->o_sb % 8) == 0, "attention: o strides must be multiples of 8");
   if (a->mask_bits)
-    PST3R_CHECK_ARG((a->mask_sq % 4) == 0 && a->mask_sq * 32 >= ((a->Nk + 127) / 128) * 128 &&
+    PST3R_CHECK_ARG((a->mask_sq % 4) == 0 && (a->mask_sq == 0 || a->mask_sq * 32 >= ((a->Nk + 127) / 128) * 128) &&
                         (reinterpret_cast<uintptr_t>(a->mask_bits) % 16) == 0 && (a->mask_sb % 4) == 0,
                     "attention: mask rows must be 16-byte aligned and padded to 128 keys");
   int splits = a->kv_splits > 0 ? a->kv_splits : pst3r_attention_auto_splits(a->B, a->H, a->Nq, a->Nk);

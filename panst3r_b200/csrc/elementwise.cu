@@ -21,11 +21,11 @@ template <bool X_F32, bool Y_F32>
 __global__ void layernorm_kernel(const void* __restrict__ x, long long ldx, const bf16* __restrict__ add,
                                  long long ld_add, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float eps, void* __restrict__ y, long long ldy, bf16* __restrict__ sum_out,
-                                 long long ld_sum, int rows, int dim) {
+                                 long long ld_sum, int rows, int dim, int x_rpb, long long x_bs) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const long long xo = (long long)row * ldx;
+  const long long xo = x_rpb > 0 ? (long long)(row / x_rpb) * x_bs + (long long)(row % x_rpb) * ldx : (long long)row * ldx;
   const long long ao = (long long)row * ld_add;
   float s = 0.0f;
   for (int i = lane; i < dim; i += 32) {
@@ -292,7 +292,8 @@ extern "C" int pst3r_check_device(void) {
 
 extern "C" int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const void* add, int64_t ld_add,
                                const float* gamma, const float* beta, float eps, void* y, int32_t y_f32, int64_t ldy,
-                               void* sum_out, int64_t ld_sum, int32_t rows, int32_t dim, pst3r_stream_t s_) {
+                               void* sum_out, int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rpb, int64_t x_bs,
+                               pst3r_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
   PST3R_CHECK_ARG(x && gamma && beta && y && rows > 0 && dim > 0, "layernorm: bad args");
   const int wpb = 8;
@@ -300,13 +301,13 @@ extern "C" int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const 
   const bf16* a = reinterpret_cast<const bf16*>(add);
   bf16* so = reinterpret_cast<bf16*>(sum_out);
   if (x_f32 && y_f32)
-    layernorm_kernel<true, true><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim);
+    layernorm_kernel<true, true><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs);
   else if (x_f32)
-    layernorm_kernel<true, false><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim);
+    layernorm_kernel<true, false><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs);
   else if (y_f32)
-    layernorm_kernel<false, true><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim);
+    layernorm_kernel<false, true><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs);
   else
-    layernorm_kernel<false, false><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim);
+    layernorm_kernel<false, false><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs);
   PST3R_CHECK_CUDA(cudaGetLastError());
   return PST3R_OK;
 }

@@ -25,6 +25,7 @@ struct GemmEpi {
   const float* col_scale;
   const bf16* residual;
   long long ldr;
+  int res_mod_rows;
   float alpha;
   int store_mode;
   long long rows_per_batch, batch_stride, ldt;
@@ -101,7 +102,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
       if (i < ncols) v[i] *= __ldg(ep.col_scale + col0 + i);
   }
   if (ep.residual) {
-    const bf16* r = ep.residual + (long long)row * ep.ldr + col0;
+    const int rrow = ep.res_mod_rows > 0 ? row % ep.res_mod_rows : row;
+    const bf16* r = ep.residual + (long long)rrow * ep.ldr + col0;
     if (full && ((ep.ldr & 7) == 0)) {
       const uint4* r4 = reinterpret_cast<const uint4*>(r);
 #pragma unroll
@@ -122,9 +124,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
 
   switch (ep.store_mode) {
     case PST3R_STORE_PLAIN: {
+      long long roff = (long long)row * ep.ldo;
+      if (ep.rows_per_batch > 0) {
+        const long long bb = row / ep.rows_per_batch;
+        roff = bb * ep.batch_stride + (row - bb * ep.rows_per_batch) * ep.ldo;
+      }
       if (ep.out_f32) {
-        float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + col0;
-        if (full && ((ep.ldo & 3) == 0)) {
+        float* o = reinterpret_cast<float*>(ep.out) + roff + col0;
+        if (full && ((ep.ldo & 3) == 0) && ((ep.batch_stride & 3) == 0)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -134,8 +141,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
             if (i < ncols) o[i] = v[i];
         }
       } else {
-        bf16* o = reinterpret_cast<bf16*>(ep.out) + (long long)row * ep.ldo + col0;
-        if (full && ((ep.ldo & 7) == 0)) {
+        bf16* o = reinterpret_cast<bf16*>(ep.out) + roff + col0;
+        if (full && ((ep.ldo & 7) == 0) && ((ep.batch_stride & 7) == 0)) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 u;
@@ -403,7 +410,7 @@ extern "C" int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   GemmEpi ep;
   ep.out = e->out; ep.ldo = e->ldo; ep.out_f32 = e->out_f32; ep.act = e->act;
   ep.bias = e->bias; ep.col_scale = e->col_scale;
-  ep.residual = reinterpret_cast<const bf16*>(e->residual); ep.ldr = e->ldr;
+  ep.residual = reinterpret_cast<const bf16*>(e->residual); ep.ldr = e->ldr; ep.res_mod_rows = e->res_mod_rows;
   ep.alpha = e->alpha; ep.store_mode = e->store_mode;
   ep.rows_per_batch = e->rows_per_batch; ep.batch_stride = e->batch_stride; ep.ldt = e->ldt;
   ep.grid_h = e->grid_h; ep.grid_w = e->grid_w; ep.d2s_patch = e->d2s_patch; ep.d2s_ch = e->d2s_ch;

@@ -25,6 +25,7 @@ class GemmEpilogue(C.Structure):
         ("col_scale", C.c_void_p),
         ("residual", C.c_void_p),
         ("ldr", C.c_int64),
+        ("res_mod_rows", C.c_int32),
         ("alpha", C.c_float),
         ("store_mode", C.c_int32),
         ("rows_per_batch", C.c_int64),
@@ -65,7 +66,7 @@ SIGNATURES = {
     "pst3r_attention_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),
     "pst3r_attention_auto_splits": (_i32, [_i32, _i32, _i32, _i32]),
     "pst3r_attention": (C.c_int, [C.POINTER(AttnArgs), _p]),
-    "pst3r_layernorm": (C.c_int, [_p, _i32, _i64, _p, _i64, _p, _p, _f, _p, _i32, _i64, _p, _i64, _i32, _i32, _p]),
+    "pst3r_layernorm": (C.c_int, [_p, _i32, _i64, _p, _i64, _p, _p, _f, _p, _i32, _i64, _p, _i64, _i32, _i32, _i32, _i64, _p]),
     "pst3r_rope2d": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f, _f, _p]),
     "pst3r_add_bcast": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _i64, _i32, _i32, _p]),
     "pst3r_cast_f32_to_bf16": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p]),

@@ -1,0 +1,305 @@
+"""CUDA MUSt3R encoder / decoder behind the reference's two operator seams.
+
+    x, pos = encoder(img, true_shape)                                    (reference engine/must3r.py:17-24)
+    mem, pointmaps, feats = decoder(x, pos, true_shape, mem, render=, return_feats=)   (:45, :93, :116)
+
+Same constructor arguments, parameter names and memory 5-tuple as oracle/must3r.py (the restatement of the
+un-vendored upstream classes named at reference configs/base.yaml:7-15); all arithmetic runs in
+libpanst3r_b200.so (tcgen05 GEMMs with fused bias/RoPE/GELU/residual epilogues, tcgen05 flash attention).
+B200-first differences from a literal translation:
+  * the memory bank stores, next to the raw memory tokens, their K/V projections per layer — projected once
+    when tokens are appended instead of on every decoder call;
+  * all views of a render call attend one shared K/V copy (kv batch stride 0) instead of an expanded memory;
+  * RoPE is applied in the QKV GEMM epilogue; the pointmap pixel-shuffle is the GEMM's store pattern.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .common import (ViTBlockParams, b16, bias_of, cat_f32, cat_w16, f32, mlp_residual, pos_grid, prepared, rope_table,
+                     self_attention, vit_block, w16)
+
+
+def _hw(true_shape) -> tuple:
+    ts = true_shape.reshape(-1, 2)
+    if ts.is_cuda:
+        ts = ts.cpu()
+    H, W = int(ts[0, 0]), int(ts[0, 1])
+    if not bool((ts == ts[0:1]).all()):
+        raise ops._l.Pst3rError("all views of a call must share one true_shape (single aspect-ratio batches)")
+    if W < H:
+        raise ops._l.Pst3rError("portrait batches are not implemented on the CUDA path yet (landscape only)")
+    return H, W
+
+
+class Dust3rEncoder(nn.Module):
+    def __init__(self, img_size=(512, 512), patch_embed="PatchEmbedDust3R", patch_size=16, embed_dim=1024, depth=24,
+                 num_heads=16, mlp_ratio=4.0, pos_embed="RoPE100"):
+        super().__init__()
+        assert patch_embed == "PatchEmbedDust3R" and pos_embed.startswith("RoPE")
+        self.patch_size, self.embed_dim, self.num_heads = patch_size, embed_dim, num_heads
+        self.rope_base = float(pos_embed[4:])
+        self.patch_embed = nn.Module()
+        self.patch_embed.proj = nn.Conv2d(3, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.blocks_enc = nn.ModuleList([ViTBlockParams(embed_dim, num_heads, mlp_ratio, eps=1e-6) for _ in range(depth)])
+        self.norm_enc = nn.LayerNorm(embed_dim, eps=1e-6)
+
+    @torch.no_grad()
+    def forward(self, img: torch.Tensor, true_shape, out: Optional[torch.Tensor] = None):
+        """img fp32 (b,3,H,W) in [-1,1] -> (x bf16 (b,N,D), pos int64 (b,N,2)).  `out`: optional bf16 destination
+        (b*N rows, D columns, any row stride) for the normalised tokens."""
+        b, _, H, W = img.shape
+        P, D = self.patch_size, self.embed_dim
+        h, w = H // P, W // P
+        N = h * w
+        pos64, pos32 = pos_grid(h, w, img.device)
+        pos_rows = pos32.repeat(b, 1) if b > 1 else pos32
+        rope = (rope_table(max(h, w), D // self.num_heads, self.rope_base, img.device), pos_rows)
+        a = ops.patchify(img.float(), P)
+        x = ops.gemm(a, w16(self.patch_embed.proj.weight), bias=f32(self.patch_embed.proj.bias))
+        for blk in self.blocks_enc:
+            x = vit_block(x, blk, b, N, rope)
+        if out is None:
+            out = torch.empty((b * N, D), device=img.device, dtype=torch.bfloat16)
+        ops.layernorm(x, f32(self.norm_enc.weight), f32(self.norm_enc.bias), 1e-6, out=out)
+        xo = out.view(b, N, D) if out.is_contiguous() else out.unflatten(0, (b, N))
+        return xo, pos64[None].expand(b, N, 2)
+
+
+class _DecBlock(ViTBlockParams):
+    """norm1/attn/norm2 from ViTBlockParams + cross_attn.{projq,projk,projv,proj}, norm3, mlp, norm_y."""
+
+    def __init__(self, dim, num_heads, mlp_ratio):
+        super().__init__(dim, num_heads, mlp_ratio, eps=1e-6)
+        self.cross_attn = nn.Module()
+        for n in ("projq", "projk", "projv", "proj"):
+            setattr(self.cross_attn, n, nn.Linear(dim, dim))
+        self.norm3 = nn.LayerNorm(dim, eps=1e-6)
+        self.norm_y = nn.LayerNorm(dim, eps=1e-6)
+
+    def kv_weight(self):
+        return cat_w16([self.cross_attn.projk.weight, self.cross_attn.projv.weight])
+
+    def kv_bias(self):
+        return cat_f32([self.cross_attn.projk.bias, self.cross_attn.projv.bias])
+
+
+class MemoryBank:
+    """Per-layer memory tokens (B, cap, D) and their K|V projections (B, cap, 2D), bf16, capacity-doubling."""
+
+    def __init__(self, B: int, depth: int, dim: int, device, capacity: int):
+        self.B, self.depth, self.dim, self.n = B, depth, dim, 0
+        self.cap = max(capacity, 1)
+        self.tok = [torch.empty((B, self.cap, dim), device=device, dtype=torch.bfloat16) for _ in range(depth)]
+        self.kv = [torch.empty((B, self.cap, 2 * dim), device=device, dtype=torch.bfloat16) for _ in range(depth)]
+
+    def reserve(self, n_total: int):
+        if n_total <= self.cap:
+            return
+        cap = max(n_total, 2 * self.cap)
+        for lst, width in ((self.tok, self.dim), (self.kv, 2 * self.dim)):
+            for l in range(self.depth):
+                nb = torch.empty((self.B, cap, width), device=lst[l].device, dtype=torch.bfloat16)
+                nb[:, :self.n].copy_(lst[l][:, :self.n])
+                lst[l] = nb
+        self.cap = cap
+
+
+class MemVals(list):
+    """`mem_vals` of the reference's memory tuple: a list of (B, Nmem, D) tensors, plus the bank that owns them."""
+    bank: Optional[MemoryBank] = None
+
+
+class MUSt3R(nn.Module):
+    def __init__(self, img_size=(512, 512), feedback_type="single_mlp", memory_mode="norm_y", enc_embed_dim=1024,
+                 embed_dim=768, depth=12, num_heads=12, mlp_ratio=4.0, patch_size=16, pos_embed="RoPE100",
+                 head_channels=7):
+        super().__init__()
+        assert feedback_type == "single_mlp" and memory_mode == "norm_y"
+        self.embed_dim, self.depth, self.num_heads, self.patch_size = embed_dim, depth, num_heads, patch_size
+        self.head_channels = head_channels
+        self.rope_base = float(pos_embed[4:])
+        self.feat_embed_enc_to_dec = nn.Linear(enc_embed_dim, embed_dim)
+        self.image2_embed = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.blocks_dec = nn.ModuleList([_DecBlock(embed_dim, num_heads, mlp_ratio) for _ in range(depth)])
+        self.feedback_layer = nn.Module()
+        self.feedback_layer.fc1 = nn.Linear(embed_dim, int(mlp_ratio * embed_dim))
+        self.feedback_layer.fc2 = nn.Linear(int(mlp_ratio * embed_dim), embed_dim)
+        self.norm_dec = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.head_dec = nn.Module()
+        self.head_dec.proj = nn.Linear(embed_dim, head_channels * patch_size * patch_size)
+        self.reserve_views = 0  # capacity hint (views) for the memory bank, set by the caller
+
+    # ---- prepared (fused / permuted) parameters -------------------------------------------------
+    def _embed_bias(self, tagged: bool):
+        b, e = self.feat_embed_enc_to_dec.bias, self.image2_embed
+        if not tagged:
+            return f32(b)
+        return prepared("embed_bias_tagged", [b, e], lambda: (b.detach().float() + e.detach().float().view(-1)).contiguous())
+
+    def _head_weight(self):
+        P, C, D = self.patch_size, self.head_channels, self.embed_dim
+        wt = self.head_dec.proj.weight
+        # reference row order (c, i, j) -> (i, j, c): the D2S epilogue then writes C-contiguous pixels
+        return prepared("head_w", [wt], lambda: wt.detach().view(C, P, P, D).permute(1, 2, 0, 3).reshape(P * P * C, D)
+                        .to(torch.bfloat16).contiguous())
+
+    def _head_bias(self):
+        P, C = self.patch_size, self.head_channels
+        bs = self.head_dec.proj.bias
+        return prepared("head_b", [bs], lambda: bs.detach().view(C, P, P).permute(1, 2, 0).reshape(-1).float().contiguous())
+
+    # ---- pieces -----------------------------------------------------------------------------------
+    def _cross_attention(self, x, blk: _DecBlock, B, n, N, kv_list, mask_bits):
+        """x += proj(attn(q = projq(norm2 x), K|V));  kv_list[b]: bf16 (1, Nk, 2D) shared by the n views of batch b."""
+        D, H = self.embed_dim, self.num_heads
+        hd = D // H
+        hq = ops.layernorm(x, f32(blk.norm2.weight), f32(blk.norm2.bias), 1e-6)
+        q = ops.gemm(hq, w16(blk.cross_attn.projq.weight), bias=bias_of(blk.cross_attn.projq)).view(B, n, N, H, hd)
+        o = torch.empty((B * n, N, D), device=x.device, dtype=torch.bfloat16)
+        for b in range(B):
+            kv = kv_list[b]
+            Nk = kv.shape[1]
+            k = kv[:, :, :D].unflatten(-1, (H, hd))
+            v = kv[:, :, D:].unflatten(-1, (H, hd))
+            ops.attention(q[b], k, v, mask_bits=mask_bits, out=o[b * n:(b + 1) * n])
+        return ops.gemm(o.view(B * n * N, D), w16(blk.cross_attn.proj.weight), bias=bias_of(blk.cross_attn.proj),
+                        residual=x, out=x)
+
+    @staticmethod
+    def _own_view_mask(n: int, N: int, n_mem: int, device) -> torch.Tensor:
+        """int32 (n, 1, W): view i may not attend to candidate keys [n_mem + i*N, n_mem + (i+1)*N) (its own tokens)."""
+        nk = n_mem + n * N
+        words = ((nk + 127) // 128) * 4
+        kidx = torch.arange(words * 32, device=device)[None]
+        lo = (torch.arange(n, device=device) * N + n_mem)[:, None]
+        blocked = (kidx >= lo) & (kidx < lo + N)
+        packed = (blocked.view(n, words, 32).to(torch.int64) << torch.arange(32, device=device)).sum(-1)
+        packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32)
+        return packed.view(n, 1, words).contiguous()
+
+    @torch.no_grad()
+    def forward(self, x, pos, true_shape, mem=None, render=False, return_feats=False, compute_pointmaps=True,
+                feats_out: Optional[torch.Tensor] = None):
+        """x bf16/fp32 (B, n, N, Denc); pos (B, n, N, 2); true_shape (B, n, 2).
+        Returns (mem, pointmaps fp32 (B, n, H, W, C) | None, feats list | None).
+        return_feats: True -> every layer's tokens (feats[-1] = last block output); 'last' -> [last] only.
+        feats_out: optional bf16 destination rows (B*n*N, D) for the last block's output."""
+        B, n, N, Denc = x.shape
+        D, L = self.embed_dim, self.depth
+        H, W = _hw(true_shape)
+        dev = x.device
+        h_, w_ = H // self.patch_size, W // self.patch_size
+        rows = B * n * N
+        xin = x if x.dtype == torch.bfloat16 else ops.to_bf16(x.float().contiguous().view(rows, Denc))
+        xin = xin.reshape(B, n, N, Denc)
+        _, pos32 = pos_grid(h_, w_, dev)
+        rope = (rope_table(max(h_, w_), D // self.num_heads, self.rope_base, dev), pos32.repeat(B * n, 1))
+
+        # enc -> dec embedding; every view except the scene's first is tagged with image2_embed (fused as a bias)
+        hx = torch.empty((B, n, N, D), device=dev, dtype=torch.bfloat16)
+        we = w16(self.feat_embed_enc_to_dec.weight)
+        first_untagged = mem is None and not render
+        if first_untagged:
+            for b in range(B):
+                ops.gemm(xin[b, 0], we, bias=self._embed_bias(False), out=hx[b, 0])
+                if n > 1:
+                    ops.gemm(xin[b, 1:], we, bias=self._embed_bias(True), out=hx[b, 1:])
+        else:
+            ops.gemm(xin, we, bias=self._embed_bias(True), out=hx)
+        cur = hx.view(rows, D)
+
+        bank: Optional[MemoryBank] = None
+        if mem is not None:
+            mem_vals, mem_labels, mem_nimgs = mem[0], mem[1], mem[2]
+            bank = getattr(mem_vals, "bank", None)
+            n_mem = mem_vals[0].shape[1]
+        else:
+            if render:
+                raise ops._l.Pst3rError("render=True needs a memory")
+            mem_vals, mem_labels, mem_nimgs, n_mem = None, None, 0, 0
+
+        keep_all = return_feats is True
+        feats: List[torch.Tensor] = [hx] if keep_all else []
+
+        def stored_kv(l):
+            if bank is not None:
+                return [bank.kv[l][b:b + 1, :n_mem] for b in range(B)]
+            # foreign memory tuple (e.g. the reference's sliced render path): project on the fly
+            blk = self.blocks_dec[l]
+            kv = ops.gemm(b16(mem_vals[l]) if mem_vals[l].dtype != torch.bfloat16 else mem_vals[l].contiguous(),
+                          blk.kv_weight(), bias=blk.kv_bias())
+            return [kv[b:b + 1] for b in range(kv.shape[0])]
+
+        if render:
+            for l, blk in enumerate(self.blocks_dec):
+                in_place = not keep_all
+                cur = self_attention(cur, blk, B * n, N, rope, in_place=in_place)
+                cur = self._cross_attention(cur, blk, B, n, N, stored_kv(l), None)
+                last = l == L - 1
+                cur = mlp_residual(cur, blk.norm3, blk.mlp, 1e-6, out=feats_out if (last and feats_out is not None) else None)
+                if keep_all:
+                    feats.append(cur.view(B, n, N, D) if cur.is_contiguous() else cur.unflatten(0, (B, n, N)))
+            new_mem = mem
+        else:
+            layer_in = []
+            mask_bits = self._own_view_mask(n, N, n_mem, dev) if n > 1 else None
+            for l, blk in enumerate(self.blocks_dec):
+                layer_in.append(cur)
+                nxt = self_attention(cur, blk, B * n, N, rope, in_place=False)
+                if n == 1:
+                    if n_mem == 0:
+                        raise ops._l.Pst3rError("a single first view has nothing to attend to (init needs >= 2 views)")
+                    kvs = stored_kv(l)
+                else:
+                    fresh = ops.layernorm(cur, f32(blk.norm_y.weight), f32(blk.norm_y.bias), 1e-6)
+                    kvf = ops.gemm(fresh, blk.kv_weight(), bias=blk.kv_bias()).view(B, n * N, 2 * D)
+                    kvs = []
+                    old = stored_kv(l) if n_mem > 0 else None
+                    for b in range(B):
+                        kvs.append(kvf[b:b + 1] if old is None else torch.cat([old[b], kvf[b:b + 1]], dim=1))
+                nxt = self._cross_attention(nxt, blk, B, n, N, kvs, mask_bits)
+                cur = mlp_residual(nxt, blk.norm3, blk.mlp, 1e-6,
+                                   out=feats_out if (l == L - 1 and feats_out is not None) else None)
+                if keep_all:
+                    feats.append(cur.view(B, n, N, D) if cur.is_contiguous() else cur.unflatten(0, (B, n, N)))
+            # feedback + memory write: stored_l = norm_y_l(layer_in_l + feedback(x_L)); K|V projected once, here
+            fb = ops.gemm(cur, w16(self.feedback_layer.fc1.weight), bias=bias_of(self.feedback_layer.fc1), act=ops.ACT_GELU)
+            fb = ops.gemm(fb, w16(self.feedback_layer.fc2.weight), bias=bias_of(self.feedback_layer.fc2))
+            if bank is None:
+                cap = max(self.reserve_views, mem_nimgs + n) * N
+                bank = MemoryBank(B, L, D, dev, cap)
+                if n_mem > 0:  # adopt a foreign memory
+                    bank.reserve(n_mem + n * N)
+                    for l, blk in enumerate(self.blocks_dec):
+                        bank.tok[l][:, :n_mem].copy_(mem_vals[l])
+                        for b in range(B):
+                            ops.gemm(bank.tok[l][b, :n_mem], blk.kv_weight(), bias=blk.kv_bias(), out=bank.kv[l][b, :n_mem])
+                    bank.n = n_mem
+            bank.reserve(n_mem + n * N)
+            for l, blk in enumerate(self.blocks_dec):
+                for b in range(B):
+                    dst = bank.tok[l][b, n_mem:n_mem + n * N]
+                    sl = slice(b * n * N, (b + 1) * n * N)
+                    ops.layernorm(layer_in[l][sl], f32(blk.norm_y.weight), f32(blk.norm_y.bias), 1e-6, add=fb[sl], out=dst)
+                    ops.gemm(dst, blk.kv_weight(), bias=blk.kv_bias(), out=bank.kv[l][b, n_mem:n_mem + n * N])
+            bank.n = n_mem + n * N
+            vals = MemVals([bank.tok[l][:, :bank.n] for l in range(L)])
+            vals.bank = bank
+            new_labels = (mem_nimgs + torch.arange(n, device=dev)).view(1, n, 1).expand(B, n, N).reshape(B, n * N)
+            labels = new_labels if mem_labels is None else torch.cat([mem_labels, new_labels], dim=1)
+            new_mem = (vals, labels, mem_nimgs + n, None, None)
+
+        pointmaps = None
+        if compute_pointmaps:
+            hn = ops.layernorm(cur, f32(self.norm_dec.weight), f32(self.norm_dec.bias), 1e-6)
+            pointmaps = torch.empty((B, n, H, W, self.head_channels), device=dev, dtype=torch.float32)
+            ops.gemm(hn, self._head_weight(), bias=self._head_bias(), out=pointmaps, store_mode=ops.STORE_D2S,
+                     grid=(h_, w_), d2s=(self.patch_size, self.head_channels))
+        if return_feats == "last":
+            feats = [cur.view(B, n, N, D) if cur.is_contiguous() else cur.unflatten(0, (B, n, N))]
+        return new_mem, pointmaps, (feats if return_feats else None)

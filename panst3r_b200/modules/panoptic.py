@@ -1,0 +1,353 @@
+"""CUDA panoptic head: PanopticDecoder / MaskTransformer / PixelShuffleUpscaler / TextEncoder with the
+reference's constructor arguments, forward signatures and state-dict names
+(reference src/panst3r/model/panoptic_decoder.py:16-77, mask_transformer.py:12-288,
+upscalers/pixel_shuffle.py:9-59, text_encoder.py:94-103).
+
+B200-first restructuring (results are those of the reference ops on the same inputs):
+  * feature maps stay pixel-major (NHWC bf16): F.pixel_shuffle is the store pattern of the producing GEMM and
+    the mask einsum "bqc,bnchw->bnqhw" is a tcgen05 GEMM (pixels x queries) with a plane-major fp32 store;
+  * the 8x bilinear downsample feeding the attention mask equals the mean of the centre 2x2 logits and is linear
+    in the features, so it is computed from centre-pooled features (1/64 of the pixels) as a second small GEMM;
+  * K/V in-projections of the (layer-invariant) memory tokens of all 6 decoder layers are two batched GEMMs;
+  * level_embed is folded into the proj_16.fc2 bias; the sine PE is a per-grid constant;
+  * the boolean attention mask is a bitmask consumed directly by the attention kernel.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .common import b16, bias_of, cat_f32, cat_w16, f32, prepared, w16
+from .must3r import _hw
+
+
+class _Mlp(nn.Module):
+    def __init__(self, i, h, o):
+        super().__init__()
+        self.fc1 = nn.Linear(i, h)
+        self.fc2 = nn.Linear(h, o)
+
+
+class PixelShuffleUpscaler(nn.Module):
+    def __init__(self, input_dim, patch_size=16, hidden_dim_factor=4, fp_dim=(768, 512, 384, 256), **kwargs):
+        super().__init__()
+        self.patch_size, self.fp_dim = patch_size, list(fp_dim)
+        f = hidden_dim_factor
+        self.proj_8 = _Mlp(input_dim, int(f * input_dim), fp_dim[1] * 4)
+        self.proj_4 = _Mlp(fp_dim[1], int(f * fp_dim[1]), fp_dim[2] * 4)
+        self.proj_2 = _Mlp(fp_dim[2], int(f * fp_dim[2]), fp_dim[3] * 4)
+        self.proj_16 = _Mlp(input_dim, int(f * input_dim), fp_dim[0])
+        self.mask_dim = fp_dim[3]
+
+    @torch.no_grad()
+    def forward_nhwc(self, feats: torch.Tensor, b: int, hs: int, ws: int, f16_extra_bias: Optional[torch.Tensor] = None):
+        """feats bf16 rows (b*hs*ws, input_dim) -> (f16 bf16 (b*hs*ws, 768) token-major,
+        mask feats bf16 (b, 8hs, 8ws, 256) pixel-major).  f16_extra_bias is added to the f16 output (level_embed)."""
+        dev = feats.device
+
+        def mlp_shuffle(x, m: _Mlp, gh, gw):
+            h = ops.gemm(x, w16(m.fc1.weight), bias=bias_of(m.fc1), act=ops.ACT_GELU)
+            cout = m.fc2.weight.shape[0] // 4
+            out = torch.empty((b * 2 * gh * 2 * gw, cout), device=dev, dtype=torch.bfloat16)
+            ops.gemm(h, w16(m.fc2.weight), bias=bias_of(m.fc2), out=out, store_mode=ops.STORE_PIXSHUF2, grid=(gh, gw))
+            return out
+
+        f8 = mlp_shuffle(feats, self.proj_8, hs, ws)
+        f4 = mlp_shuffle(f8, self.proj_4, 2 * hs, 2 * ws)
+        f2 = mlp_shuffle(f4, self.proj_2, 4 * hs, 4 * ws)
+        h = ops.gemm(feats, w16(self.proj_16.fc1.weight), bias=bias_of(self.proj_16.fc1), act=ops.ACT_GELU)
+        bias16 = f32(self.proj_16.fc2.bias)
+        if f16_extra_bias is not None:
+            bias16 = prepared("f16bias", [self.proj_16.fc2.bias, f16_extra_bias],
+                              lambda: (self.proj_16.fc2.bias.detach().float() + f16_extra_bias.detach().float().view(-1)).contiguous())
+        f16 = ops.gemm(h, w16(self.proj_16.fc2.weight), bias=bias16)
+        return f16, f2.view(b, 8 * hs, 8 * ws, self.mask_dim)
+
+    @torch.no_grad()
+    def forward(self, inputs, img_shape):
+        """Reference signature: (feats (b, N, C), imgs), (H, W) -> ([f16 (b,768,hs,ws)], mask_feats (b,256,H/2,W/2)) fp32 NCHW."""
+        feats = inputs[0]
+        H, W = img_shape
+        hs, ws = H // self.patch_size, W // self.patch_size
+        b = feats.shape[0]
+        x = feats if feats.dtype == torch.bfloat16 else ops.to_bf16(feats.float().contiguous())
+        f16, f2 = self.forward_nhwc(x.reshape(b * hs * ws, -1), b, hs, ws)
+        f16_nchw = ops.nhwc_to_nchw_f32(f16.view(b, hs * ws, -1)).view(b, -1, hs, ws)
+        f2_nchw = ops.nhwc_to_nchw_f32(f2.view(b, 64 * hs * ws, -1)).view(b, -1, 8 * hs, 8 * ws)
+        return [f16_nchw], f2_nchw
+
+
+class TextEncoder(nn.Module):
+    """Fixed-vocabulary mode: dictionary lookup + L2 normalisation (text_encoder.py:94-103).  The HF text tower
+    (`set_vocab`) runs once per vocabulary, needs downloaded weights and is out of scope: provide embeddings
+    through `class_embeddings` (same attribute as the reference)."""
+
+    def __init__(self, model_name="siglip", out_dim=768, fixed_vocab=True):
+        super().__init__()
+        self.embed_dim = {"siglip": 768, "siglip2": 768, "clip": 512}[model_name]
+        self.fixed_vocab = fixed_vocab
+        self.class_embeddings: Dict[str, torch.Tensor] = {}
+        self._norm_cache = {}
+
+    def set_vocab(self, classes, device=None):
+        raise NotImplementedError("the HF text tower is outside the CUDA hot path; assign `class_embeddings` directly")
+
+    @torch.no_grad()
+    def forward(self, classes: List[str], device=None) -> torch.Tensor:
+        assert all(c in self.class_embeddings for c in classes), "Missing classes in vocabulary"
+        key = tuple(classes)
+        hit = self._norm_cache.get(key)
+        if hit is None or hit.device != torch.device(device):
+            e = torch.stack([self.class_embeddings[c] for c in classes]).to(device=device, dtype=torch.float32).contiguous()
+            hit = ops.l2norm_rows(e, 0.0, torch.bfloat16)
+            self._norm_cache = {key: hit}
+        return hit
+
+
+class _MHA(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d, d))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d))
+        self.out_proj = nn.Linear(d, d)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+
+
+class _SALayer(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.self_attn = _MHA(d)
+        self.norm = nn.LayerNorm(d)
+
+
+class _CALayer(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.multihead_attn = _MHA(d)
+        self.norm = nn.LayerNorm(d)
+
+
+class _FFN(nn.Module):
+    def __init__(self, d, ff):
+        super().__init__()
+        self.linear1 = nn.Linear(d, ff)
+        self.linear2 = nn.Linear(ff, d)
+        self.norm = nn.LayerNorm(d)
+
+
+class _MaskMLP(nn.Module):
+    def __init__(self, i, h, o, n):
+        super().__init__()
+        dims = [i] + [h] * (n - 1) + [o]
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+
+
+def sine_pe(h: int, w: int, num_pos_feats: int, temperature: float = 10000.0) -> torch.Tensor:
+    """PositionEmbeddingSine(normalize=True) on an unmasked (h, w) grid -> fp32 (h*w, 2*num_pos_feats), row-major
+    tokens, channels [pos_y | pos_x] (mask_transformer.py:504-527).  A constant of the grid shape."""
+    eps, scale = 1e-6, 2 * math.pi
+    y = torch.arange(1, h + 1, dtype=torch.float32) / (h + eps) * scale
+    x = torch.arange(1, w + 1, dtype=torch.float32) / (w + eps) * scale
+    i = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(i, 2, rounding_mode="floor") / num_pos_feats)
+
+    def enc(v):
+        a = v[:, None] / dim_t
+        return torch.stack([a[:, 0::2].sin(), a[:, 1::2].cos()], dim=2).flatten(1)
+
+    py = enc(y)[:, None, :].expand(h, w, num_pos_feats)
+    px = enc(x)[None, :, :].expand(h, w, num_pos_feats)
+    return torch.cat([py, px], dim=2).reshape(h * w, 2 * num_pos_feats)
+
+
+class MaskTransformer(nn.Module):
+    def __init__(self, in_dim, hidden_dim, ff_dim, mask_dim, num_queries, num_heads, dec_layers, lang_dim=768,
+                 normalize_before=False, num_feature_levels=1, enforce_input_project=False, two_stage=False,
+                 landscape_only=False):
+        super().__init__()
+        in_dim = [in_dim] * num_feature_levels if isinstance(in_dim, int) else list(in_dim)
+        assert num_feature_levels == 1 and in_dim == [hidden_dim] and not two_stage and not normalize_before
+        self.hidden_dim, self.num_heads, self.num_layers, self.num_queries = hidden_dim, num_heads, dec_layers, num_queries
+        self.mask_dim = mask_dim
+        self.self_attn_layers = nn.ModuleList(_SALayer(hidden_dim) for _ in range(dec_layers))
+        self.cross_attn_layers = nn.ModuleList(_CALayer(hidden_dim) for _ in range(dec_layers))
+        self.ffn_layers = nn.ModuleList(_FFN(hidden_dim, ff_dim) for _ in range(dec_layers))
+        self.decoder_norm = nn.LayerNorm(hidden_dim)
+        self.query_feat = nn.Embedding(num_queries, hidden_dim)
+        self.query_embed = nn.Embedding(num_queries, hidden_dim)
+        self.level_embed = nn.Embedding(num_feature_levels, hidden_dim)
+        self.input_proj = nn.ModuleList([nn.Sequential()])
+        self.lang_embed = nn.Linear(hidden_dim, lang_dim)
+        self.cls_logit_scale = nn.Parameter(torch.ones([]))
+        self.mask_embed = _MaskMLP(hidden_dim, hidden_dim, mask_dim, 3)
+
+    # ---- prepared -------------------------------------------------------------------------------
+    def _kv_weights(self):
+        d = self.hidden_dim
+        ws = [l.multihead_attn.in_proj_weight for l in self.cross_attn_layers]
+        bs = [l.multihead_attn.in_proj_bias for l in self.cross_attn_layers]
+        wk = prepared("mt_wk", ws, lambda: torch.cat([w.detach()[d:2 * d] for w in ws], 0).to(torch.bfloat16).contiguous())
+        wv = prepared("mt_wv", ws, lambda: torch.cat([w.detach()[2 * d:] for w in ws], 0).to(torch.bfloat16).contiguous())
+        bk = prepared("mt_bk", bs, lambda: torch.cat([b.detach()[d:2 * d] for b in bs], 0).float().contiguous())
+        bv = prepared("mt_bv", bs, lambda: torch.cat([b.detach()[2 * d:] for b in bs], 0).float().contiguous())
+        return wk, bk, wv, bv
+
+    def _pos(self, h, w, device):
+        return prepared(f"mt_pe_{h}x{w}", [self.level_embed.weight],
+                        lambda: sine_pe(h, w, self.hidden_dim // 2).to(device=device, dtype=torch.bfloat16).contiguous())
+
+    @staticmethod
+    def _slice_w(p: torch.Tensor, a: int, b: int, tag: str):
+        return prepared(f"mt_slice_{tag}_{a}_{b}", [p], lambda: (p.detach()[a:b].to(torch.bfloat16) if p.dim() == 2 else
+                                                                 p.detach()[a:b].float()).contiguous())
+
+    # ---- prediction heads (mask_transformer.py:215-288) -----------------------------------------------
+    @torch.no_grad()
+    def prediction_heads(self, output: torch.Tensor, mask_feats: torch.Tensor, pooled: Optional[torch.Tensor],
+                         cls_emb: torch.Tensor, want_masks: bool):
+        """output bf16 (Q, C) [batch 1]; mask_feats bf16 (V, Hm, Wm, Cm) pixel-major; pooled bf16 (V*h*w, Cm) or None.
+        Returns (class logits fp32 (Q, K), mask logits fp32 (V, Q, Hm, Wm) | None, mask bits int32 (1, Q, W) | None)."""
+        Q = output.shape[0]
+        dec = ops.layernorm(output, f32(self.decoder_norm.weight), f32(self.decoder_norm.bias), 1e-5)
+        lang = ops.gemm(dec, w16(self.lang_embed.weight), bias=bias_of(self.lang_embed), out_dtype=torch.float32)
+        lang = ops.l2norm_rows(lang, 1e-7, torch.bfloat16)
+        scale = prepared("mt_scale", [self.cls_logit_scale], lambda: self.cls_logit_scale.detach().float().exp().cpu())
+        logits = ops.gemm(lang, cls_emb, alpha=float(scale), out_dtype=torch.float32)
+        e = dec
+        nl = len(self.mask_embed.layers)
+        for i, l in enumerate(self.mask_embed.layers):
+            e = ops.gemm(e, w16(l.weight), bias=bias_of(l), act=ops.ACT_RELU if i < nl - 1 else ops.ACT_NONE)
+        masks = None
+        if want_masks:
+            V, Hm, Wm, Cm = mask_feats.shape
+            masks = torch.empty((V, Q, Hm, Wm), device=output.device, dtype=torch.float32)
+            ops.gemm(mask_feats.view(V * Hm * Wm, Cm), e, out=masks, store_mode=ops.STORE_TRANSPOSED,
+                     rows_per_batch=Hm * Wm, batch_stride=Q * Hm * Wm, ldt=Hm * Wm)
+        bits = None
+        if pooled is not None:
+            nk = pooled.shape[0]
+            small = torch.empty((Q, nk), device=output.device, dtype=torch.float32)
+            ops.gemm(pooled, e, out=small, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=nk, batch_stride=0, ldt=nk)
+            bits = ops.attn_mask_bits(small, nk)
+        return logits, masks, bits
+
+    def _mha(self, q_in, k, v, m: _MHA, mask_bits, residual):
+        """residual + out_proj(attention(q_in Wq^T + bq, k, v));  k, v already projected: (1, Nk, H, hd)."""
+        d, H = self.hidden_dim, self.num_heads
+        wq, bq = self._slice_w(m.in_proj_weight, 0, d, "wq"), self._slice_w(m.in_proj_bias, 0, d, "bq")
+        q = ops.gemm(q_in, wq, bias=bq).view(1, -1, H, d // H)
+        o = ops.attention(q, k, v, mask_bits=mask_bits)
+        return ops.gemm(o.view(-1, d), w16(m.out_proj.weight), bias=bias_of(m.out_proj), residual=residual)
+
+    @torch.no_grad()
+    def forward_nhwc(self, src: torch.Tensor, mask_feats: torch.Tensor, hw, cls_emb: torch.Tensor,
+                     deep_supervision: bool = True):
+        """src bf16 (V*h*w, C) = stride-16 features + level_embed, views flattened view-major (batch 1);
+        mask_feats bf16 (V, Hm, Wm, Cm).  Returns the reference's output dict (batch dim 1)."""
+        h, w = hw
+        d, H, Q = self.hidden_dim, self.num_heads, self.num_queries
+        hd = d // H
+        Nk = src.shape[0]
+        dev = src.device
+        pos = self._pos(h, w, dev)
+        src_pos = ops.add_bcast(src, pos)  # key = memory + pos (pos of view 0 tiled over views, :139-141)
+        wk, bk, wv, bv = self._kv_weights()
+        k_all = ops.gemm(src_pos, wk, bias=bk).view(1, Nk, self.num_layers, H, hd)
+        v_all = ops.gemm(src, wv, bias=bv).view(1, Nk, self.num_layers, H, hd)
+        Vn, Hm, Wm, Cm = mask_feats.shape
+        pooled = ops.center_pool8(mask_feats).view(Vn * (Hm // 8) * (Wm // 8), Cm)
+        qe = b16(self.query_embed.weight)
+        output = b16(self.query_feat.weight)
+        pred_cls, pred_msk = [], []
+        cls, msk, bits = self.prediction_heads(output, mask_feats, pooled, cls_emb, want_masks=deep_supervision)
+        if deep_supervision:
+            pred_cls.append(cls)
+            pred_msk.append(msk)
+        for i in range(self.num_layers):
+            ca, sa, ff = self.cross_attn_layers[i], self.self_attn_layers[i], self.ffn_layers[i]
+            # masked cross-attention (post-norm): tgt = LN(tgt + MHA(tgt + query_pos, memory + pos, memory))
+            t = self._mha(ops.add_bcast(output, qe), k_all[:, :, i], v_all[:, :, i], ca.multihead_attn, bits, output)
+            output = ops.layernorm(t, f32(ca.norm.weight), f32(ca.norm.bias), 1e-5)
+            # self-attention: q = k = tgt + query_pos, v = tgt
+            m = sa.self_attn
+            qk_in = ops.add_bcast(output, qe)
+            kk = ops.gemm(qk_in, self._slice_w(m.in_proj_weight, d, 2 * d, "wk"), bias=self._slice_w(m.in_proj_bias, d, 2 * d, "bk"))
+            vv = ops.gemm(output, self._slice_w(m.in_proj_weight, 2 * d, 3 * d, "wv"), bias=self._slice_w(m.in_proj_bias, 2 * d, 3 * d, "bv"))
+            t = self._mha(qk_in, kk.view(1, Q, H, hd), vv.view(1, Q, H, hd), m, None, output)
+            output = ops.layernorm(t, f32(sa.norm.weight), f32(sa.norm.bias), 1e-5)
+            # FFN
+            hmid = ops.gemm(output, w16(ff.linear1.weight), bias=bias_of(ff.linear1), act=ops.ACT_RELU)
+            t = ops.gemm(hmid, w16(ff.linear2.weight), bias=bias_of(ff.linear2), residual=output)
+            output = ops.layernorm(t, f32(ff.norm.weight), f32(ff.norm.bias), 1e-5)
+            last = i == self.num_layers - 1
+            cls, msk, bits = self.prediction_heads(output, mask_feats, None if last else pooled, cls_emb,
+                                                   want_masks=deep_supervision or last)
+            if deep_supervision or last:
+                pred_cls.append(cls)
+                pred_msk.append(msk)
+        return {
+            "pred_logits": pred_cls[-1][None],
+            "pred_masks": pred_msk[-1][None],
+            "aux_outputs": [{"pred_logits": a[None], "pred_masks": b_[None]} for a, b_ in zip(pred_cls[:-1], pred_msk[:-1])],
+            "out_queries": output.view(Q, 1, d),
+        }
+
+
+class PanopticDecoder(nn.Module):
+    def __init__(self, input_mixer=None, upscaler=None, fpn_dim=[768], hidden_dim=768, mask_dim=256, ff_dim=2048,
+                 num_queries=200, num_heads=8, dec_layers=6, text_encoder="siglip", fixed_vocab=True,
+                 label_mode="sigmoid", two_stage=False, landscape_only=True, deep_supervision=True):
+        super().__init__()
+        assert upscaler is not None, "Upscaler module must be provided"
+        assert label_mode == "sigmoid" and not two_stage
+        self.input_mixer = input_mixer
+        self.upscaler = upscaler
+        self.text_encoder = TextEncoder(text_encoder, out_dim=hidden_dim, fixed_vocab=fixed_vocab)
+        self.label_mode = label_mode
+        self.mask_transformer = MaskTransformer(list(fpn_dim), hidden_dim, ff_dim, mask_dim, num_queries, num_heads,
+                                                dec_layers, lang_dim=self.text_encoder.embed_dim,
+                                                num_feature_levels=len(fpn_dim), landscape_only=landscape_only)
+        self.deep_supervision = deep_supervision
+
+    @torch.no_grad()
+    def forward(self, in_feats, in_imgs, pos, true_shape, classes, max_bs=None, outdevice=None, memory_queries=None,
+                multi_ar=False, cat_feats: Optional[torch.Tensor] = None):
+        """Reference signature (panoptic_decoder.py:41).  in_feats = (x_enc, y_dec, x_dino), each (B, V, N, C_i);
+        `cat_feats`: optional pre-concatenated bf16 (B, V, N, 2816) buffer the producers already wrote into
+        (then in_feats is ignored).  B must be 1 on the CUDA path."""
+        if multi_ar:
+            raise ops._l.Pst3rError("multi aspect-ratio batches are not implemented on the CUDA path yet")
+        if cat_feats is None:
+            # producers that did not write into a shared buffer: concatenate (pure data movement)
+            parts = [t if t.dtype == torch.bfloat16 else ops.to_bf16(t.float().contiguous()) for t in in_feats]
+            cat_feats = torch.cat(parts, dim=-1)
+        B, V, N, Cc = cat_feats.shape
+        if B != 1:
+            raise ops._l.Pst3rError("CUDA PanopticDecoder supports batch size 1 (one scene per call)")
+        H, W = _hw(true_shape)
+        P = self.upscaler.patch_size
+        hs, ws = H // P, W // P
+        dev = cat_feats.device
+        x = cat_feats.reshape(V * N, Cc)
+        if self.input_mixer is not None:
+            x = self.input_mixer.forward_rows(x, V, hs, ws)
+        mt = self.mask_transformer
+        src, mask_f = self.upscaler.forward_nhwc(x, V, hs, ws, f16_extra_bias=mt.level_embed.weight) \
+            if isinstance(self.upscaler, PixelShuffleUpscaler) else \
+            self.upscaler.forward_nhwc(x, in_imgs.reshape(V, 3, H, W), V, hs, ws, f16_extra_bias=mt.level_embed.weight)
+        cls_emb = self.text_encoder(classes, device=dev)
+        if memory_queries is None:
+            out = mt.forward_nhwc(src, mask_f, (hs, ws), cls_emb, deep_supervision=self.deep_supervision)
+        else:
+            q = memory_queries.reshape(mt.num_queries, mt.hidden_dim)
+            q = q if q.dtype == torch.bfloat16 else ops.to_bf16(q.float().contiguous())
+            logits, masks, _ = mt.prediction_heads(q, mask_f, None, cls_emb, want_masks=True)
+            out = {"pred_logits": logits[None], "pred_masks": masks[None]}
+        if outdevice is not None and torch.device(outdevice) != dev:
+            out = {k: (v.to(outdevice) if torch.is_tensor(v) else
+                       [{kk: vv.to(outdevice) for kk, vv in a.items()} for a in v]) for k, v in out.items()}
+        return out

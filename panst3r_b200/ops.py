@@ -60,8 +60,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
          store_mode: int = STORE_PLAIN, rows_per_batch: int = 0, batch_stride: int = 0, ldt: int = 0,
          grid: Tuple[int, int] = (0, 0), d2s: Tuple[int, int] = (0, 0),
-         rope: Optional[Tuple[torch.Tensor, torch.Tensor, int]] = None) -> torch.Tensor:
-    """out = epilogue(a @ w.T).  a: bf16 [..., K] (row-strided), w: bf16 [N, K]."""
+         rope: Optional[Tuple[torch.Tensor, torch.Tensor, int]] = None, res_mod_rows: int = 0,
+         out_ld: int = 0) -> torch.Tensor:
+    """out = epilogue(a @ w.T).  a: bf16 [..., K] (row-strided), w: bf16 [N, K].
+    PLAIN store with rows_per_batch > 0: `out` is only a base pointer, rows are remapped (pass out_ld)."""
     global launches
     lib = _l.load()
     _need(a, torch.bfloat16, "gemm.a")
@@ -71,7 +73,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     if K != K2:
         raise _l.Pst3rError(f"gemm: K mismatch {K} vs {K2}")
     e = _l.GemmEpilogue()
-    if store_mode == STORE_PLAIN:
+    if store_mode == STORE_PLAIN and rows_per_batch > 0:
+        if out is None or out_ld <= 0:
+            raise _l.Pst3rError("gemm: remapped PLAIN store needs out and out_ld")
+        e.ldo = out_ld
+    elif store_mode == STORE_PLAIN:
         if out is None:
             out = torch.empty((*a.shape[:-1], N), device=a.device, dtype=out_dtype)
         _, oc, ldo = _rows2d(out, "gemm.out")
@@ -98,6 +104,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         _, _, ldr = _rows2d(residual, "gemm.residual")
         e.residual = residual.data_ptr()
         e.ldr = ldr
+        e.res_mod_rows = res_mod_rows
     e.alpha = alpha
     e.store_mode = store_mode
     e.rows_per_batch, e.batch_stride, e.ldt = rows_per_batch, batch_stride, ldt
@@ -158,7 +165,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optio
             raise _l.Pst3rError("attention.mask_bits: expected int32 [B or 1, Nq, W]")
         a.mask_bits = mask_bits.data_ptr()
         a.mask_sb = 0 if mask_bits.shape[0] == 1 else mask_bits.stride(0)
-        a.mask_sq = mask_bits.stride(1)
+        a.mask_sq = 0 if (mask_bits.shape[1] == 1 and Nq > 1) else mask_bits.stride(1)  # one row for all queries
     splits = kv_splits if kv_splits > 0 else lib.pst3r_attention_auto_splits(B, H, Nq, Nk)
     a.kv_splits = splits
     need = lib.pst3r_attention_workspace_bytes(B, H, Nq, hd, splits)
@@ -172,12 +179,20 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optio
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
               add: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-              out_dtype: torch.dtype = torch.bfloat16, sum_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out_dtype: torch.dtype = torch.bfloat16, sum_out: Optional[torch.Tensor] = None,
+              x_rows: Optional[Tuple[int, int, int, int, int]] = None) -> torch.Tensor:
+    """x_rows = (rows, dim, ldx, rows_per_batch, batch_stride): x is only a base pointer with remapped rows."""
     global launches
     lib = _l.load()
     if x.dtype not in (torch.bfloat16, torch.float32) or not x.is_cuda:
         raise _l.Pst3rError("layernorm.x: expected CUDA bf16/fp32")
-    rows, dim, ldx = _rows2d(x, "layernorm.x")
+    x_rpb, x_bs = 0, 0
+    if x_rows is not None:
+        rows, dim, ldx, x_rpb, x_bs = x_rows
+        if out is None:
+            raise _l.Pst3rError("layernorm: remapped input needs out")
+    else:
+        rows, dim, ldx = _rows2d(x, "layernorm.x")
     _need(gamma, torch.float32, "layernorm.gamma")
     _need(beta, torch.float32, "layernorm.beta")
     if out is None:
@@ -193,7 +208,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         _, _, ld_sum = _rows2d(sum_out, "layernorm.sum_out")
     _l.check(lib.pst3r_layernorm(x.data_ptr(), int(x.dtype == torch.float32), ldx, _ptr(add), ld_add, gamma.data_ptr(),
                                  beta.data_ptr(), eps, out.data_ptr(), int(out.dtype == torch.float32), ldy,
-                                 _ptr(sum_out), ld_sum, rows, dim, _stream()), "pst3r_layernorm")
+                                 _ptr(sum_out), ld_sum, rows, dim, x_rpb, x_bs, _stream()), "pst3r_layernorm")
     launches += 1
     return out
 

@@ -1,0 +1,205 @@
+"""PanSt3R façade on the CUDA modules — same surface as the reference's `PanSt3R(nn.Module)`
+(reference src/panst3r/panst3r.py:19-325): constructor arguments, the four sub-module attribute names
+(= state-dict prefixes), `forward`, `forward_inference_multi_ar`, `set_vocab`, `from_checkpoint`.
+
+    forward(imgs, true_shape, classes, max_bs=None, outdevice=None) -> (panout, pointmaps)          (:286-296)
+    forward_inference_multi_ar(imgs, true_shape, classes, num_keyframes=None, use_retrieval=False,
+                               max_bs=None, outdevice=None, amp=False) -> (pointmaps, panout)       (:169-284)
+
+Orchestration follows engine/must3r.py:28-69 (sequential memory build, mem_batches [2,1,1,...]) and :71-94
+(render of every view against the final memory).  B200-first choices: the three feature producers write straight
+into one (V, N, 2816) bf16 buffer (the torch.cat at panoptic_decoder.py:44-47 disappears), DINOv2 runs on a side
+stream concurrently with the MUSt3R encoder/decoder, `max_bs` chunking is unnecessary (everything is one batch,
+results are chunk-invariant for v1) and accepted only for signature parity.
+Multi-GPU: see panst3r_b200/dist.py (views sharded across ranks, one all-gather of encoder tokens).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .modules.dino import DinoV2Encoder
+from .modules.must3r import MUSt3R, Dust3rEncoder
+from .modules.panoptic import PanopticDecoder, PixelShuffleUpscaler
+
+ENC_DIM, DEC_DIM, DINO_DIM = 1024, 768, 1024
+
+
+class PanSt3R(nn.Module):
+    def __init__(self, must3r_encoder: nn.Module, must3r_decoder: nn.Module, dino_encoder: nn.Module,
+                 panoptic_decoder: nn.Module, retrieval=None, preserve_gpu_mem: bool = False,
+                 postprocess_default: str = "standard_v2", qubo_enabled: bool = True,
+                 must3r_encoder_requires_grad=False, must3r_decoder_requires_grad=False, verbose: bool = False):
+        super().__init__()
+        self.must3r_encoder = must3r_encoder
+        self.must3r_decoder = must3r_decoder
+        self.dino_encoder = dino_encoder
+        self.panoptic_decoder = panoptic_decoder
+        self.retrieval = retrieval
+        self.preserve_gpu_mem = preserve_gpu_mem
+        self.verbose = verbose
+        self.must3r_params = dict(init_num_views=2, batch_num_views=1, render_iterations=1)
+        self.postprocess_default = postprocess_default
+        self.qubo_enabled = qubo_enabled
+        self.overlap_dino = True
+        self._side_stream: Optional[torch.cuda.Stream] = None
+
+    # ---- reference helper methods ----------------------------------------------------------------
+    def get_must3r_mem_batches(self, n_imgs):
+        mem_batches = [self.must3r_params["init_num_views"]]
+        while (s := sum(mem_batches)) != n_imgs:
+            mem_batches.append(min(self.must3r_params["batch_num_views"], n_imgs - s))
+        return mem_batches
+
+    def forward_dino(self, imgs, true_shape, max_bs=None, verbose=None, out=None):
+        B, V = imgs.shape[:2]
+        x = self.dino_encoder(imgs.flatten(0, 1), true_shape.flatten(0, 1), out=out)
+        return x.unflatten(0, (B, V))
+
+    def forward_must3r_encoder(self, imgs, true_shape, max_bs=None, out=None):
+        B, V = imgs.shape[:2]
+        x, pos = self.must3r_encoder(imgs.flatten(0, 1), true_shape.flatten(0, 1), out=out)
+        return x.unflatten(0, (B, V)), pos.unflatten(0, (B, V))
+
+    def build_memory(self, x, pos, true_shape):
+        """engine/must3r.py:28-69 — V-1 dependent decoder passes; first-pass pointmaps are discarded by the caller
+        (panst3r.py:77) so they are not computed."""
+        self.must3r_decoder.reserve_views = x.shape[1]
+        edges = [0] + np.cumsum(self.get_must3r_mem_batches(x.shape[1])).tolist()
+        mem = None
+        for a, b in zip(edges[:-1], edges[1:]):
+            mem, _, _ = self.must3r_decoder(x[:, a:b], pos[:, a:b], true_shape[:, a:b], mem, render=False,
+                                            return_feats=False, compute_pointmaps=False)
+        return mem
+
+    def forward_must3r_decoder(self, x_must3r, pos_must3r, true_shape, max_bs=None, feats_out=None):
+        mem = self.build_memory(x_must3r, pos_must3r, true_shape)
+        _, pointmaps, feats = self.must3r_decoder(x_must3r, pos_must3r, true_shape, mem, render=True,
+                                                  return_feats="last", feats_out=feats_out)
+        return feats[-1], pointmaps, mem
+
+    # ---- shared core -----------------------------------------------------------------------------
+    def _features(self, imgs, true_shape):
+        """Run DINOv2 (side stream) + MUSt3R encoder into one concatenated (B, V, N, 2816) bf16 buffer."""
+        B, V, _, H, W = imgs.shape
+        if B != 1:
+            raise ops._l.Pst3rError("the CUDA path processes one scene per call (B == 1)")
+        P = self.must3r_encoder.patch_size
+        N = (H // P) * (W // P)
+        cat = torch.empty((B, V, N, ENC_DIM + DEC_DIM + DINO_DIM), device=imgs.device, dtype=torch.bfloat16)
+        rows = cat.view(B * V * N, -1)
+        cur = torch.cuda.current_stream()
+        if self.overlap_dino and not torch.cuda.is_current_stream_capturing():
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self.forward_dino(imgs, true_shape, out=rows[:, ENC_DIM + DEC_DIM:])
+            x, pos = self.forward_must3r_encoder(imgs, true_shape, out=rows[:, :ENC_DIM])
+            join = side
+        else:
+            self.forward_dino(imgs, true_shape, out=rows[:, ENC_DIM + DEC_DIM:])
+            x, pos = self.forward_must3r_encoder(imgs, true_shape, out=rows[:, :ENC_DIM])
+            join = None
+        return cat, rows, x, pos, join
+
+    @torch.no_grad()
+    def forward(self, imgs, true_shape, classes, max_bs=None, outdevice=None):
+        """imgs fp32 (1, V, 3, H, W) in [-1, 1] on CUDA; true_shape (1, V, 2) (H, W); returns (panout, pointmaps)."""
+        ts = true_shape.cpu() if true_shape.is_cuda else true_shape
+        cat, rows, x, pos, join = self._features(imgs, ts)
+        _, pointmaps, _ = self.forward_must3r_decoder(x, pos, ts, feats_out=rows[:, ENC_DIM:ENC_DIM + DEC_DIM])
+        if join is not None:
+            torch.cuda.current_stream().wait_stream(join)
+        panout = self.panoptic_decoder(None, imgs, pos, ts, classes, outdevice=outdevice, cat_feats=cat)
+        if outdevice is not None:
+            pointmaps = pointmaps.to(outdevice)
+        return panout, pointmaps
+
+    @torch.no_grad()
+    def forward_inference_multi_ar(self, imgs: List[torch.Tensor], true_shape, classes, num_keyframes=None,
+                                   use_retrieval=False, max_bs=None, outdevice=None, amp=False):
+        """Keyframes build the memory and run the full panoptic head; the remaining frames are rendered against the
+        frozen memory and decoded with the keyframes' final queries (panst3r.py:254-277, panoptic_decoder.py:70-76).
+        All images must share one shape on the CUDA path (single aspect ratio)."""
+        if use_retrieval:
+            raise NotImplementedError("retrieval keyframe selection needs asmk + a retrieval checkpoint (out of scope)")
+        N = len(imgs)
+        if num_keyframes is None or num_keyframes > N:
+            num_keyframes = N
+            keyframes = list(range(N))
+        else:
+            keyframes = np.linspace(0, N - 1, num_keyframes, dtype=int).tolist()
+        not_keyframes = sorted(set(range(N)).difference(set(keyframes)))
+        assert len(keyframes) + len(not_keyframes) == N
+        order = keyframes + not_keyframes
+        ts_all = (true_shape.cpu() if true_shape.is_cuda else true_shape)[order][None]
+        im = torch.stack([imgs[i] for i in order])[None]
+        k = num_keyframes
+        cat, rows, x, pos, join = self._features(im, ts_all)
+        Ntok = x.shape[2]
+        mem = self.build_memory(x[:, :k], pos[:, :k], ts_all[:, :k])
+        # render keyframes and the rest in one batch against the final memory (identical per-view results)
+        _, pointmaps, _ = self.must3r_decoder(x, pos, ts_all, mem, render=True, return_feats="last",
+                                              feats_out=rows[:, ENC_DIM:ENC_DIM + DEC_DIM])
+        if join is not None:
+            torch.cuda.current_stream().wait_stream(join)
+        pan_kf = self.panoptic_decoder(None, im[:, :k], pos[:, :k], ts_all[:, :k], classes, cat_feats=cat[:, :k])
+        masks = list(pan_kf["pred_masks"][0])
+        if N > k:
+            pan_nk = self.panoptic_decoder(None, im[:, k:], pos[:, k:], ts_all[:, k:], classes, cat_feats=cat[:, k:],
+                                           memory_queries=pan_kf["out_queries"])
+            masks += list(pan_nk["pred_masks"][0])
+        pms = list(pointmaps[0])
+        inv = np.argsort(order)
+        panout = {"pred_logits": pan_kf["pred_logits"], "pred_masks": [masks[i] for i in inv],
+                  "out_queries": pan_kf["out_queries"]}
+        pms = [pms[i] for i in inv]
+        if outdevice is not None:
+            pms = [p.to(outdevice) for p in pms]
+            panout["pred_masks"] = [m.to(outdevice) for m in panout["pred_masks"]]
+        return pms, panout
+
+    def set_vocab(self, class_names, device=None):
+        self.panoptic_decoder.text_encoder.set_vocab(class_names, device=device)
+
+    @classmethod
+    def from_checkpoint(cls, checkpoint_path, retrieval_path=None):
+        """Loads the reference's checkpoint format: {'args': Namespace of constructor strings, 'weights': state dict}
+        (panst3r.py:301-325).  The constructor strings are evaluated against this package's CUDA classes."""
+        ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+        assert "args" in ckpt, "Checkpoint must contain 'args' with model parameters."
+        from .modules import panoptic as _p
+        ns = {"Dust3rEncoder": Dust3rEncoder, "MUSt3R": MUSt3R, "DinoV2Encoder": DinoV2Encoder,
+              "PanopticDecoder": PanopticDecoder, "PixelShuffleUpscaler": PixelShuffleUpscaler}
+        for extra in ("InputMixer", "LoftUpUpscaler"):
+            if hasattr(_p, extra):
+                ns[extra] = getattr(_p, extra)
+        a = ckpt["args"]
+        get = (lambda k: a[k]) if isinstance(a, dict) else (lambda k: getattr(a, k))
+        model = cls(must3r_encoder=eval(get("must3r_encoder"), ns), must3r_decoder=eval(get("must3r_decoder"), ns),
+                    dino_encoder=eval(get("dino_encoder"), ns), panoptic_decoder=eval(get("panoptic_decoder"), ns),
+                    retrieval=ckpt.get("retrieval"))
+        model.load_state_dict(ckpt["weights"], strict=False)
+        return model
+
+
+def build_panst3r(variant: str = "v1", enc_depth=24, dec_depth=12, dino_depth=24, mixer_layers=3) -> PanSt3R:
+    """Reference configuration (configs/base.yaml, base_v2.yaml) with reducible depths for tests."""
+    enc = Dust3rEncoder(depth=enc_depth)
+    dec = MUSt3R(depth=dec_depth)
+    dino = DinoV2Encoder(depth=dino_depth)
+    if variant == "v1":
+        pd = PanopticDecoder(upscaler=PixelShuffleUpscaler(input_dim=ENC_DIM + DEC_DIM + DINO_DIM))
+    elif variant == "v2":
+        from .modules.panoptic import InputMixer, LoftUpUpscaler
+        pd = PanopticDecoder(input_mixer=InputMixer([512, 512], 16, 2816, 768, num_layers=mixer_layers),
+                             upscaler=LoftUpUpscaler(input_dim=768, dim=384), mask_dim=384)
+    else:
+        raise ValueError(variant)
+    return PanSt3R(enc, dec, dino, pd).eval()
