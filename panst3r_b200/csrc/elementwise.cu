@@ -54,6 +54,93 @@ __global__ void layernorm_kernel(const void* __restrict__ x, long long ldx, cons
   }
 }
 
+// Fast path: bf16 rows with dim % 8 == 0 and dim <= VPL*256.  One warp per row; the row lives in registers
+// (VPL 16-byte vectors per lane), so HBM sees exactly one read and one write per element.
+template <int VPL, bool Y_F32>
+__global__ void __launch_bounds__(256)
+layernorm_vec_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ add, long long ld_add,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, void* __restrict__ y,
+                     long long ldy, bf16* __restrict__ sum_out, long long ld_sum, int rows, int dim, int x_rpb,
+                     long long x_bs) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = dim >> 3;
+  const long long xo = x_rpb > 0 ? (long long)(row / x_rpb) * x_bs + (long long)(row % x_rpb) * ldx : (long long)row * ldx;
+  const uint4* xp = reinterpret_cast<const uint4*>(x + xo);
+  const uint4* ap = add ? reinterpret_cast<const uint4*>(add + (long long)row * ld_add) : nullptr;
+  float v[VPL][8];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      const uint4 u = __ldg(xp + vi);
+      float2 f;
+      f = unpack_bf16x2(u.x); v[i][0] = f.x; v[i][1] = f.y;
+      f = unpack_bf16x2(u.y); v[i][2] = f.x; v[i][3] = f.y;
+      f = unpack_bf16x2(u.z); v[i][4] = f.x; v[i][5] = f.y;
+      f = unpack_bf16x2(u.w); v[i][6] = f.x; v[i][7] = f.y;
+      if (ap) {
+        const uint4 a = __ldg(ap + vi);
+        f = unpack_bf16x2(a.x); v[i][0] += f.x; v[i][1] += f.y;
+        f = unpack_bf16x2(a.y); v[i][2] += f.x; v[i][3] += f.y;
+        f = unpack_bf16x2(a.z); v[i][4] += f.x; v[i][5] += f.y;
+        f = unpack_bf16x2(a.w); v[i][6] += f.x; v[i][7] += f.y;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[i][k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[i][k] = 0.0f;
+    }
+  }
+  const float mean = warp_sum(s) / dim;
+  float ss = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = v[i][k] - mean;
+        ss += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / dim + eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      if (sum_out) {
+        uint4 u;
+        u.x = pack_bf16x2(v[i][0], v[i][1]); u.y = pack_bf16x2(v[i][2], v[i][3]);
+        u.z = pack_bf16x2(v[i][4], v[i][5]); u.w = pack_bf16x2(v[i][6], v[i][7]);
+        reinterpret_cast<uint4*>(sum_out + (long long)row * ld_sum)[vi] = u;
+      }
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi + 1);
+      float o[8];
+      o[0] = (v[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[i][1] - mean) * rstd * g0.y + b0.y;
+      o[2] = (v[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[i][3] - mean) * rstd * g0.w + b0.w;
+      o[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
+      o[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
+      if (Y_F32) {
+        float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (long long)row * ldy) + 2 * vi;
+        yp[0] = make_float4(o[0], o[1], o[2], o[3]);
+        yp[1] = make_float4(o[4], o[5], o[6], o[7]);
+      } else {
+        uint4 u;
+        u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+        u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+        reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(y) + (long long)row * ldy)[vi] = u;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 2-D RoPE (curope semantics), in place.  One thread per (token, head, pair).
 // ------------------------------------------------------------------------------------------------
@@ -300,6 +387,28 @@ extern "C" int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const 
   const unsigned grid = blocks_for(rows, wpb);
   const bf16* a = reinterpret_cast<const bf16*>(add);
   bf16* so = reinterpret_cast<bf16*>(sum_out);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec_ok = !x_f32 && (dim % 8) == 0 && dim <= 12 * 256 && (ldx % 8) == 0 && (x_bs % 8) == 0 && al16(x) &&
+                      (!add || ((ld_add % 8) == 0 && al16(add))) && (!sum_out || ((ld_sum % 8) == 0 && al16(sum_out))) &&
+                      al16(y) && (ldy % (y_f32 ? 4 : 8)) == 0 && al16(gamma) && al16(beta);
+  if (vec_ok) {
+    const int vpl = (dim / 8 + 31) / 32;
+    const bf16* xb = reinterpret_cast<const bf16*>(x);
+#define PST3R_LN_CASE(V)                                                                                              \
+  if (y_f32)                                                                                                          \
+    layernorm_vec_kernel<V, true><<<grid, wpb * 32, 0, s>>>(xb, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, \
+                                                             rows, dim, x_rpb, x_bs);                                  \
+  else                                                                                                                \
+    layernorm_vec_kernel<V, false><<<grid, wpb * 32, 0, s>>>(xb, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, \
+                                                              rows, dim, x_rpb, x_bs);
+    if (vpl <= 2) { PST3R_LN_CASE(2) }
+    else if (vpl <= 4) { PST3R_LN_CASE(4) }
+    else if (vpl <= 8) { PST3R_LN_CASE(8) }
+    else { PST3R_LN_CASE(12) }
+#undef PST3R_LN_CASE
+    PST3R_CHECK_CUDA(cudaGetLastError());
+    return PST3R_OK;
+  }
   if (x_f32 && y_f32)
     layernorm_kernel<true, true><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs);
   else if (x_f32)

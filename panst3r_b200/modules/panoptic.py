@@ -245,9 +245,11 @@ class MaskTransformer(nn.Module):
 
     @torch.no_grad()
     def forward_nhwc(self, src: torch.Tensor, mask_feats: torch.Tensor, hw, cls_emb: torch.Tensor,
-                     deep_supervision: bool = True):
+                     deep_supervision: bool = True, pooled: Optional[torch.Tensor] = None):
         """src bf16 (V*h*w, C) = stride-16 features + level_embed, views flattened view-major (batch 1);
-        mask_feats bf16 (V, Hm, Wm, Cm).  Returns the reference's output dict (batch dim 1)."""
+        mask_feats bf16 (V', Hm, Wm, Cm) — the views whose full-resolution masks this call produces (all V, or this
+        rank's shard); pooled bf16 (V*h*w, Cm): centre-pooled mask features of ALL views (computed from mask_feats
+        when omitted).  Returns the reference's output dict (batch dim 1)."""
         h, w = hw
         d, H, Q = self.hidden_dim, self.num_heads, self.num_queries
         hd = d // H
@@ -259,7 +261,8 @@ class MaskTransformer(nn.Module):
         k_all = ops.gemm(src_pos, wk, bias=bk).view(1, Nk, self.num_layers, H, hd)
         v_all = ops.gemm(src, wv, bias=bv).view(1, Nk, self.num_layers, H, hd)
         Vn, Hm, Wm, Cm = mask_feats.shape
-        pooled = ops.center_pool8(mask_feats).view(Vn * (Hm // 8) * (Wm // 8), Cm)
+        if pooled is None:
+            pooled = ops.center_pool8(mask_feats).view(Vn * (Hm // 8) * (Wm // 8), Cm)
         qe = b16(self.query_embed.weight)
         output = b16(self.query_feat.weight)
         pred_cls, pred_msk = [], []

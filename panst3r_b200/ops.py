@@ -351,3 +351,74 @@ def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
     _l.check(lib.pst3r_nhwc_to_nchw_f32(x.data_ptr(), B, HW, Cc, out.data_ptr(), _stream()), "pst3r_nhwc_to_nchw_f32")
     launches += 1
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Per-kernel-kind profiler (CUDA events on the launching stream around every C-ABI call).  Used by bench.py
+# to find the dominant kernel of a step; never active inside a timed region.
+# ---------------------------------------------------------------------------------------------------
+class _Profiler:
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for kind, e0, e1 in self.records:
+            d = agg.setdefault(kind, {"ms": 0.0, "calls": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["calls"] += 1
+        total = sum(d["ms"] for d in agg.values()) or 1.0
+        for d in agg.values():
+            d["share"] = d["ms"] / total
+            d["ms"] = round(d["ms"], 4)
+        return dict(sorted(agg.items(), key=lambda kv: -kv[1]["ms"]))
+
+
+_prof: Optional[_Profiler] = None
+
+
+class profiler:
+    def __enter__(self):
+        global _prof
+        _prof = _Profiler()
+        return _prof
+
+    def __exit__(self, *exc):
+        global _prof
+        _prof = None
+        return False
+
+
+def _wrap(fn, kind_of):
+    import functools
+
+    @functools.wraps(fn)
+    def inner(*a, **k):
+        if _prof is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **k)
+        e1.record()
+        _prof.records.append((kind_of(a, k), e0, e1))
+        return r
+    return inner
+
+
+def _gemm_kind(a, k):
+    sm = k.get("store_mode", STORE_PLAIN)
+    return "gemm" + {STORE_PLAIN: "", STORE_TRANSPOSED: "_transposed_store", STORE_PIXSHUF2: "_pixshuf_store", STORE_D2S: "_d2s_store"}[sm]
+
+
+def _attn_kind(a, k):
+    q, kk = a[0], a[1]
+    return f"attention_hd{q.shape[-1]}" + ("_masked" if k.get("mask_bits") is not None else "") + \
+        ("_mem" if kk.shape[1] > 2 * q.shape[1] else "")
+
+
+gemm = _wrap(gemm, _gemm_kind)
+attention = _wrap(attention, _attn_kind)
+for _n in ("layernorm", "rope2d_", "add_bcast", "to_bf16", "to_f32", "patchify", "dino_preprocess_patchify", "center_pool8",
+           "attn_mask_bits", "l2norm_rows", "nhwc_to_nchw_f32"):
+    globals()[_n] = _wrap(globals()[_n], (lambda name: (lambda a, k: name))(_n))

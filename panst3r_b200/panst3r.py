@@ -86,6 +86,9 @@ class PanSt3R(nn.Module):
     def _features(self, imgs, true_shape):
         """Run DINOv2 (side stream) + MUSt3R encoder into one concatenated (B, V, N, 2816) bf16 buffer."""
         B, V, _, H, W = imgs.shape
+        if not imgs.is_cuda or not next(self.parameters()).is_cuda:
+            raise ops._l.Pst3rError("PanSt3R (panst3r_b200) runs on CUDA sm_100 only: move the module and inputs to the "
+                                    "GPU; there is no CPU fallback")
         if B != 1:
             raise ops._l.Pst3rError("the CUDA path processes one scene per call (B == 1)")
         P = self.must3r_encoder.patch_size
