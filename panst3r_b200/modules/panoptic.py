@@ -245,7 +245,8 @@ class MaskTransformer(nn.Module):
 
     @torch.no_grad()
     def forward_nhwc(self, src: torch.Tensor, mask_feats: torch.Tensor, hw, cls_emb: torch.Tensor,
-                     deep_supervision: bool = True, pooled: Optional[torch.Tensor] = None):
+                     deep_supervision: bool = True, pooled: Optional[torch.Tensor] = None,
+                     mask_override: Optional[List[torch.Tensor]] = None):
         """src bf16 (V*h*w, C) = stride-16 features + level_embed, views flattened view-major (batch 1);
         mask_feats bf16 (V', Hm, Wm, Cm) — the views whose full-resolution masks this call produces (all V, or this
         rank's shard); pooled bf16 (V*h*w, Cm): centre-pooled mask features of ALL views (computed from mask_feats
@@ -273,6 +274,8 @@ class MaskTransformer(nn.Module):
         for i in range(self.num_layers):
             ca, sa, ff = self.cross_attn_layers[i], self.self_attn_layers[i], self.ffn_layers[i]
             # masked cross-attention (post-norm): tgt = LN(tgt + MHA(tgt + query_pos, memory + pos, memory))
+            if mask_override is not None:  # test hook: force the block mask of layer i (isolates threshold flips)
+                bits = mask_override[i]
             t = self._mha(ops.add_bcast(output, qe), k_all[:, :, i], v_all[:, :, i], ca.multihead_attn, bits, output)
             output = ops.layernorm(t, f32(ca.norm.weight), f32(ca.norm.bias), 1e-5)
             # self-attention: q = k = tgt + query_pos, v = tgt

@@ -1,0 +1,297 @@
+"""GPU parity tests of every C-ABI kernel against a plain PyTorch fp32 statement of the same op (same bf16-rounded
+inputs).  Tolerances: fp32 outputs 1e-3 of the output max (north-star tolerance; observed ~1e-6); bf16 outputs one
+bf16 ulp of the output max (2^-8 = 3.9e-3); attention 4e-3 (bf16 probabilities feed the tensor core)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-3
+TOL_BF16 = 4e-3
+TOL_ATTN = 4e-3
+
+
+def rnd(*shape, scale=1.0, dtype=torch.bfloat16):
+    return (torch.randn(*shape, device="cuda") * scale).to(dtype)
+
+
+def relmax(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from panst3r_b200 import lib, ops as o
+    assert lib.load().pst3r_check_device() == 0, lib.load().pst3r_last_error()
+    torch.manual_seed(0)
+    return o
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (300, 200, 96), (1, 8, 8), (1000, 3072, 1024),
+                                   (768, 768, 3072), (200, 768, 768), (12288, 1024, 1024), (130, 72, 2816), (129, 264, 72)])
+def test_gemm_shapes(ops, M, N, K):
+    a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    ref = a.float() @ w.float().t() + bias
+    assert relmax(ops.gemm(a, w, bias=bias, out_dtype=torch.float32), ref) < TOL_F32
+    assert relmax(ops.gemm(a, w, bias=bias), ref) < TOL_BF16
+
+
+def test_gemm_epilogues(ops):
+    M, N, K = 512, 1024, 512
+    a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    bias, ls, res = torch.randn(N, device="cuda"), torch.randn(N, device="cuda"), rnd(M, N)
+    y = a.float() @ w.float().t() + bias
+    assert relmax(ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, out_dtype=torch.float32), torch.nn.functional.gelu(y)) < TOL_F32
+    assert relmax(ops.gemm(a, w, bias=bias, act=ops.ACT_RELU, out_dtype=torch.float32), torch.relu(y)) < TOL_F32
+    assert relmax(ops.gemm(a, w, bias=bias, col_scale=ls, residual=res, out_dtype=torch.float32), y * ls + res.float()) < TOL_F32
+    assert relmax(ops.gemm(a, w, alpha=0.37, out_dtype=torch.float32), 0.37 * (a.float() @ w.float().t())) < TOL_F32
+    # in-place residual (out aliases residual), broadcast residual rows, strided operands
+    x = rnd(M, N)
+    ref = y + x.float()
+    ops.gemm(a, w, bias=bias, residual=x, out=x)
+    assert relmax(x, ref) < TOL_BF16
+    pe = rnd(128, N)
+    got = ops.gemm(a, w, residual=pe, res_mod_rows=128, out_dtype=torch.float32)
+    assert relmax(got, a.float() @ w.float().t() + pe.float().repeat(M // 128, 1)) < TOL_F32
+    big = rnd(M, 2 * K)
+    outbuf = torch.zeros(M, 2 * N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(big[:, K:], w, out=outbuf[:, N:])
+    assert relmax(outbuf[:, N:], big[:, K:].float() @ w.float().t()) < TOL_BF16
+    assert outbuf[:, :N].abs().max().item() == 0
+
+
+def test_gemm_row_remap_store(ops):
+    b, N, T, D, K = 3, 10, 11, 64, 64
+    a, w = rnd(b * N, K), rnd(D, K)
+    x = torch.zeros(b, T, D, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out=x[:, 1:], rows_per_batch=N, batch_stride=T * D, out_ld=D)
+    ref = (a.float() @ w.float().t()).view(b, N, D)
+    assert relmax(x[:, 1:], ref) < TOL_BF16 and x[:, 0].abs().max().item() == 0
+
+
+def test_gemm_mask_einsum_store(ops):
+    """torch.einsum('bqc,bnchw->bnqhw') (mask_transformer.py:280) as pixels x queries GEMM with plane-major store."""
+    V, Hm, Wm, Q, Cm = 2, 24, 64, 200, 256
+    feats = rnd(V, Hm, Wm, Cm)
+    emb = rnd(Q, Cm, scale=Cm ** -0.5)
+    out = torch.empty(V, Q, Hm, Wm, device="cuda", dtype=torch.float32)
+    ops.gemm(feats.view(-1, Cm), emb, out=out, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=Hm * Wm,
+             batch_stride=Q * Hm * Wm, ldt=Hm * Wm)
+    ref = torch.einsum("bqc,bnchw->bnqhw", emb.float()[None], feats.float().permute(0, 3, 1, 2)[None])[0]
+    assert relmax(out, ref) < TOL_F32
+
+
+def test_gemm_pixel_shuffle_and_d2s_stores(ops):
+    B, gh, gw, Cout = 2, 6, 8, 64
+    a = rnd(B * gh * gw, 128)
+    w = rnd(Cout * 4, 128, scale=128 ** -0.5)
+    out = torch.empty(B * 2 * gh * 2 * gw, Cout, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out=out, store_mode=ops.STORE_PIXSHUF2, grid=(gh, gw))
+    y = (a.float() @ w.float().t()).view(B, gh, gw, Cout * 4).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.pixel_shuffle(y, 2).permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert relmax(out, ref) < TOL_BF16
+    P, Cc = 16, 7
+    a = rnd(B * gh * gw, 768)
+    w_ref = rnd(Cc * P * P, 768, scale=768 ** -0.5)
+    b_ref = torch.randn(Cc * P * P, device="cuda")
+    w_perm = w_ref.view(Cc, P, P, 768).permute(1, 2, 0, 3).reshape(P * P * Cc, 768).contiguous()
+    b_perm = b_ref.view(Cc, P, P).permute(1, 2, 0).reshape(-1).contiguous()
+    out = torch.empty(B, gh * P, gw * P, Cc, device="cuda", dtype=torch.float32)
+    ops.gemm(a, w_perm, bias=b_perm, out=out, store_mode=ops.STORE_D2S, grid=(gh, gw), d2s=(P, Cc))
+    y = (a.float() @ w_ref.float().t() + b_ref).view(B, gh, gw, Cc * P * P).permute(0, 3, 1, 2)
+    assert relmax(out, torch.nn.functional.pixel_shuffle(y, P).permute(0, 2, 3, 1)) < TOL_F32
+
+
+def rope_ref(t, pos, base=100.0):
+    B, N, H, D = t.shape
+    Q = D // 4
+    inv = base ** (-torch.arange(Q, device=t.device, dtype=torch.float32) / Q)
+    out = t.clone()
+    for half in range(2):
+        ang = pos[..., half].float()[..., None] * inv
+        c, s = ang.cos()[:, :, None, :], ang.sin()[:, :, None, :]
+        lo = half * D // 2
+        u, v = t[..., lo:lo + Q], t[..., lo + Q:lo + 2 * Q]
+        out[..., lo:lo + Q] = u * c - v * s
+        out[..., lo + Q:lo + 2 * Q] = v * c + u * s
+    return out
+
+
+def test_rope_standalone_and_fused(ops):
+    B, N, H, D = 2, 48, 12, 64
+    t = rnd(B, N, H, D)
+    ys, xs = torch.meshgrid(torch.arange(6), torch.arange(8), indexing="ij")
+    pos = torch.stack([ys.flatten(), xs.flatten()], -1)[None].expand(B, -1, -1).contiguous().to("cuda", torch.int32)
+    assert relmax(ops.rope2d_(t.clone(), pos), rope_ref(t.float(), pos)) < TOL_BF16
+    back = ops.rope2d_(ops.rope2d_(t.clone(), pos), pos, fwd=-1.0)  # inverse rotation (curope fwd = -1)
+    assert relmax(back, t) < 3 * TOL_BF16
+    dim = H * D
+    x, w, bias = rnd(B * N, dim), rnd(3 * dim, dim, scale=dim ** -0.5), torch.randn(3 * dim, device="cuda")
+    inv = 100.0 ** (-torch.arange(16, device="cuda", dtype=torch.float32) / 16)
+    ang = torch.arange(8, device="cuda", dtype=torch.float32)[:, None] * inv
+    cs = torch.stack([ang.cos(), ang.sin()], -1).contiguous()
+    got = ops.gemm(x, w, bias=bias, out_dtype=torch.float32, rope=(cs, pos.view(-1, 2), 2 * dim))
+    qkv = (x.float() @ w.float().t() + bias).view(B, N, 3, H, D)
+    ref = torch.stack([rope_ref(qkv[:, :, 0], pos), rope_ref(qkv[:, :, 1], pos), qkv[:, :, 2]], 2).view(B * N, 3 * dim)
+    assert relmax(got, ref) < TOL_F32
+
+
+def attn_ref(q, k, v, scale, mask=None):
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale
+    if mask is not None:
+        s = s.masked_fill(mask[:, None], float("-inf"))
+    return torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v.float()).reshape(q.shape[0], q.shape[1], -1)
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,hd,splits", [(1, 1, 128, 128, 64, 1), (2, 4, 300, 500, 64, 1), (2, 12, 768, 768, 64, 1),
+                                                 (1, 12, 768, 1536, 64, 2), (1, 1, 1, 1, 64, 1), (1, 3, 5, 129, 64, 1),
+                                                 (1, 1, 128, 128, 96, 1), (2, 4, 200, 1000, 96, 1), (1, 8, 200, 3000, 96, 4),
+                                                 (1, 16, 769, 769, 64, 1), (1, 2, 130, 4000, 64, 0)])
+def test_attention(ops, B, H, Nq, Nk, hd, splits):
+    q, k, v = rnd(B, Nq, H, hd), rnd(B, Nk, H, hd), rnd(B, Nk, H, hd)
+    assert relmax(ops.attention(q, k, v, kv_splits=splits), attn_ref(q, k, v, hd ** -0.5)) < TOL_ATTN
+
+
+def test_attention_layouts(ops):
+    B, N, H, hd = 2, 384, 12, 64
+    qkv = rnd(B, N, 3, H, hd)  # packed QKV projection output
+    got = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2])
+    assert relmax(got, attn_ref(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], hd ** -0.5)) < TOL_ATTN
+    q, k, v = rnd(3, 256, 12, 64), rnd(1, 640, 12, 64), rnd(1, 640, 12, 64)  # K/V shared by the batch (render)
+    assert relmax(ops.attention(q, k, v), attn_ref(q, k.expand(3, -1, -1, -1), v.expand(3, -1, -1, -1), 0.125)) < TOL_ATTN
+    kv = rnd(1, 640, 2 * 768)  # K|V packed per memory token
+    k2, v2 = kv[:, :, :768].unflatten(-1, (12, 64)), kv[:, :, 768:].unflatten(-1, (12, 64))
+    assert relmax(ops.attention(q, k2, v2), attn_ref(q, k2.expand(3, -1, -1, -1), v2.expand(3, -1, -1, -1), 0.125)) < TOL_ATTN
+
+
+def pack_bits(mask):  # bool [B, Nq, Nk] -> int32 [B, Nq, W]
+    B, Nq, Nk = mask.shape
+    words = ((Nk + 127) // 128) * 4
+    mb = torch.zeros(B, Nq, words * 32, device=mask.device, dtype=torch.bool)
+    mb[:, :, :Nk] = mask
+    bits = (mb.view(B, Nq, words, 32).to(torch.int64) << torch.arange(32, device=mask.device)).sum(-1)
+    return torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32).contiguous()
+
+
+@pytest.mark.parametrize("hd,splits", [(96, 1), (96, 3), (64, 1)])
+def test_attention_block_mask(ops, hd, splits):
+    B, H, Nq, Nk = 1, 8, 200, 1536
+    q, k, v = rnd(B, Nq, H, hd), rnd(B, Nk, H, hd), rnd(B, Nk, H, hd)
+    mask = torch.rand(B, Nq, Nk, device="cuda") < 0.6
+    mask[:, 5] = False
+    mask[:, 7, :1400] = True  # whole 128-key tiles blocked for this query
+    got = ops.attention(q, k, v, mask_bits=pack_bits(mask), kv_splits=splits)
+    assert relmax(got, attn_ref(q, k, v, hd ** -0.5, mask)) < TOL_ATTN
+    # one mask row shared by all queries of a batch item (MUSt3R initialisation: a view skips its own tokens)
+    row = torch.zeros(2, 1, Nk, device="cuda", dtype=torch.bool)
+    row[0, 0, :768] = True
+    row[1, 0, 768:] = True
+    q2 = rnd(2, 300, H, hd)
+    got = ops.attention(q2, k, v, mask_bits=pack_bits(row))
+    assert relmax(got, attn_ref(q2, k.expand(2, -1, -1, -1), v.expand(2, -1, -1, -1), hd ** -0.5, row.expand(2, 300, Nk))) < TOL_ATTN
+
+
+def test_layernorm(ops):
+    for dim in (1024, 768, 384, 2816, 100):
+        x = rnd(333, dim)
+        g, b = torch.randn(dim, device="cuda"), torch.randn(dim, device="cuda")
+        ref = torch.nn.functional.layer_norm(x.float(), (dim,), g, b, 1e-6)
+        assert relmax(ops.layernorm(x, g, b, 1e-6), ref) < TOL_BF16
+        assert relmax(ops.layernorm(x, g, b, 1e-6, out_dtype=torch.float32), ref) < 1e-5
+    x, add = rnd(500, 768), rnd(500, 768)
+    g, b = torch.randn(768, device="cuda"), torch.randn(768, device="cuda")
+    so = torch.empty_like(x)
+    got = ops.layernorm(x, g, b, 1e-5, add=add, sum_out=so, out_dtype=torch.float32)
+    assert relmax(got, torch.nn.functional.layer_norm(x.float() + add.float(), (768,), g, b, 1e-5)) < 1e-5
+    assert relmax(so, x.float() + add.float()) < TOL_BF16
+    xf = torch.randn(200, 768, device="cuda")
+    assert relmax(ops.layernorm(xf, g, b, 1e-5, out_dtype=torch.float32), torch.nn.functional.layer_norm(xf, (768,), g, b, 1e-5)) < 1e-5
+    buf = rnd(4, 11, 256)  # drop the first row of every batch item while normalising (DINOv2 CLS)
+    g, b = torch.randn(256, device="cuda"), torch.randn(256, device="cuda")
+    out = torch.empty(40, 256, device="cuda", dtype=torch.bfloat16)
+    ops.layernorm(buf[:, 1:], g, b, 1e-6, out=out, x_rows=(40, 256, 256, 10, 11 * 256))
+    assert relmax(out, torch.nn.functional.layer_norm(buf[:, 1:].float(), (256,), g, b, 1e-6).reshape(40, 256)) < TOL_BF16
+    wide = torch.zeros(333, 2816, device="cuda", dtype=torch.bfloat16)  # strided destination (concat buffer slice)
+    x = rnd(333, 1024)
+    g, b = torch.randn(1024, device="cuda"), torch.randn(1024, device="cuda")
+    ops.layernorm(x, g, b, 1e-6, out=wide[:, 1792:])
+    assert relmax(wide[:, 1792:], torch.nn.functional.layer_norm(x.float(), (1024,), g, b, 1e-6)) < TOL_BF16
+    assert wide[:, :1792].abs().max().item() == 0
+
+
+def test_patchify_and_dino_preprocess(ops):
+    img = torch.rand(2, 3, 64, 96, device="cuda") * 2 - 1
+    ref = torch.nn.functional.unfold(img, 16, stride=16).transpose(1, 2).reshape(-1, 768)
+    assert relmax(ops.patchify(img, 16), ref) < TOL_BF16
+    Ho, Wo = 64 // 16 * 14, 96 // 16 * 14
+    got = ops.dino_preprocess_patchify(img, Ho, Wo, 14, 592)
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda").view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda").view(1, 3, 1, 1)
+    y = torch.nn.functional.interpolate((img * 0.5 + 0.5 - mean) / std, size=(Ho, Wo), mode="bilinear", align_corners=False)
+    ref = torch.nn.functional.unfold(y, 14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert relmax(got[:, :588], ref) < TOL_BF16 and got[:, 588:].abs().max().item() == 0
+
+
+def test_mask_helpers(ops):
+    f = rnd(2, 16, 24, 64)
+    ref = torch.nn.functional.interpolate(f.float().permute(0, 3, 1, 2), size=(2, 3), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    assert relmax(ops.center_pool8(f), ref) < TOL_BF16
+    lg = torch.randn(200, 1536, device="cuda")
+    lg[7] = -lg[7].abs()  # fully blocked row -> unblocked (mask_transformer.py:172)
+    bits = ops.attn_mask_bits(lg, 1500)
+    blocked = lg[:, :1500] < 0
+    blocked[blocked.all(-1)] = False
+    unpacked = ((bits[0].to(torch.int64)[..., None] >> torch.arange(32, device="cuda")) & 1).bool().view(200, -1)
+    assert torch.equal(unpacked[:, :1500], blocked) and not unpacked[:, 1500:].any()
+    xx = torch.randn(200, 768, device="cuda")
+    assert relmax(ops.l2norm_rows(xx, 1e-7, torch.float32), xx / (xx.norm(dim=-1, keepdim=True) + 1e-7)) < 1e-6
+    t = rnd(2, 100, 48)
+    assert torch.equal(ops.nhwc_to_nchw_f32(t), t.float().transpose(1, 2))
+    a_, b_ = rnd(6, 10, 64), rnd(10, 64)
+    assert relmax(ops.add_bcast(a_.view(60, 64), b_), (a_.float() + b_.float()).view(60, 64)) < TOL_BF16
+    assert torch.equal(ops.to_f32(ops.to_bf16(xx)), xx.bfloat16().float())
+
+
+def test_full_size_properties(ops):
+    """BASELINE config-2 sizes, checked through size-independent properties."""
+    # mask einsum at 16 x 192 x 256 x 256: linearity in the query embedding + spot check of random pixels
+    V, Hm, Wm, Q, Cm = 16, 192, 256, 200, 256
+    feats = rnd(V, Hm, Wm, Cm)
+    e1, e2 = rnd(Q, Cm, scale=0.06), rnd(Q, Cm, scale=0.06)
+    def run(e):
+        out = torch.empty(V, Q, Hm, Wm, device="cuda", dtype=torch.float32)
+        ops.gemm(feats.view(-1, Cm), e, out=out, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=Hm * Wm, batch_stride=Q * Hm * Wm, ldt=Hm * Wm)
+        return out
+    o1, o2 = run(e1), run(e2)
+    e12 = (e1.float() + e2.float()).bfloat16()
+    exact = (e12.float() == e1.float() + e2.float())  # rows where the bf16 sum is exact
+    o12 = run(e12)
+    rows = exact.all(-1).nonzero().flatten()[:8]
+    if rows.numel():
+        assert relmax(o12[:, rows], o1[:, rows] + o2[:, rows]) < 1e-4
+    idx = torch.randint(0, V * Hm * Wm, (4096,), device="cuda")
+    ref = feats.view(-1, Cm)[idx].float() @ e1.float().t()
+    got = o1.permute(0, 2, 3, 1).reshape(-1, Q)[idx]
+    assert relmax(got, ref) < TOL_F32
+    del o1, o2, o12
+    # attention over 12288 memory keys: result is invariant to the KV split count and to key permutation
+    q, k, v = rnd(2, 768, 12, 64), rnd(1, 12288, 12, 64), rnd(1, 12288, 12, 64)
+    # (outputs are means of 12288 random values, |o| ~ 0.02: the bf16 rounding of P and O is 1.2e-2 of that max)
+    tol = 1.2e-2
+    a1 = ops.attention(q, k, v, kv_splits=1)
+    a4 = ops.attention(q, k, v, kv_splits=4)
+    assert relmax(a4, a1) < tol
+    perm = torch.randperm(12288, device="cuda")
+    assert relmax(ops.attention(q, k[:, perm].contiguous(), v[:, perm].contiguous()), a1) < tol
+    assert relmax(a1, attn_ref(q, k.expand(2, -1, -1, -1), v.expand(2, -1, -1, -1), 0.125)) < tol
+
+
+def test_error_reporting(ops):
+    from panst3r_b200.lib import Pst3rError
+    with pytest.raises(Pst3rError):
+        ops.gemm(rnd(128, 60), rnd(64, 60))  # K stride not 16-byte aligned
+    with pytest.raises(Pst3rError):
+        ops.attention(rnd(1, 8, 2, 32), rnd(1, 8, 2, 32), rnd(1, 8, 2, 32))  # unsupported head_dim
+    with pytest.raises(Pst3rError):
+        ops.gemm(rnd(128, 64).float(), rnd(64, 64))
