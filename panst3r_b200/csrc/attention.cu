@@ -372,6 +372,10 @@ __global__ void attention_combine_kernel(const float* __restrict__ ws_o, const f
   }
 }
 
+}  // namespace pst3r
+#include "attention2.cuh"
+namespace pst3r {
+
 static int make_qkv_map(CUtensorMap* m, const void* ptr, int hd, long long n, int H, int B, long long sn,
                         long long sh, long long sb) {
   uint64_t dims[4] = {(uint64_t)hd, (uint64_t)n, (uint64_t)H, (uint64_t)B};
@@ -405,7 +409,13 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
     p.ws_ml = p.ws_o + (long long)splits * rows * HD;
   }
   dim3 grid((a->Nq + ATT_BM - 1) / ATT_BM, a->B * a->H, splits);
-  if (a->mask_bits) {
+  if (HD == 64 && !a->mask_bits) {
+    // second-generation kernel: 256 queries per CTA
+    static bool cfg2 = false;
+    if (!cfg2) { PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_DYN_BYTES)); cfg2 = true; }
+    dim3 grid2((a->Nq + 255) / 256, a->B * a->H, splits);
+    attention2_fwd_kernel<<<grid2, AT2_THREADS, AT2_DYN_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  } else if (a->mask_bits) {
     auto kern = attention_fwd_kernel<HD, true>;
     static bool cfg = false;
     if (!cfg) { PST3R_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::DYN_BYTES)); cfg = true; }
@@ -433,7 +443,7 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
 using namespace pst3r;
 
 extern "C" int32_t pst3r_attention_auto_splits(int32_t B, int32_t H, int32_t Nq, int32_t Nk) {
-  const int ctas = ((Nq + ATT_BM - 1) / ATT_BM) * B * H;
+  const int ctas = ((Nq + 255) / 256) * B * H;  // CTAs of the 256-query kernel (a slight over-split for the 128-query one)
   const int tiles = (Nk + ATT_BN - 1) / ATT_BN;
   const int sms = num_sms();
   if (ctas >= sms || tiles <= 1) return 1;

@@ -5,10 +5,11 @@
 // pointmap head).  Fused epilogues: bias, GELU/ReLU, LayerScale, residual add, 2-D RoPE on q/k columns,
 // pixel_shuffle(2) store, 16x16 depth-to-space store, transposed (plane-major) fp32 store.
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0      : TMA producer   (A 128x64 + B BNx64 bf16 tiles, SWIZZLE_128B, STAGES-deep mbarrier ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x n x 16, fp32 accum in TMEM)
-//   warps 2..5  : epilogue (tcgen05.ld 32 lanes x 32 cols -> registers -> math -> global)
+//   warps 2..9  : epilogue, two warps per TMEM lane quadrant taking alternate 32-column chunks
+//                 (tcgen05.ld 32 lanes x 32 cols -> registers -> math -> global)
 //   TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the mainloop of tile i+1.
 #include "common.cuh"
 #include "host_util.h"
@@ -39,7 +40,7 @@ struct GemmEpi {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;
 
 template <int BN, int STAGES>
 struct GemmSmem {
@@ -260,7 +261,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     mbar_fence_init();
   }
@@ -329,6 +330,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ------------------------------- epilogue -----------------------------------
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int cgrp = (warp - 2) >> 2;  // which half of the 32-column chunks
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int m_blk = tile % num_m_blocks;
@@ -341,7 +343,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       const int n_rem = N - n_blk * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = cgrp; c < BN / 32; c += 2) {
         if (c * 32 >= n_rem) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(t_base + c * 32, r);
@@ -420,10 +422,18 @@ extern "C" int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   // Tile-width heuristic: the widest BN whose tile count still fills the machine.
   const int sms = num_sms();
   const int mb = (M + GEMM_BM - 1) / GEMM_BM;
-  int BN = 256;
-  if (mb * ((N + 255) / 256) < sms || N <= 128) BN = 128;
-  if (BN == 128 && (mb * ((N + 127) / 128) < sms || N <= 64)) BN = 64;
-  if (N > 128 && N <= 256 && mb >= sms) BN = 256;  // e.g. mask einsum: N = 200, huge M
+  // A CTA ingests (128 + BN) x 64 bf16 per k-block and is bound by its L2->smem rate long before the tensor pipe
+  // (measured: 128x256 tiles run at ~65 % of the cuBLAS peak), so pick the BN that minimises
+  // waves x bytes-per-k-block, i.e. the per-SM load time of the slowest SM.
+  int BN = 64;
+  long long best = -1;
+  for (int cand = 64; cand <= 256; cand *= 2) {
+    const long long tiles = (long long)mb * ((N + cand - 1) / cand);
+    const long long waves = (tiles + sms - 1) / sms;
+    const long long cost = waves * (128 + cand);
+    if (best < 0 || cost < best || (cost == best && cand > BN)) { best = cost; BN = cand; }
+    if (cand >= N) break;  // wider tiles would only add padding
+  }
 
   CUtensorMap tmA, tmB;
   {
