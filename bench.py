@@ -274,13 +274,14 @@ def run_ours(args):
 
     # ---- per-kernel-kind profile of one eager step + roofline of the dominant kernel ----
     roofline, breakdown = None, None
+    with ops.profiler() as prof:  # every rank runs the step (it contains collectives); rank 0 reports
+        step_device()
+    barrier()
     if rank == 0:
         peaks, peak_src = _peaks()
-        with ops.profiler() as prof:
-            step_device()
-        torch.cuda.synchronize()
         breakdown = prof.summary()
         roofline = dominant_roofline(ops, torch, V, peaks, peak_src, breakdown)
+    barrier()
 
     if rank == 0:
         cpu_base = None
