@@ -96,7 +96,7 @@ class PanSt3R(nn.Module):
         cat = torch.empty((B, V, N, ENC_DIM + DEC_DIM + DINO_DIM), device=imgs.device, dtype=torch.bfloat16)
         rows = cat.view(B * V * N, -1)
         cur = torch.cuda.current_stream()
-        if self.overlap_dino and not torch.cuda.is_current_stream_capturing():
+        if self.overlap_dino:  # also legal under CUDA-graph capture: the side stream forks from / joins the capturing one
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream()
             side = self._side_stream
