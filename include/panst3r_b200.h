@@ -84,6 +84,14 @@ typedef struct pst3r_gemm_epilogue {
 int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
                     const pst3r_gemm_epilogue* epi, pst3r_stream_t stream);
 
+/* 3x3 convolution, stride 1, zero padding 1, over a pixel-major bf16 map x [V, H, W, ldx] (C <= ldx valid channels)
+ * as an implicit GEMM: out[(v, y, x), o] = epi(sum_{ky,kx,c} x[v, y+ky-1, x+kx-1, c] * w[o, (ky*3+kx)*cpad + c]).
+ * w is bf16 [O, 9*cpad] (Conv2d weight [O, C, 3, 3] permuted to tap-major and zero-padded to cpad, cpad % 64 == 0).
+ * The A operand is fetched by a 4-D TMA map whose out-of-bounds zero fill IS the padding.  PLAIN store only
+ * (out rows = V*H*W pixels).  Replaces nn.Conv2d(k=3, padding=1) at model/upscalers/loftup.py:124,127. */
+int pst3r_conv3x3_nhwc(const void* x, int64_t ldx, int32_t V, int32_t H, int32_t W, int32_t C, const void* w,
+                       int32_t cpad, int32_t O, const pst3r_gemm_epilogue* epi, pst3r_stream_t stream);
+
 /* ---- Attention: O = softmax(scale * Q K^T [+ mask]) V ----------------------------------------
  * bf16 Q/K/V with head_dim 64 or 96, element strides given per (batch, token, head); head_dim contiguous.
  * kv_batch_stride may be 0 (all batch items attend the same memory tokens: MUSt3R render pass).
@@ -161,6 +169,24 @@ int pst3r_l2norm_rows(const float* x, int64_t ldx, void* y, int32_t y_f32, int64
 
 /* bf16 pixel-major [B, HW, C] -> fp32 channel-major [B, C, HW] (reference NCHW layout of mask_feats / fpn) */
 int pst3r_nhwc_to_nchw_f32(const void* x, int32_t B, int32_t HW, int32_t C, float* y, pst3r_stream_t stream);
+
+/* ---- LoftUp guidance path (model/upscalers/loftup.py:9-79,122-130,152-157) ------------------------ */
+int64_t pst3r_loftup_workspace_bytes(int32_t V, int32_t C, int32_t groups);
+/* img fp32 [V,3,H,W] -> half fp32 [V,3,H/2,W/2] (bilinear x0.5) and minmax fp32 [3][2] = per-channel (min, max)
+ * over the WHOLE batch (MinMaxScaler, loftup.py:14-19). */
+int pst3r_loftup_guidance(const float* img, int32_t V, int32_t H, int32_t W, float* half, float* minmax,
+                          void* workspace, pst3r_stream_t stream);
+/* MinMaxScaler -> ImplicitFeaturizer (n_freqs sin/cos features of [gy, gx, r, g, b] + scaled rgb; channel order
+ * [sin(f*5+m) | cos(f*5+m) | rgb]) -> GroupNorm(1, C) with (gamma, beta) -> bf16 pixel-major out [V, Hh, Wh, ldo]
+ * (channels [C, ldo) zeroed).  gy/gx = torch.linspace(-1,1,.) tables, freqs = exp(linspace(-2,10,n_freqs)),
+ * biases = the flat (2, 5, n_freqs) parameter. */
+int pst3r_loftup_fourier_gn(const float* half, const float* minmax, const float* gy, const float* gx,
+                            const float* freqs, const float* biases, int32_t V, int32_t Hh, int32_t Wh,
+                            int32_t n_freqs, const float* gamma, const float* beta, float eps, void* out, int64_t ldo,
+                            void* workspace, pst3r_stream_t stream);
+/* In-place GroupNorm (+ optional ReLU) on a pixel-major bf16 map x [V, npix, C] (nn.GroupNorm(groups, C)). */
+int pst3r_groupnorm_nhwc(void* x, int32_t V, int32_t npix, int32_t C, int32_t groups, const float* gamma,
+                         const float* beta, float eps, int32_t relu, void* workspace, pst3r_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,9 @@ struct GemmEpi {
   const int* rope_pos;
   int rope_cols;
   int rope_maxpos;
+  // implicit-GEMM 3x3 convolution over a pixel-major [V, Hc, Wc, C] map (A is a 4-D TMA map; OOB = zero padding)
+  int conv_cblocks;  // 64-channel blocks per tap (0 = plain GEMM)
+  int conv_w, conv_h, conv_tpr;  // map width / height, 128-pixel tiles per image row
 };
 
 constexpr int GEMM_BM = 128;
@@ -287,7 +290,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
           uint8_t* a_dst = smem + s * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + L::A_BYTES;
-          tma_load_2d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
+          if (ep.conv_cblocks > 0) {
+            // k-block -> (tap, channel block); m-tile -> (view, y, 128-pixel segment of the row)
+            const int tap = kb / ep.conv_cblocks, cb = kb - tap * ep.conv_cblocks;
+            const int xb = m_blk % ep.conv_tpr, rowidx = m_blk / ep.conv_tpr;
+            tma_load_4d(a_dst, &tmA, &full_bar[s], cb * 64, xb * GEMM_BM + tap % 3 - 1, rowidx % ep.conv_h + tap / 3 - 1,
+                        rowidx / ep.conv_h);
+          } else {
+            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
+          }
           tma_load_2d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -339,7 +350,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t acc_ph = (local >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
-      const int row = m_blk * GEMM_BM + quad * 32 + lane;
+      int row = m_blk * GEMM_BM + quad * 32 + lane;
+      int m_lim = M;
+      if (ep.conv_cblocks > 0) {
+        const int xcol = (m_blk % ep.conv_tpr) * GEMM_BM + quad * 32 + lane;
+        row = (m_blk / ep.conv_tpr) * ep.conv_w + xcol;
+        m_lim = xcol < ep.conv_w ? 0x7fffffff : 0;  // segment tail beyond the image row: nothing to store
+      }
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       const int n_rem = N - n_blk * BN;
 #pragma unroll 1
@@ -351,7 +368,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_chunk(ep, v, row, n_blk * BN + c * 32, M, N);
+        epilogue_chunk(ep, v, row, n_blk * BN + c * 32, m_lim, N);
       }
       tc_fence_before();
       __syncwarp();
@@ -388,14 +405,16 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 using namespace pst3r;
 
-extern "C" int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N,
-                               int32_t K, const pst3r_gemm_epilogue* e, pst3r_stream_t stream_) {
+struct ConvCfg { int V, H, W, C, cpad; };
+
+static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
+                    const pst3r_gemm_epilogue* e, pst3r_stream_t stream_, const ConvCfg* conv) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PST3R_CHECK_ARG(A && B && e && e->out, "gemm: null pointer");
   PST3R_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   PST3R_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 (lda=%lld ldb=%lld)",
                   (long long)lda, (long long)ldb);
-  PST3R_CHECK_ARG(lda >= K && ldb >= K, "gemm: lda/ldb smaller than K");
+  PST3R_CHECK_ARG((conv || lda >= K) && ldb >= K, "gemm: lda/ldb smaller than K");
   if (e->store_mode == PST3R_STORE_TRANSPOSED)
     PST3R_CHECK_ARG(e->rows_per_batch > 0 && e->ldt > 0, "gemm: TRANSPOSED store needs rows_per_batch/ldt");
   if (e->store_mode == PST3R_STORE_PIXSHUF2)
@@ -418,6 +437,10 @@ extern "C" int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   ep.grid_h = e->grid_h; ep.grid_w = e->grid_w; ep.d2s_patch = e->d2s_patch; ep.d2s_ch = e->d2s_ch;
   ep.rope_cs = reinterpret_cast<const float2*>(e->rope_cs); ep.rope_pos = e->rope_pos;
   ep.rope_cols = e->rope_cols; ep.rope_maxpos = e->rope_maxpos;
+  ep.conv_cblocks = 0; ep.conv_w = ep.conv_h = ep.conv_tpr = 0;
+  if (conv) {
+    ep.conv_cblocks = conv->cpad / 64; ep.conv_w = conv->W; ep.conv_h = conv->H; ep.conv_tpr = (conv->W + GEMM_BM - 1) / GEMM_BM;
+  }
 
   // Tile-width heuristic: the widest BN whose tile count still fills the machine.
   const int sms = num_sms();
@@ -436,7 +459,15 @@ extern "C" int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   }
 
   CUtensorMap tmA, tmB;
-  {
+  if (conv) {
+    // pixel-major map [V, H, W, C] (row pitch lda): box = 64 channels x 128 pixels of one image row; coordinates outside
+    // the map (x = -1, W; y = -1, H; channels >= C) are zero-filled by TMA == the convolution's zero padding
+    uint64_t dims[4] = {(uint64_t)conv->C, (uint64_t)conv->W, (uint64_t)conv->H, (uint64_t)conv->V};
+    uint64_t str[4] = {2, (uint64_t)lda * 2, (uint64_t)lda * conv->W * 2, (uint64_t)lda * conv->W * conv->H * 2};
+    uint32_t box[4] = {GEMM_BK, GEMM_BM, 1, 1};
+    int r = encode_tmap(&tmA, A, 2, 4, dims, str, box);
+    if (r) return r;
+  } else {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     uint64_t str[2] = {2, (uint64_t)lda * 2};
     uint32_t box[2] = {GEMM_BK, GEMM_BM};
@@ -455,4 +486,21 @@ extern "C" int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     case 128: return launch_gemm<128, 6>(tmA, tmB, ep, M, N, K, stream);
     default: return launch_gemm<64, 8>(tmA, tmB, ep, M, N, K, stream);
   }
+}
+
+extern "C" int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N,
+                               int32_t K, const pst3r_gemm_epilogue* e, pst3r_stream_t stream) {
+  return gemm_run(A, lda, B, ldb, M, N, K, e, stream, nullptr);
+}
+
+extern "C" int pst3r_conv3x3_nhwc(const void* x, int64_t ldx, int32_t V, int32_t H, int32_t W, int32_t C, const void* w,
+                                  int32_t cpad, int32_t O, const pst3r_gemm_epilogue* e, pst3r_stream_t stream) {
+  PST3R_CHECK_ARG(x && w && e && V > 0 && H > 0 && W > 0 && C > 0 && O > 0, "conv3x3: bad args");
+  PST3R_CHECK_ARG(cpad >= C && (cpad % 64) == 0 && (ldx % 8) == 0 && ldx >= C, "conv3x3: cpad must be a multiple of 64 >= C; ldx %% 8 == 0");
+  PST3R_CHECK_ARG(e->store_mode == PST3R_STORE_PLAIN && e->rows_per_batch == 0 && !e->rope_cs, "conv3x3: plain store only");
+  ConvCfg c{V, H, W, C, cpad};
+  const int tpr = (W + GEMM_BM - 1) / GEMM_BM;
+  const long long mv = (long long)V * H * tpr * GEMM_BM;  // virtual rows: 128-pixel row segments
+  PST3R_CHECK_ARG(mv < 0x7fffffffLL, "conv3x3: map too large");
+  return gemm_run(x, ldx, w, 9LL * cpad, (int32_t)mv, O, 9 * cpad, e, stream, &c);
 }

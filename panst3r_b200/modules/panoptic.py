@@ -357,3 +357,186 @@ class PanopticDecoder(nn.Module):
             out = {k: (v.to(outdevice) if torch.is_tensor(v) else
                        [{kk: vv.to(outdevice) for kk, vv in a.items()} for a in v]) for k, v in out.items()}
         return out
+
+
+# =====================================================================================================
+# v2 head pieces: InputMixer (reference model/input_mixer.py:8-29) and LoftUpUpscaler
+# (reference model/upscalers/loftup.py:84-190, model/blocks.py:9-35)
+# =====================================================================================================
+class InputMixer(nn.Module):
+    """Linear 2816 -> 768, three croco RoPE `Block`s (12 heads, LayerNorm eps 1e-5, qkv bias), LayerNorm."""
+
+    def __init__(self, img_size, patch_size, in_dim, hidden_dim, num_heads=12, num_layers=3, ff_dim_mult=4):
+        super().__init__()
+        from .common import ViTBlockParams
+        self.hidden_dim, self.num_heads = hidden_dim, num_heads
+        self.in_proj = nn.Linear(in_dim, hidden_dim)
+        self.mixer_blk = nn.ModuleList([ViTBlockParams(hidden_dim, num_heads, ff_dim_mult, eps=1e-5) for _ in range(num_layers)])
+        self.mixer_norm = nn.LayerNorm(hidden_dim)
+
+    @torch.no_grad()
+    def forward_rows(self, x: torch.Tensor, V: int, hs: int, ws: int) -> torch.Tensor:
+        """x bf16 rows (V*hs*ws, in_dim) -> bf16 rows (V*hs*ws, hidden_dim)"""
+        from .common import pos_grid, rope_table, vit_block
+        N = hs * ws
+        _, pos32 = pos_grid(hs, ws, x.device)
+        rope = (rope_table(max(hs, ws), self.hidden_dim // self.num_heads, 100.0, x.device), pos32.repeat(V, 1))
+        h = ops.gemm(x, w16(self.in_proj.weight), bias=bias_of(self.in_proj))
+        for blk in self.mixer_blk:
+            h = vit_block(h, blk, V, N, rope)
+        return ops.layernorm(h, f32(self.mixer_norm.weight), f32(self.mixer_norm.bias), 1e-5)
+
+    def forward(self, x, pos):
+        b, N, _ = x.shape
+        raise ops._l.Pst3rError("call forward_rows (the CUDA PanopticDecoder does); token grids are needed for RoPE tables")
+
+
+class _ImplicitFeaturizerParams(nn.Module):
+    def __init__(self, dim_multiplier, n_freqs):
+        super().__init__()
+        self.biases = nn.Parameter(torch.randn(2, dim_multiplier, n_freqs))
+
+
+class _CrossAttn(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.projq = nn.Linear(dim, dim, bias=False)
+        self.projk = nn.Linear(dim, dim, bias=False)
+        self.projv = nn.Linear(dim, dim, bias=False)
+        self.proj = nn.Linear(dim, dim)
+
+
+class CrossonlyDecoderBlock(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio=4.0):
+        super().__init__()
+        self.dim, self.num_heads = dim, num_heads
+        self.cross_attn = _CrossAttn(dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.norm3 = nn.LayerNorm(dim)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio), dim)
+        self.norm_y = nn.LayerNorm(dim)
+
+
+class LoftUpUpscaler(nn.Module):
+    def __init__(self, input_dim, dim, output_stride=2, patch_size=16, color_feats=True, n_freqs=20, num_heads=4,
+                 num_layers=2, lr_pe_type="sine"):
+        super().__init__()
+        assert color_feats and lr_pe_type == "sine" and output_stride == 2
+        self.input_dim, self.dim, self.patch_size, self.n_freqs, self.num_heads = input_dim, dim, patch_size, n_freqs, num_heads
+        self.mask_dim = dim
+        self.patch_embed = nn.Conv2d(input_dim, input_dim, kernel_size=1)
+        start_dim = 5 * n_freqs * 2 + 3
+        self.start_dim = start_dim
+        self.lr_pe = _ImplicitFeaturizerParams(2, 5)
+        self.lr_input_proj = nn.Sequential(nn.Linear(input_dim + 20, dim), nn.LayerNorm(dim))
+        self.fourier_feat = nn.Sequential(nn.Identity(), _ImplicitFeaturizerParams(5, n_freqs))  # .1.biases
+        self.first_conv = nn.Sequential(
+            nn.GroupNorm(1, start_dim), nn.Conv2d(start_dim, dim, 3, padding=1), nn.GroupNorm(8, dim), nn.ReLU(),
+            nn.Conv2d(dim, dim, 3, padding=1), nn.GroupNorm(8, dim), nn.ReLU())
+        self.ca_transformer_blocks = nn.ModuleList([CrossonlyDecoderBlock(dim, num_heads, mlp_ratio=1) for _ in range(num_layers)])
+        self.ca_transformer_norm = nn.LayerNorm(dim)
+
+    # ---- prepared constants ----------------------------------------------------------------------
+    @staticmethod
+    def _conv_w(conv: nn.Conv2d, cpad: int):
+        wt = conv.weight
+
+        def build():
+            O, Cc = wt.shape[:2]
+            t = torch.zeros((O, 3, 3, cpad), device=wt.device, dtype=torch.float32)
+            t[..., :Cc] = wt.detach().float().permute(0, 2, 3, 1)  # [O, C, ky, kx] -> [O, ky, kx, C]
+            return t.reshape(O, 9 * cpad).to(torch.bfloat16).contiguous()
+        return prepared(f"conv_w_{cpad}", [wt], build)
+
+    def _tables(self, Hh, Wh, device):
+        def build():
+            gy = torch.linspace(-1, 1, Hh, device=device)
+            gx = torch.linspace(-1, 1, Wh, device=device)
+            fr = torch.exp(torch.linspace(-2, 10, self.n_freqs, device=device))
+            return torch.cat([gy, gx, fr]).float().contiguous()
+        t = prepared(f"loftup_tab_{Hh}x{Wh}", [self.ca_transformer_norm.weight], build)
+        return t[:Hh], t[Hh:Hh + Wh], t[Hh + Wh:]
+
+    def _lr_pe_term(self, hs, ws, device):
+        """Constant of (grid, weights): lr_input_proj.0 applied to the 20 sine-PE channels of the low-res grid, plus its
+        bias -> bf16 (hs*ws, dim).  (ImplicitFeaturizer(color_feats=False, n_freqs=5, learn_bias=True), loftup.py:99.)"""
+        lin = self.lr_input_proj[0]
+        b = self.lr_pe.biases
+
+        def build():
+            gy = torch.linspace(-1, 1, hs, device=device).view(1, hs, 1).expand(1, hs, ws)
+            gx = torch.linspace(-1, 1, ws, device=device).view(1, 1, ws).expand(1, hs, ws)
+            base = torch.cat([gy, gx], 0)  # (2, hs, ws)
+            fr = torch.exp(torch.linspace(-2, 10, 5, device=device)).view(5, 1, 1, 1)
+            arg = base.unsqueeze(0) * fr  # (5, 2, hs, ws)
+            bb = b.detach().float()
+            s = torch.sin(arg + bb[0].reshape(5, 2, 1, 1)).flatten(0, 1)
+            c = torch.cos(arg + bb[1].reshape(5, 2, 1, 1)).flatten(0, 1)
+            pe = torch.cat([s, c], 0).flatten(1).t()  # (hs*ws, 20)
+            wpe = lin.weight.detach().float()[:, self.input_dim:]
+            return (pe @ wpe.t() + lin.bias.detach().float()).to(torch.bfloat16).contiguous()
+        return prepared(f"loftup_lrpe_{hs}x{ws}", [lin.weight, lin.bias, b], build)
+
+    def _lr_feat_w(self):
+        lin = self.lr_input_proj[0]
+        return prepared("loftup_lrw", [lin.weight], lambda: lin.weight.detach()[:, :self.input_dim].to(torch.bfloat16).contiguous())
+
+    @torch.no_grad()
+    def forward_nhwc(self, feats: torch.Tensor, imgs: torch.Tensor, b: int, hs: int, ws: int,
+                     f16_extra_bias: Optional[torch.Tensor] = None):
+        """feats bf16 rows (b*hs*ws, input_dim) (InputMixer output), imgs fp32 (b,3,H,W) ->
+        (f16 bf16 (b*hs*ws, input_dim) = patch_embed(feats) [+ level_embed], mask feats bf16 (b, H/2, W/2, dim))."""
+        dev = feats.device
+        N = hs * ws
+        D, Hh, Wh = self.dim, hs * self.patch_size // 2, ws * self.patch_size // 2
+        # stride-16 features for the query decoder: 1x1 conv == GEMM
+        pb = f32(self.patch_embed.bias)
+        if f16_extra_bias is not None:
+            pb = prepared("loftup_f16bias", [self.patch_embed.bias, f16_extra_bias],
+                          lambda: (self.patch_embed.bias.detach().float() + f16_extra_bias.detach().float().view(-1)).contiguous())
+        f16 = ops.gemm(feats, w16(self.patch_embed.weight), bias=pb)
+        # guidance branch: x0.5 image -> MinMaxScaler (batch global) -> Fourier features -> GN(1) -> 2 x (conv3x3, GN(8), ReLU)
+        half, minmax = ops.loftup_guidance(imgs.float())
+        gy, gx, fr = self._tables(Hh, Wh, dev)
+        gn0, c1, gn1, c2, gn2 = (self.first_conv[i] for i in (0, 1, 2, 4, 5))
+        ld0 = ((self.start_dim + 7) // 8) * 8
+        x0 = ops.loftup_fourier_gn(half, minmax, gy, gx, fr, f32(self.fourier_feat[1].biases).view(-1), f32(gn0.weight),
+                                   f32(gn0.bias), gn0.eps, ld0)
+        x0 = x0[..., :self.start_dim] if ld0 != self.start_dim else x0
+        cpad1 = ((self.start_dim + 63) // 64) * 64
+        x1 = ops.conv3x3_nhwc(x0, self._conv_w(c1, cpad1), cpad1, bias=f32(c1.bias))
+        ops.groupnorm_nhwc_(x1, gn1.num_groups, f32(gn1.weight), f32(gn1.bias), gn1.eps, True)
+        cpad2 = ((D + 63) // 64) * 64
+        x2 = ops.conv3x3_nhwc(x1, self._conv_w(c2, cpad2), cpad2, bias=f32(c2.bias))
+        ops.groupnorm_nhwc_(x2, gn2.num_groups, f32(gn2.weight), f32(gn2.bias), gn2.eps, True)
+        x = x2.view(b * Hh * Wh, D)
+        # low-res tokens: Linear([feats | sine PE]) + LN, the PE part folded into a per-token constant
+        ln = self.lr_input_proj[1]
+        lr = ops.gemm(feats, self._lr_feat_w(), residual=self._lr_pe_term(hs, ws, dev), res_mod_rows=N)
+        lr = ops.layernorm(lr, f32(ln.weight), f32(ln.bias), ln.eps)
+        H4, hd = self.num_heads, D // self.num_heads
+        for blk in self.ca_transformer_blocks:
+            ca = blk.cross_attn
+            y_ = ops.layernorm(lr, f32(blk.norm_y.weight), f32(blk.norm_y.bias), 1e-5)
+            kv = ops.gemm(y_, cat_w16([ca.projk.weight, ca.projv.weight])).view(b, N, 2 * D)
+            q = ops.gemm(ops.layernorm(x, f32(blk.norm2.weight), f32(blk.norm2.bias), 1e-5), w16(ca.projq.weight))
+            o = ops.attention(q.view(b, Hh * Wh, H4, hd), kv[:, :, :D].unflatten(-1, (H4, hd)), kv[:, :, D:].unflatten(-1, (H4, hd)))
+            x = ops.gemm(o.view(b * Hh * Wh, D), w16(ca.proj.weight), bias=bias_of(ca.proj), residual=x, out=x)
+            h = ops.layernorm(x, f32(blk.norm3.weight), f32(blk.norm3.bias), 1e-5)
+            h = ops.gemm(h, w16(blk.mlp.fc1.weight), bias=bias_of(blk.mlp.fc1), act=ops.ACT_GELU)
+            x = ops.gemm(h, w16(blk.mlp.fc2.weight), bias=bias_of(blk.mlp.fc2), residual=x, out=x)
+        x = ops.layernorm(x, f32(self.ca_transformer_norm.weight), f32(self.ca_transformer_norm.bias), 1e-5)
+        return f16, x.view(b, Hh, Wh, D)
+
+    @torch.no_grad()
+    def forward(self, inputs, img_shape):
+        """Reference signature: ((lr_feats (b,N,C), img (b,3,H,W)), (H, W)) -> ([patch_feats (b,C,hs,ws)], (b,dim,H/2,W/2)) fp32."""
+        lr, img = inputs
+        H, W = img_shape
+        hs, ws = H // self.patch_size, W // self.patch_size
+        b = lr.shape[0]
+        x = lr if lr.dtype == torch.bfloat16 else ops.to_bf16(lr.float().contiguous())
+        f16, mf = self.forward_nhwc(x.reshape(b * hs * ws, -1), img, b, hs, ws)
+        f16_nchw = ops.nhwc_to_nchw_f32(f16.view(b, hs * ws, -1)).view(b, -1, hs, ws)
+        mf_nchw = ops.nhwc_to_nchw_f32(mf.reshape(b, -1, self.dim)).view(b, self.dim, H // 2, W // 2)
+        return [f16_nchw], mf_nchw

@@ -353,6 +353,87 @@ def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def conv3x3_nhwc(x: torch.Tensor, w: torch.Tensor, cpad: int, *, bias: Optional[torch.Tensor] = None,
+                 act: int = ACT_NONE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / stride 1 / zero-pad 1 convolution of a pixel-major bf16 map x [V, H, W, ld>=C] with tap-major weights
+    w bf16 [O, 9*cpad] as an implicit tcgen05 GEMM.  Returns bf16 [V, H, W, O]."""
+    global launches
+    lib = _l.load()
+    _need(x, torch.bfloat16, "conv3x3.x")
+    _need(w, torch.bfloat16, "conv3x3.w")
+    V, H, W, Cc = x.shape
+    if x.stride(-1) != 1 or x.stride(2) != x.stride(-2) or x.stride(1) != W * x.stride(2) or x.stride(0) != H * x.stride(1):
+        raise _l.Pst3rError("conv3x3.x: expected a dense pixel-major map")
+    O = w.shape[0]
+    if w.shape[1] != 9 * cpad or not w.is_contiguous():
+        raise _l.Pst3rError("conv3x3.w: expected contiguous [O, 9*cpad]")
+    if out is None:
+        out = torch.empty((V, H, W, O), device=x.device, dtype=torch.bfloat16)
+    e = _l.GemmEpilogue()
+    e.out, e.ldo, e.out_f32, e.act, e.alpha = out.data_ptr(), out.stride(2), 0, act, 1.0
+    if bias is not None:
+        _need(bias, torch.float32, "conv3x3.bias")
+        e.bias = bias.data_ptr()
+    _l.check(lib.pst3r_conv3x3_nhwc(x.data_ptr(), x.stride(2), V, H, W, Cc, w.data_ptr(), cpad, O, C.byref(e), _stream()),
+             "pst3r_conv3x3_nhwc")
+    launches += 1
+    return out
+
+
+def _loftup_ws(V: int, Cc: int, groups: int, device) -> torch.Tensor:
+    return _workspace(_l.load().pst3r_loftup_workspace_bytes(V, Cc, groups) + (1 << 16), device)
+
+
+def loftup_guidance(img: torch.Tensor):
+    """img fp32 [V,3,H,W] -> (half fp32 [V,3,H/2,W/2], minmax fp32 [3,2] over the whole batch)."""
+    global launches
+    lib = _l.load()
+    _need(img, torch.float32, "loftup_guidance.img")
+    img = img.contiguous()
+    V, _, H, W = img.shape
+    half = torch.empty((V, 3, H // 2, W // 2), device=img.device, dtype=torch.float32)
+    minmax = torch.empty((3, 2), device=img.device, dtype=torch.float32)
+    ws = _loftup_ws(V, 3, 1, img.device)
+    _l.check(lib.pst3r_loftup_guidance(img.data_ptr(), V, H, W, half.data_ptr(), minmax.data_ptr(), ws.data_ptr(), _stream()),
+             "pst3r_loftup_guidance")
+    launches += 2
+    return half, minmax
+
+
+def loftup_fourier_gn(half, minmax, gy, gx, freqs, biases, gamma, beta, eps: float, ld: int) -> torch.Tensor:
+    """-> bf16 pixel-major [V, Hh, Wh, ld]: GroupNorm(1)(ImplicitFeaturizer(MinMaxScaler(half)))."""
+    global launches
+    lib = _l.load()
+    for t, n in ((half, "half"), (minmax, "minmax"), (gy, "gy"), (gx, "gx"), (freqs, "freqs"), (biases, "biases"),
+                 (gamma, "gamma"), (beta, "beta")):
+        _need(t, torch.float32, f"loftup_fourier_gn.{n}")
+    V, _, Hh, Wh = half.shape
+    nf = freqs.numel()
+    out = torch.empty((V, Hh, Wh, ld), device=half.device, dtype=torch.bfloat16)
+    ws = _loftup_ws(V, 10 * nf + 3, 1, half.device)
+    _l.check(lib.pst3r_loftup_fourier_gn(half.data_ptr(), minmax.data_ptr(), gy.data_ptr(), gx.data_ptr(), freqs.data_ptr(),
+                                         biases.data_ptr(), V, Hh, Wh, nf, gamma.data_ptr(), beta.data_ptr(), eps,
+                                         out.data_ptr(), ld, ws.data_ptr(), _stream()), "pst3r_loftup_fourier_gn")
+    launches += 3
+    return out
+
+
+def groupnorm_nhwc_(x: torch.Tensor, groups: int, gamma, beta, eps: float, relu: bool) -> torch.Tensor:
+    """In-place GroupNorm(groups) (+ReLU) on a dense pixel-major bf16 map [V, ..., C]."""
+    global launches
+    lib = _l.load()
+    _need(x, torch.bfloat16, "groupnorm.x")
+    if not x.is_contiguous():
+        raise _l.Pst3rError("groupnorm.x: expected contiguous")
+    V, Cc = x.shape[0], x.shape[-1]
+    npix = x.numel() // (V * Cc)
+    ws = _loftup_ws(V, Cc, groups, x.device)
+    _l.check(lib.pst3r_groupnorm_nhwc(x.data_ptr(), V, npix, Cc, groups, gamma.data_ptr(), beta.data_ptr(), eps, int(relu),
+                                      ws.data_ptr(), _stream()), "pst3r_groupnorm_nhwc")
+    launches += 3
+    return x
+
+
 # ---------------------------------------------------------------------------------------------------
 # Per-kernel-kind profiler (CUDA events on the launching stream around every C-ABI call).  Used by bench.py
 # to find the dominant kernel of a step; never active inside a timed region.
@@ -420,5 +501,6 @@ def _attn_kind(a, k):
 gemm = _wrap(gemm, _gemm_kind)
 attention = _wrap(attention, _attn_kind)
 for _n in ("layernorm", "rope2d_", "add_bcast", "to_bf16", "to_f32", "patchify", "dino_preprocess_patchify", "center_pool8",
-           "attn_mask_bits", "l2norm_rows", "nhwc_to_nchw_f32"):
+           "attn_mask_bits", "l2norm_rows", "nhwc_to_nchw_f32", "conv3x3_nhwc", "loftup_guidance", "loftup_fourier_gn",
+           "groupnorm_nhwc_"):
     globals()[_n] = _wrap(globals()[_n], (lambda name: (lambda a, k: name))(_n))
