@@ -124,6 +124,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -337,6 +339,8 @@ template <int HD>
 __global__ void attention_combine_kernel(const float* __restrict__ ws_o, const float* __restrict__ ws_ml, bf16* o,
                                          long long o_sb, long long o_sn, int B, int H, int Nq, int splits,
                                          float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warps_per_block = blockDim.x >> 5;
   const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const long long rows = (long long)B * H * Nq;
@@ -414,26 +418,25 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
     static bool cfg2 = false;
     if (!cfg2) { PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_DYN_BYTES)); cfg2 = true; }
     dim3 grid2((a->Nq + 255) / 256, a->B * a->H, splits);
-    attention2_fwd_kernel<<<grid2, AT2_THREADS, AT2_DYN_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    PST3R_CHECK_CUDA(launch_pdl(attention2_fwd_kernel, grid2, dim3(AT2_THREADS), AT2_DYN_BYTES, stream, tmQ, tmK, tmV, p));
   } else if (a->mask_bits) {
     auto kern = attention_fwd_kernel<HD, true>;
     static bool cfg = false;
     if (!cfg) { PST3R_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::DYN_BYTES)); cfg = true; }
-    kern<<<grid, ATT_THREADS, C::DYN_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    PST3R_CHECK_CUDA(launch_pdl(kern, grid, dim3(ATT_THREADS), C::DYN_BYTES, stream, tmQ, tmK, tmV, p));
   } else {
     auto kern = attention_fwd_kernel<HD, false>;
     static bool cfg = false;
     if (!cfg) { PST3R_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::DYN_BYTES)); cfg = true; }
-    kern<<<grid, ATT_THREADS, C::DYN_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    PST3R_CHECK_CUDA(launch_pdl(kern, grid, dim3(ATT_THREADS), C::DYN_BYTES, stream, tmQ, tmK, tmV, p));
   }
   PST3R_CHECK_CUDA(cudaGetLastError());
   if (splits > 1) {
     const long long rows = (long long)a->B * a->H * a->Nq;
     const int wpb = 8;
     const unsigned blocks = (unsigned)((rows + wpb - 1) / wpb);
-    attention_combine_kernel<HD><<<blocks, wpb * 32, 0, stream>>>(p.ws_o, p.ws_ml, p.o, p.o_sb, p.o_sn, a->B, a->H,
-                                                                  a->Nq, splits, p.scale_log2);
-    PST3R_CHECK_CUDA(cudaGetLastError());
+    PST3R_CHECK_CUDA(launch_pdl(attention_combine_kernel<HD>, dim3(blocks), dim3(wpb * 32), 0, stream, p.ws_o, p.ws_ml, p.o,
+                                p.o_sb, p.o_sn, a->B, a->H, a->Nq, splits, p.scale_log2));
   }
   return PST3R_OK;
 }

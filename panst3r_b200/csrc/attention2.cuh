@@ -100,6 +100,8 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------

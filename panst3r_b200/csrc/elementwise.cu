@@ -62,6 +62,8 @@ layernorm_vec_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __re
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, void* __restrict__ y,
                      long long ldy, bf16* __restrict__ sum_out, long long ld_sum, int rows, int dim, int x_rpb,
                      long long x_bs) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -396,11 +398,11 @@ extern "C" int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const 
     const bf16* xb = reinterpret_cast<const bf16*>(x);
 #define PST3R_LN_CASE(V)                                                                                              \
   if (y_f32)                                                                                                          \
-    layernorm_vec_kernel<V, true><<<grid, wpb * 32, 0, s>>>(xb, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, \
-                                                             rows, dim, x_rpb, x_bs);                                  \
+    PST3R_CHECK_CUDA(launch_pdl(layernorm_vec_kernel<V, true>, dim3(grid), dim3(wpb * 32), 0, s, xb, ldx, a, ld_add, gamma, \
+                                beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs));                              \
   else                                                                                                                \
-    layernorm_vec_kernel<V, false><<<grid, wpb * 32, 0, s>>>(xb, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, \
-                                                              rows, dim, x_rpb, x_bs);
+    PST3R_CHECK_CUDA(launch_pdl(layernorm_vec_kernel<V, false>, dim3(grid), dim3(wpb * 32), 0, s, xb, ldx, a, ld_add, gamma, \
+                                beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs));
     if (vpl <= 2) { PST3R_LN_CASE(2) }
     else if (vpl <= 4) { PST3R_LN_CASE(4) }
     else if (vpl <= 8) { PST3R_LN_CASE(8) }

@@ -11,6 +11,8 @@
 //   warps 2..9  : epilogue, two warps per TMEM lane quadrant taking alternate 32-column chunks
 //                 (tcgen05.ld 32 lanes x 32 cols -> registers -> math -> global)
 //   TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the mainloop of tile i+1.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/panst3r_b200.h"
@@ -276,6 +278,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // prologue done: the next kernel's prologue may overlap our main loop's tail
+  pdl_wait();               // predecessor's global writes are visible from here on
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -396,12 +400,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
-  PST3R_CHECK_CUDA(cudaGetLastError());
+  PST3R_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::DYN_BYTES, stream, tmA, tmB, ep, M, N, K));
   return PST3R_OK;
 }
 
 }  // namespace pst3r
+
+#include "gemm2.cuh"
 
 using namespace pst3r;
 
@@ -456,6 +461,21 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
     const long long cost = waves * (128 + cand);
     if (best < 0 || cost < best || (cost == best && cand > BN)) { best = cost; BN = cand; }
     if (cand >= N) break;  // wider tiles would only add padding
+  }
+
+  // large plain GEMMs with N % 256 == 0 go to the 2-CTA kernel (256 x 256 tiles per SM pair)
+  const bool use2 = !conv && gemm2_enabled() && (N % G2_BN) == 0 &&
+                    (long long)((M + 255) / 256) * (N / G2_BN) >= (sms / 2);
+  if (use2) {
+    CUtensorMap tA2, tB2;
+    uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[2] = {2, (uint64_t)lda * 2};
+    uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[2] = {2, (uint64_t)ldb * 2};
+    uint32_t bA[2] = {GEMM_BK, GEMM_BM}, bB[2] = {GEMM_BK, G2_BN / 2};
+    int r = encode_tmap(&tA2, A, 2, 2, dA, sA, bA);
+    if (r) return r;
+    r = encode_tmap(&tB2, B, 2, 2, dB, sB, bB);
+    if (r) return r;
+    return launch_gemm2(tA2, tB2, ep, M, N, K, stream);
   }
 
   CUtensorMap tmA, tmB;

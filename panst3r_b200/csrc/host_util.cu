@@ -2,6 +2,7 @@
 
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace pst3r {
 
@@ -80,6 +81,15 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
     return PST3R_ERR_DRIVER;
   }
   return PST3R_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PST3R_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int num_sms() {

@@ -51,4 +51,24 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
 
 int num_sms();
 
+// Programmatic dependent launch (PDL): the kernel may start while its stream predecessor drains; every kernel
+// launched this way executes griddepcontrol.wait (pdl_wait() in common.cuh) before touching global memory.
+// PST3R_PDL=0 in the environment disables the attribute (plain stream order).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace pst3r
