@@ -38,6 +38,12 @@ const char* pst3r_last_error(void);
 int pst3r_version(void);
 /* Returns 0 if the current CUDA device is sm_100 (B200); <0 otherwise. */
 int pst3r_check_device(void);
+int pst3r_num_sms(void);
+/* Limits the SMs the following launches may fill (persistent grids, tile / split heuristics); 0 = all.  Returns the
+ * previous budget.  Host-side setting read at launch time: lets the latency-bound sequential memory build
+ * (engine/must3r.py:40-54) and the throughput-bound DINOv2 encoder (model/dino.py:59-71) run side by side on
+ * two streams, each on its own share of the 148 SMs. */
+int pst3r_set_sm_budget(int32_t n_sms);
 
 /* ---- GEMM: C[M,N] = epilogue(A[M,K] * B[N,K]^T) ---------------------------------------------
  * A, B are bf16, K contiguous (row strides lda/ldb in elements, multiples of 8).  tcgen05 tensor cores,
@@ -84,6 +90,16 @@ typedef struct pst3r_gemm_epilogue {
 int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
                     const pst3r_gemm_epilogue* epi, pst3r_stream_t stream);
 
+/* Strided-batched variant: problem b (0 <= b < batches) computes epi(A_b * B_b^T) with A_b = A + b*a_batch_stride,
+ * B_b = B + b*b_batch_stride (elements), out_b = epi->out + b*out_batch_stride, bias_b = epi->bias + b*bias_batch_stride.
+ * One launch covers all problems (3-D TMA maps; the tile scheduler walks (batch, m, n)).  PLAIN store with bias /
+ * activation only.  Used for the per-layer K|V projections of freshly appended memory tokens: 12 decoder layers,
+ * one launch (upstream MUSt3R memory update driven from engine/must3r.py:45). */
+int pst3r_gemm_bf16_batched(const void* A, int64_t lda, int64_t a_batch_stride, const void* B, int64_t ldb,
+                            int64_t b_batch_stride, int32_t M, int32_t N, int32_t K, int32_t batches,
+                            const pst3r_gemm_epilogue* epi, int64_t out_batch_stride, int64_t bias_batch_stride,
+                            pst3r_stream_t stream);
+
 /* 3x3 convolution, stride 1, zero padding 1, over a pixel-major bf16 map x [V, H, W, ldx] (C <= ldx valid channels)
  * as an implicit GEMM: out[(v, y, x), o] = epi(sum_{ky,kx,c} x[v, y+ky-1, x+kx-1, c] * w[o, (ky*3+kx)*cpad + c]).
  * w is bf16 [O, 9*cpad] (Conv2d weight [O, C, 3, 3] permuted to tap-major and zero-padded to cpad, cpad % 64 == 0).
@@ -125,6 +141,16 @@ int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const void* add, 
                     const float* beta, float eps, void* y, int32_t y_f32, int64_t ldy, void* sum_out,
                     int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rows_per_batch, int64_t x_batch_stride,
                     pst3r_stream_t stream);
+
+/* Batched LayerNorm over `batches` equally shaped bf16 matrices with per-batch parameters:
+ *   y[b][r] = LN(x[b][r] + add[r]) * gamma[b] + beta[b],   x[b] = x + b*x_batch_stride, y[b] = y + b*y_batch_stride,
+ *   gamma[b] = gamma + b*param_batch_stride (same for beta); `add` (may be NULL) is shared by all batches.
+ * One launch normalises the 12 per-layer memory-token sets of a MUSt3R memory update (norm_y of
+ * layer input + feedback, memory_mode='norm_y', configs/base.yaml:12-15). */
+int pst3r_layernorm_batched(const void* x, int64_t ldx, int64_t x_batch_stride, const void* add, int64_t ld_add,
+                            const float* gamma, const float* beta, int64_t param_batch_stride, float eps, void* y,
+                            int64_t ldy, int64_t y_batch_stride, int32_t rows_per_batch, int32_t batches, int32_t dim,
+                            pst3r_stream_t stream);
 
 /* In-place 2-D RoPE, curope semantics: tokens bf16 [B, N, H, D] (D contiguous, D % 4 == 0),
  * positions int32 [B, N, 2] = (y, x); angle = p * base^(-j/(D/4)); fwd = +1 / -1. */

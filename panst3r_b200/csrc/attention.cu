@@ -448,7 +448,7 @@ using namespace pst3r;
 extern "C" int32_t pst3r_attention_auto_splits(int32_t B, int32_t H, int32_t Nq, int32_t Nk) {
   const int ctas = ((Nq + 255) / 256) * B * H;  // CTAs of the 256-query kernel (a slight over-split for the 128-query one)
   const int tiles = (Nk + ATT_BN - 1) / ATT_BN;
-  const int sms = num_sms();
+  const int sms = sm_budget();
   if (ctas >= sms || tiles <= 1) return 1;
   int s = sms / ctas;
   if (s > tiles) s = tiles;

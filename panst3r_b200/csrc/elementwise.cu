@@ -61,16 +61,24 @@ __global__ void __launch_bounds__(256)
 layernorm_vec_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ add, long long ld_add,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, void* __restrict__ y,
                      long long ldy, bf16* __restrict__ sum_out, long long ld_sum, int rows, int dim, int x_rpb,
-                     long long x_bs) {
+                     long long x_bs, long long y_bs, long long p_bs, int add_mod) {
+  // x_rpb > 0: row = (batch, local row); x is read at batch * x_bs + local * ldx.  Batched mode additionally
+  // writes y at batch * y_bs + local * ldy (y_bs != 0), uses gamma/beta + batch * p_bs and, with add_mod, the
+  // SAME `add` rows for every batch (add row = local row).
   pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nvec = dim >> 3;
-  const long long xo = x_rpb > 0 ? (long long)(row / x_rpb) * x_bs + (long long)(row % x_rpb) * ldx : (long long)row * ldx;
+  const int bidx = x_rpb > 0 ? row / x_rpb : 0;
+  const int lrow = x_rpb > 0 ? row - bidx * x_rpb : row;
+  const long long xo = x_rpb > 0 ? (long long)bidx * x_bs + (long long)lrow * ldx : (long long)row * ldx;
+  const long long yo = y_bs != 0 ? (long long)bidx * y_bs + (long long)lrow * ldy : (long long)row * ldy;
+  gamma += bidx * p_bs;
+  beta += bidx * p_bs;
   const uint4* xp = reinterpret_cast<const uint4*>(x + xo);
-  const uint4* ap = add ? reinterpret_cast<const uint4*>(add + (long long)row * ld_add) : nullptr;
+  const uint4* ap = add ? reinterpret_cast<const uint4*>(add + (long long)(add_mod ? lrow : row) * ld_add) : nullptr;
   float v[VPL][8];
   float s = 0.0f;
 #pragma unroll
@@ -130,14 +138,14 @@ layernorm_vec_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __re
       o[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
       o[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
       if (Y_F32) {
-        float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (long long)row * ldy) + 2 * vi;
+        float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + yo) + 2 * vi;
         yp[0] = make_float4(o[0], o[1], o[2], o[3]);
         yp[1] = make_float4(o[4], o[5], o[6], o[7]);
       } else {
         uint4 u;
         u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
         u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-        reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(y) + (long long)row * ldy)[vi] = u;
+        reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(y) + yo)[vi] = u;
       }
     }
   }
@@ -379,10 +387,10 @@ extern "C" int pst3r_check_device(void) {
   return PST3R_OK;
 }
 
-extern "C" int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const void* add, int64_t ld_add,
-                               const float* gamma, const float* beta, float eps, void* y, int32_t y_f32, int64_t ldy,
-                               void* sum_out, int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rpb, int64_t x_bs,
-                               pst3r_stream_t s_) {
+static int layernorm_run(const void* x, int32_t x_f32, int64_t ldx, const void* add, int64_t ld_add,
+                         const float* gamma, const float* beta, float eps, void* y, int32_t y_f32, int64_t ldy,
+                         void* sum_out, int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rpb, int64_t x_bs,
+                         int64_t y_bs, int64_t p_bs, int32_t add_mod, pst3r_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
   PST3R_CHECK_ARG(x && gamma && beta && y && rows > 0 && dim > 0, "layernorm: bad args");
   const int wpb = 8;
@@ -392,17 +400,18 @@ extern "C" int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const 
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec_ok = !x_f32 && (dim % 8) == 0 && dim <= 12 * 256 && (ldx % 8) == 0 && (x_bs % 8) == 0 && al16(x) &&
                       (!add || ((ld_add % 8) == 0 && al16(add))) && (!sum_out || ((ld_sum % 8) == 0 && al16(sum_out))) &&
-                      al16(y) && (ldy % (y_f32 ? 4 : 8)) == 0 && al16(gamma) && al16(beta);
+                      al16(y) && (ldy % (y_f32 ? 4 : 8)) == 0 && al16(gamma) && al16(beta) &&
+                      (y_bs % (y_f32 ? 4 : 8)) == 0 && (p_bs % 4) == 0;
   if (vec_ok) {
     const int vpl = (dim / 8 + 31) / 32;
     const bf16* xb = reinterpret_cast<const bf16*>(x);
 #define PST3R_LN_CASE(V)                                                                                              \
   if (y_f32)                                                                                                          \
     PST3R_CHECK_CUDA(launch_pdl(layernorm_vec_kernel<V, true>, dim3(grid), dim3(wpb * 32), 0, s, xb, ldx, a, ld_add, gamma, \
-                                beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs));                              \
+                                beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs, y_bs, p_bs, add_mod));       \
   else                                                                                                                \
     PST3R_CHECK_CUDA(launch_pdl(layernorm_vec_kernel<V, false>, dim3(grid), dim3(wpb * 32), 0, s, xb, ldx, a, ld_add, gamma, \
-                                beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs));
+                                beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs, y_bs, p_bs, add_mod));
     if (vpl <= 2) { PST3R_LN_CASE(2) }
     else if (vpl <= 4) { PST3R_LN_CASE(4) }
     else if (vpl <= 8) { PST3R_LN_CASE(8) }
@@ -411,6 +420,7 @@ extern "C" int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const 
     PST3R_CHECK_CUDA(cudaGetLastError());
     return PST3R_OK;
   }
+  PST3R_CHECK_ARG(y_bs == 0 && p_bs == 0 && !add_mod, "layernorm_batched: needs bf16 rows, dim %% 8 == 0, 16-byte alignment");
   if (x_f32 && y_f32)
     layernorm_kernel<true, true><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs);
   else if (x_f32)
@@ -421,6 +431,23 @@ extern "C" int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const 
     layernorm_kernel<false, false><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs);
   PST3R_CHECK_CUDA(cudaGetLastError());
   return PST3R_OK;
+}
+
+extern "C" int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const void* add, int64_t ld_add,
+                               const float* gamma, const float* beta, float eps, void* y, int32_t y_f32, int64_t ldy,
+                               void* sum_out, int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rpb, int64_t x_bs,
+                               pst3r_stream_t s_) {
+  return layernorm_run(x, x_f32, ldx, add, ld_add, gamma, beta, eps, y, y_f32, ldy, sum_out, ld_sum, rows, dim, x_rpb, x_bs,
+                       0, 0, 0, s_);
+}
+
+extern "C" int pst3r_layernorm_batched(const void* x, int64_t ldx, int64_t x_batch_stride, const void* add, int64_t ld_add,
+                                       const float* gamma, const float* beta, int64_t param_batch_stride, float eps,
+                                       void* y, int64_t ldy, int64_t y_batch_stride, int32_t rows_per_batch,
+                                       int32_t batches, int32_t dim, pst3r_stream_t s_) {
+  PST3R_CHECK_ARG(rows_per_batch > 0 && batches > 0 && y_batch_stride != 0, "layernorm_batched: bad args");
+  return layernorm_run(x, 0, ldx, add, ld_add, gamma, beta, eps, y, 0, ldy, nullptr, 0, rows_per_batch * batches, dim,
+                       rows_per_batch, x_batch_stride, y_batch_stride, param_batch_stride, 1, s_);
 }
 
 extern "C" int pst3r_rope2d(void* tokens, int64_t s_b, int64_t s_n, int64_t s_h, const int32_t* pos, int32_t B,

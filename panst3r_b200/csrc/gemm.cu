@@ -41,6 +41,10 @@ struct GemmEpi {
   // implicit-GEMM 3x3 convolution over a pixel-major [V, Hc, Wc, C] map (A is a 4-D TMA map; OOB = zero padding)
   int conv_cblocks;  // 64-channel blocks per tap (0 = plain GEMM)
   int conv_w, conv_h, conv_tpr;  // map width / height, 128-pixel tiles per image row
+  // strided-batched mode (batches > 1): problem b reads A/B through the third TMA coordinate and writes
+  // out + b * out_bs with bias + b * bias_bs (PLAIN store only)
+  int batches;
+  long long out_bs, bias_bs;
 };
 
 constexpr int GEMM_BM = 128;
@@ -58,7 +62,8 @@ struct GemmSmem {
 };
 
 // ---- epilogue for one 32-column chunk owned by one thread (one output row) --------------------
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32], int row, int col0, int M, int N) {
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32], int row, int col0, int M, int N,
+                                               int bidx = 0) {
   if (row >= M || col0 >= N) return;
   const int ncols = min(32, N - col0);
   const bool full = (ncols == 32);
@@ -68,8 +73,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
     for (int i = 0; i < 32; ++i) v[i] *= ep.alpha;
   }
   if (ep.bias) {
+    const float* bias = ep.bias + bidx * ep.bias_bs;
     if (full) {
-      const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+      const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float4 b = __ldg(b4 + i);
@@ -78,7 +84,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (i < ncols) v[i] += __ldg(ep.bias + col0 + i);
+        if (i < ncols) v[i] += __ldg(bias + col0 + i);
     }
   }
   if (ep.rope_cs && col0 < ep.rope_cols) {
@@ -86,13 +92,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
     const int half = (col0 >> 5) & 1;
     int p = __ldg(ep.rope_pos + 2 * (long long)row + half);
     p = max(0, min(p, ep.rope_maxpos - 1));
-    const float2* cs = ep.rope_cs + (long long)p * 16;
+    const float4* cs = reinterpret_cast<const float4*>(ep.rope_cs + (long long)p * 16);  // 128 B per position
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float2 c = __ldg(cs + j);
-      const float a = v[j], b = v[j + 16];
-      v[j] = a * c.x - b * c.y;
-      v[j + 16] = b * c.x + a * c.y;
+    for (int j = 0; j < 8; ++j) {
+      const float4 c = __ldg(cs + j);  // (cos, sin) of frequencies 2j, 2j+1
+      const float a0 = v[2 * j], b0 = v[2 * j + 16], a1 = v[2 * j + 1], b1 = v[2 * j + 17];
+      v[2 * j] = a0 * c.x - b0 * c.y;
+      v[2 * j + 16] = b0 * c.x + a0 * c.y;
+      v[2 * j + 1] = a1 * c.z - b1 * c.w;
+      v[2 * j + 17] = b1 * c.z + a1 * c.w;
     }
   }
   if (ep.act == PST3R_ACT_GELU) {
@@ -130,7 +138,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
 
   switch (ep.store_mode) {
     case PST3R_STORE_PLAIN: {
-      long long roff = (long long)row * ep.ldo;
+      long long roff = (long long)row * ep.ldo + bidx * ep.out_bs;
       if (ep.rows_per_batch > 0) {
         const long long bb = row / ep.rows_per_batch;
         roff = bb * ep.batch_stride + (row - bb * ep.rows_per_batch) * ep.ldo;
@@ -253,7 +261,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int num_m_blocks = (M + GEMM_BM - 1) / GEMM_BM;
   const int num_n_blocks = (N + BN - 1) / BN;
-  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int tiles_per_batch = num_m_blocks * num_n_blocks;
+  const int num_tiles = tiles_per_batch * ep.batches;
   const int num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
@@ -287,8 +296,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m_blocks;
-        const int n_blk = tile / num_m_blocks;
+        const int bidx = tile / tiles_per_batch;
+        const int trem = tile - bidx * tiles_per_batch;
+        const int m_blk = trem % num_m_blocks;
+        const int n_blk = trem / num_m_blocks;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
@@ -300,10 +311,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int xb = m_blk % ep.conv_tpr, rowidx = m_blk / ep.conv_tpr;
             tma_load_4d(a_dst, &tmA, &full_bar[s], cb * 64, xb * GEMM_BM + tap % 3 - 1, rowidx % ep.conv_h + tap / 3 - 1,
                         rowidx / ep.conv_h);
+          } else if (ep.batches > 1) {
+            tma_load_3d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM, bidx);
           } else {
             tma_load_2d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
           }
-          tma_load_2d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
+          if (ep.batches > 1)
+            tma_load_3d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN, bidx);
+          else
+            tma_load_2d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -315,7 +331,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t ph = 0;
       int local = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-        const int n_blk = tile / num_m_blocks;
+        const int n_blk = (tile % tiles_per_batch) / num_m_blocks;
         const int n_rem = N - n_blk * BN;
         const int n_mma = n_rem >= BN ? BN : ((n_rem + 15) & ~15);
         const uint32_t idesc = make_idesc_bf16(GEMM_BM, n_mma, 0, 0);
@@ -348,8 +364,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int cgrp = (warp - 2) >> 2;  // which half of the 32-column chunks
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const int m_blk = tile % num_m_blocks;
-      const int n_blk = tile / num_m_blocks;
+      const int bidx = tile / tiles_per_batch;
+      const int trem = tile - bidx * tiles_per_batch;
+      const int m_blk = trem % num_m_blocks;
+      const int n_blk = trem / num_m_blocks;
       const int acc = local & 1;
       const uint32_t acc_ph = (local >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_ph);
@@ -372,7 +390,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_chunk(ep, v, row, n_blk * BN + c * 32, m_lim, N);
+        epilogue_chunk(ep, v, row, n_blk * BN + c * 32, m_lim, N, bidx);
       }
       tc_fence_before();
       __syncwarp();
@@ -398,8 +416,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     PST3R_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     configured = true;
   }
-  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN) * ep.batches;
+  const int grid = tiles < sm_budget() ? tiles : sm_budget();
   PST3R_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::DYN_BYTES, stream, tmA, tmB, ep, M, N, K));
   return PST3R_OK;
 }
@@ -411,9 +429,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 using namespace pst3r;
 
 struct ConvCfg { int V, H, W, C, cpad; };
+struct BatchCfg { int batches; long long a_bs, b_bs, out_bs, bias_bs; };
 
 static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
-                    const pst3r_gemm_epilogue* e, pst3r_stream_t stream_, const ConvCfg* conv) {
+                    const pst3r_gemm_epilogue* e, pst3r_stream_t stream_, const ConvCfg* conv,
+                    const BatchCfg* bat = nullptr) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PST3R_CHECK_ARG(A && B && e && e->out, "gemm: null pointer");
   PST3R_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
@@ -430,8 +450,9 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
                         N == e->d2s_patch * e->d2s_patch * e->d2s_ch && (M % (e->grid_h * e->grid_w)) == 0,
                     "gemm: D2S store needs grid/patch/channels, N == P*P*C, fp32 out");
   if (e->rope_cs)
-    PST3R_CHECK_ARG(e->rope_pos && e->rope_cols > 0 && (e->rope_cols % 64) == 0 && e->rope_maxpos > 0,
-                    "gemm: rope epilogue needs pos, rope_cols %% 64 == 0, maxpos");
+    PST3R_CHECK_ARG(e->rope_pos && e->rope_cols > 0 && (e->rope_cols % 64) == 0 && e->rope_maxpos > 0 &&
+                        (reinterpret_cast<uintptr_t>(e->rope_cs) & 15) == 0,
+                    "gemm: rope epilogue needs pos, rope_cols %% 64 == 0, maxpos, 16-byte aligned table");
 
   GemmEpi ep;
   ep.out = e->out; ep.ldo = e->ldo; ep.out_f32 = e->out_f32; ep.act = e->act;
@@ -443,12 +464,17 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   ep.rope_cs = reinterpret_cast<const float2*>(e->rope_cs); ep.rope_pos = e->rope_pos;
   ep.rope_cols = e->rope_cols; ep.rope_maxpos = e->rope_maxpos;
   ep.conv_cblocks = 0; ep.conv_w = ep.conv_h = ep.conv_tpr = 0;
+  ep.batches = 1; ep.out_bs = 0; ep.bias_bs = 0;
+  const int nb = bat ? bat->batches : 1;
+  if (nb > 1) {
+    ep.batches = nb; ep.out_bs = bat->out_bs; ep.bias_bs = bat->bias_bs;
+  }
   if (conv) {
     ep.conv_cblocks = conv->cpad / 64; ep.conv_w = conv->W; ep.conv_h = conv->H; ep.conv_tpr = (conv->W + GEMM_BM - 1) / GEMM_BM;
   }
 
   // Tile-width heuristic: the widest BN whose tile count still fills the machine.
-  const int sms = num_sms();
+  const int sms = sm_budget();
   const int mb = (M + GEMM_BM - 1) / GEMM_BM;
   // A CTA ingests (128 + BN) x 64 bf16 per k-block and is bound by its L2->smem rate long before the tensor pipe
   // (measured: 128x256 tiles run at ~65 % of the cuBLAS peak), so pick the BN that minimises
@@ -456,7 +482,7 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   int BN = 64;
   long long best = -1;
   for (int cand = 64; cand <= 256; cand *= 2) {
-    const long long tiles = (long long)mb * ((N + cand - 1) / cand);
+    const long long tiles = (long long)mb * ((N + cand - 1) / cand) * nb;
     const long long waves = (tiles + sms - 1) / sms;
     const long long cost = waves * (128 + cand);
     if (best < 0 || cost < best || (cost == best && cand > BN)) { best = cost; BN = cand; }
@@ -464,7 +490,7 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   }
 
   // large plain GEMMs with N % 256 == 0 go to the 2-CTA kernel (256 x 256 tiles per SM pair)
-  const bool use2 = !conv && gemm2_enabled() && (N % G2_BN) == 0 &&
+  const bool use2 = !conv && nb == 1 && gemm2_enabled() && (N % G2_BN) == 0 &&
                     (long long)((M + 255) / 256) * (N / G2_BN) >= (sms / 2);
   if (use2) {
     CUtensorMap tA2, tB2;
@@ -487,6 +513,13 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
     uint32_t box[4] = {GEMM_BK, GEMM_BM, 1, 1};
     int r = encode_tmap(&tmA, A, 2, 4, dims, str, box);
     if (r) return r;
+  } else if (nb > 1) {
+    // rows beyond M of problem b are out of bounds of dimension 1 (zero filled), never rows of problem b + 1
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)nb};
+    uint64_t str[3] = {2, (uint64_t)lda * 2, (uint64_t)bat->a_bs * 2};
+    uint32_t box[3] = {GEMM_BK, GEMM_BM, 1};
+    int r = encode_tmap(&tmA, A, 2, 3, dims, str, box);
+    if (r) return r;
   } else {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     uint64_t str[2] = {2, (uint64_t)lda * 2};
@@ -494,7 +527,13 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
     int r = encode_tmap(&tmA, A, 2, 2, dims, str, box);
     if (r) return r;
   }
-  {
+  if (nb > 1) {
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)nb};
+    uint64_t str[3] = {2, (uint64_t)ldb * 2, (uint64_t)bat->b_bs * 2};
+    uint32_t box[3] = {GEMM_BK, (uint32_t)BN, 1};
+    int r = encode_tmap(&tmB, B, 2, 3, dims, str, box);
+    if (r) return r;
+  } else {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t str[2] = {2, (uint64_t)ldb * 2};
     uint32_t box[2] = {GEMM_BK, (uint32_t)BN};
@@ -511,6 +550,20 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
 extern "C" int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N,
                                int32_t K, const pst3r_gemm_epilogue* e, pst3r_stream_t stream) {
   return gemm_run(A, lda, B, ldb, M, N, K, e, stream, nullptr);
+}
+
+extern "C" int pst3r_gemm_bf16_batched(const void* A, int64_t lda, int64_t a_batch_stride, const void* B, int64_t ldb,
+                                       int64_t b_batch_stride, int32_t M, int32_t N, int32_t K, int32_t batches,
+                                       const pst3r_gemm_epilogue* e, int64_t out_batch_stride, int64_t bias_batch_stride,
+                                       pst3r_stream_t stream) {
+  PST3R_CHECK_ARG(e && batches > 0, "gemm_batched: bad args");
+  PST3R_CHECK_ARG(e->store_mode == PST3R_STORE_PLAIN && e->rows_per_batch == 0 && !e->residual && !e->rope_cs &&
+                      !e->col_scale, "gemm_batched: plain store, bias / activation epilogue only");
+  PST3R_CHECK_ARG((a_batch_stride % 8) == 0 && (b_batch_stride % 8) == 0 && (bias_batch_stride % 4) == 0 &&
+                      (out_batch_stride % (e->out_f32 ? 4 : 8)) == 0,
+                  "gemm_batched: batch strides must keep 16-byte alignment");
+  BatchCfg bc{batches, a_batch_stride, b_batch_stride, out_batch_stride, bias_batch_stride};
+  return gemm_run(A, lda, B, ldb, M, N, K, e, stream, nullptr, batches > 1 ? &bc : nullptr);
 }
 
 extern "C" int pst3r_conv3x3_nhwc(const void* x, int64_t ldx, int32_t V, int32_t H, int32_t W, int32_t C, const void* w,

@@ -223,7 +223,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
     configured = true;
   }
   const int tiles = ((M + 255) / 256) * (N / G2_BN);
-  const int max_pairs = num_sms() / 2;
+  const int max_pairs = sm_budget() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);

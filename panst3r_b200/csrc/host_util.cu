@@ -104,4 +104,18 @@ int num_sms() {
   return n;
 }
 
+static int g_sm_budget = 0;
+int sm_budget() {
+  const int n = num_sms();
+  return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
+}
+void set_sm_budget(int n) { g_sm_budget = n > 0 ? n : 0; }
+
 }  // namespace pst3r
+
+extern "C" int pst3r_set_sm_budget(int32_t n) {
+  const int prev = pst3r::sm_budget();
+  pst3r::set_sm_budget(n);
+  return prev;
+}
+extern "C" int pst3r_num_sms(void) { return pst3r::num_sms(); }

@@ -50,6 +50,11 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
                 const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128 = true);
 
 int num_sms();
+// SMs the launchers may fill (<= num_sms()).  Persistent kernels size their grids with it and the tile / split
+// heuristics count waves against it, so that two streams can share the GPU side by side (the latency-bound sequential
+// memory build next to the throughput-bound DINOv2 encoder).  Set through pst3r_set_sm_budget(); 0 = all SMs.
+int sm_budget();
+void set_sm_budget(int n);
 
 // Programmatic dependent launch (PDL): the kernel may start while its stream predecessor drains; every kernel
 // launched this way executes griddepcontrol.wait (pdl_wait() in common.cuh) before touching global memory.

@@ -81,25 +81,29 @@ class ShardedPanSt3R:
         cur = torch.cuda.current_stream()
         side = m._side_stream or torch.cuda.Stream()
         m._side_stream = side
+        dino_sms = m.dino_sms if (nv > 0 and m.overlap_dino) else 0
         if nv > 0:
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                m.forward_dino(my_imgs, my_ts, out=rows[:, ENC_DIM + DEC_DIM:])
             x_loc, _ = m.forward_must3r_encoder(my_imgs, my_ts, out=rows[:, :ENC_DIM])
             x_loc = x_loc[0]
+            # DINOv2 of the local views shares the GPU with the (replicated, latency-bound) memory build below
+            side.wait_stream(cur)
+            with torch.cuda.stream(side), ops.sm_budget(dino_sms):
+                m.forward_dino(my_imgs, my_ts, out=rows[:, ENC_DIM + DEC_DIM:])
         else:
             x_loc = torch.empty((0, N, ENC_DIM), device=dev, dtype=torch.bfloat16)
         # ---- exchange 1: encoder tokens of every view, then the replicated sequential memory build
         x_all = gather_rows(x_loc, counts, self.group).view(1, V, N, ENC_DIM)
         from .modules.common import pos_grid
         pos_all = pos_grid(hs, ws, dev)[0][None, None].expand(1, V, N, 2)
-        mem = m.build_memory(x_all, pos_all, ts)
+        with ops.sm_budget(max(ops.num_sms() - dino_sms, 8) if dino_sms else 0):
+            mem = m.build_memory(x_all, pos_all, ts)
+        if nv > 0:
+            cur.wait_stream(side)
         pointmaps = None
         mt = m.panoptic_decoder.mask_transformer
         if nv > 0:
             _, pointmaps, _ = m.must3r_decoder(x_all[:, s:e], pos_all[:, s:e], my_ts, mem, render=True, return_feats="last",
                                                feats_out=rows[:, ENC_DIM:ENC_DIM + DEC_DIM])
-            cur.wait_stream(side)
             src_loc, mask_f = m.panoptic_decoder.upscaler.forward_nhwc(rows, nv, hs, ws, f16_extra_bias=mt.level_embed.weight)
             Cm = mask_f.shape[-1]
             pooled_loc = ops.center_pool8(mask_f).view(nv * N, Cm)

@@ -62,6 +62,11 @@ SIGNATURES = {
     "pst3r_last_error": (C.c_char_p, []),
     "pst3r_version": (C.c_int, []),
     "pst3r_check_device": (C.c_int, []),
+    "pst3r_num_sms": (C.c_int, []),
+    "pst3r_set_sm_budget": (C.c_int, [_i32]),
+    "pst3r_gemm_bf16_batched": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, C.POINTER(GemmEpilogue),
+                                          _i64, _i64, _p]),
+    "pst3r_layernorm_batched": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _i64, _f, _p, _i64, _i64, _i32, _i32, _i32, _p]),
     "pst3r_gemm_bf16": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _i32, C.POINTER(GemmEpilogue), _p]),
     "pst3r_conv3x3_nhwc": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, C.POINTER(GemmEpilogue), _p]),
     "pst3r_loftup_workspace_bytes": (_i64, [_i32, _i32, _i32]),

@@ -89,24 +89,29 @@ class _DecBlock(ViTBlockParams):
 
 
 class MemoryBank:
-    """Per-layer memory tokens (B, cap, D) and their K|V projections (B, cap, 2D), bf16, capacity-doubling."""
+    """Memory tokens (L, B, cap, D) and their K|V projections (L, B, cap, 2D) of all decoder layers, bf16,
+    capacity-doubling.  One allocation per kind so that the per-layer appends of a memory update are ONE
+    strided-batched LayerNorm + ONE strided-batched GEMM; tok[l] / kv[l] are the per-layer (B, cap, .) views."""
 
     def __init__(self, B: int, depth: int, dim: int, device, capacity: int):
         self.B, self.depth, self.dim, self.n = B, depth, dim, 0
         self.cap = max(capacity, 1)
-        self.tok = [torch.empty((B, self.cap, dim), device=device, dtype=torch.bfloat16) for _ in range(depth)]
-        self.kv = [torch.empty((B, self.cap, 2 * dim), device=device, dtype=torch.bfloat16) for _ in range(depth)]
+        self._alloc(device)
+
+    def _alloc(self, device):
+        self.tok_all = torch.empty((self.depth, self.B, self.cap, self.dim), device=device, dtype=torch.bfloat16)
+        self.kv_all = torch.empty((self.depth, self.B, self.cap, 2 * self.dim), device=device, dtype=torch.bfloat16)
+        self.tok = [self.tok_all[l] for l in range(self.depth)]
+        self.kv = [self.kv_all[l] for l in range(self.depth)]
 
     def reserve(self, n_total: int):
         if n_total <= self.cap:
             return
-        cap = max(n_total, 2 * self.cap)
-        for lst, width in ((self.tok, self.dim), (self.kv, 2 * self.dim)):
-            for l in range(self.depth):
-                nb = torch.empty((self.B, cap, width), device=lst[l].device, dtype=torch.bfloat16)
-                nb[:, :self.n].copy_(lst[l][:, :self.n])
-                lst[l] = nb
-        self.cap = cap
+        old_tok, old_kv = self.tok_all, self.kv_all
+        self.cap = max(n_total, 2 * self.cap)
+        self._alloc(old_tok.device)
+        self.tok_all[:, :, :self.n].copy_(old_tok[:, :, :self.n])
+        self.kv_all[:, :, :self.n].copy_(old_kv[:, :, :self.n])
 
 
 class MemVals(list):
@@ -147,6 +152,19 @@ class MUSt3R(nn.Module):
         # reference row order (c, i, j) -> (i, j, c): the D2S epilogue then writes C-contiguous pixels
         return prepared("head_w", [wt], lambda: wt.detach().view(C, P, P, D).permute(1, 2, 0, 3).reshape(P * P * C, D)
                         .to(torch.bfloat16).contiguous())
+
+    def _stacked(self, what: str):
+        """Per-layer parameters of the memory update stacked along a leading layer axis (batched launches)."""
+        blks = list(self.blocks_dec)
+        if what == "kv_w":
+            ps = [p for b in blks for p in (b.cross_attn.projk.weight, b.cross_attn.projv.weight)]
+            return prepared("stk_kv_w", ps, lambda: torch.stack([b.kv_weight() for b in blks]).contiguous())
+        if what == "kv_b":
+            ps = [p for b in blks for p in (b.cross_attn.projk.bias, b.cross_attn.projv.bias)]
+            return prepared("stk_kv_b", ps, lambda: torch.stack([b.kv_bias() for b in blks]).contiguous())
+        attr = {"ny_g": "weight", "ny_b": "bias"}[what]
+        ps = [getattr(b.norm_y, attr) for b in blks]
+        return prepared("stk_" + what, ps, lambda: torch.stack([p.detach().float() for p in ps]).contiguous())
 
     def _head_bias(self):
         P, C = self.patch_size, self.head_channels
@@ -201,7 +219,9 @@ class MUSt3R(nn.Module):
         rope = (rope_table(max(h_, w_), D // self.num_heads, self.rope_base, dev), pos32.repeat(B * n, 1))
 
         # enc -> dec embedding; every view except the scene's first is tagged with image2_embed (fused as a bias)
-        hx = torch.empty((B, n, N, D), device=dev, dtype=torch.bfloat16)
+        # memory update: the inputs of all L layers live in one (L, rows, D) stack (batched norm_y / K|V append)
+        stack = None if render else torch.empty((L, rows, D), device=dev, dtype=torch.bfloat16)
+        hx = torch.empty((B, n, N, D), device=dev, dtype=torch.bfloat16) if render else stack[0].view(B, n, N, D)
         we = w16(self.feat_embed_enc_to_dec.weight)
         first_untagged = mem is None and not render
         if first_untagged:
@@ -264,7 +284,7 @@ class MUSt3R(nn.Module):
                         kvs.append(kvf[b:b + 1] if old is None else torch.cat([old[b], kvf[b:b + 1]], dim=1))
                 nxt = self._cross_attention(nxt, blk, B, n, N, kvs, mask_bits)
                 cur = mlp_residual(nxt, blk.norm3, blk.mlp, 1e-6,
-                                   out=feats_out if (l == L - 1 and feats_out is not None) else None)
+                                   out=stack[l + 1] if l < L - 1 else (feats_out if feats_out is not None else None))
                 if keep_all:
                     feats.append(cur.view(B, n, N, D) if cur.is_contiguous() else cur.unflatten(0, (B, n, N)))
             # feedback + memory write: stored_l = norm_y_l(layer_in_l + feedback(x_L)); K|V projected once, here
@@ -281,12 +301,18 @@ class MUSt3R(nn.Module):
                             ops.gemm(bank.tok[l][b, :n_mem], blk.kv_weight(), bias=blk.kv_bias(), out=bank.kv[l][b, :n_mem])
                     bank.n = n_mem
             bank.reserve(n_mem + n * N)
-            for l, blk in enumerate(self.blocks_dec):
-                for b in range(B):
-                    dst = bank.tok[l][b, n_mem:n_mem + n * N]
-                    sl = slice(b * n * N, (b + 1) * n * N)
-                    ops.layernorm(layer_in[l][sl], f32(blk.norm_y.weight), f32(blk.norm_y.bias), 1e-6, add=fb[sl], out=dst)
-                    ops.gemm(dst, blk.kv_weight(), bias=blk.kv_bias(), out=bank.kv[l][b, n_mem:n_mem + n * N])
+            if B == 1:  # all L layers in two launches
+                dst = bank.tok_all[:, 0, n_mem:n_mem + n * N]
+                ops.layernorm_batched(stack, self._stacked("ny_g"), self._stacked("ny_b"), 1e-6, add=fb, out=dst)
+                ops.gemm_batched(dst, self._stacked("kv_w"), bias=self._stacked("kv_b"),
+                                 out=bank.kv_all[:, 0, n_mem:n_mem + n * N])
+            else:
+                for l, blk in enumerate(self.blocks_dec):
+                    for b in range(B):
+                        dst = bank.tok[l][b, n_mem:n_mem + n * N]
+                        sl = slice(b * n * N, (b + 1) * n * N)
+                        ops.layernorm(layer_in[l][sl], f32(blk.norm_y.weight), f32(blk.norm_y.bias), 1e-6, add=fb[sl], out=dst)
+                        ops.gemm(dst, blk.kv_weight(), bias=blk.kv_bias(), out=bank.kv[l][b, n_mem:n_mem + n * N])
             bank.n = n_mem + n * N
             vals = MemVals([bank.tok[l][:, :bank.n] for l in range(L)])
             vals.bank = bank

@@ -120,6 +120,88 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     return out
 
 
+def gemm_batched(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+                 out: torch.Tensor) -> torch.Tensor:
+    """out[b] = act(a[b] @ w[b].T + bias[b]) for b < L in ONE launch.  a: bf16 [L, M, K], w: bf16 [L, N, K],
+    bias: fp32 [L, N], out: bf16/fp32 [L, M, N]; any batch / row strides, contiguous last dim."""
+    global launches
+    lib = _l.load()
+    _need(a, torch.bfloat16, "gemm_batched.a")
+    _need(w, torch.bfloat16, "gemm_batched.w")
+    if a.dim() != 3 or w.dim() != 3 or out.dim() != 3 or a.stride(-1) != 1 or w.stride(-1) != 1 or out.stride(-1) != 1:
+        raise _l.Pst3rError("gemm_batched: expected 3-D operands with contiguous last dim")
+    L, M, K = a.shape
+    L2, N, K2 = w.shape
+    if L2 != L or K2 != K or tuple(out.shape) != (L, M, N):
+        raise _l.Pst3rError(f"gemm_batched: shape mismatch a{tuple(a.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
+    if out.dtype not in (torch.float32, torch.bfloat16) or not out.is_cuda:
+        raise _l.Pst3rError("gemm_batched: out must be CUDA bf16 or fp32")
+    e = _l.GemmEpilogue()
+    e.out, e.ldo, e.out_f32, e.act, e.alpha, e.store_mode = out.data_ptr(), out.stride(1), int(out.dtype == torch.float32), act, 1.0, STORE_PLAIN
+    bias_bs = 0
+    if bias is not None:
+        _need(bias, torch.float32, "gemm_batched.bias")
+        if tuple(bias.shape) != (L, N) or bias.stride(1) != 1:
+            raise _l.Pst3rError("gemm_batched: bias must be [L, N]")
+        e.bias, bias_bs = bias.data_ptr(), bias.stride(0)
+    _l.check(lib.pst3r_gemm_bf16_batched(a.data_ptr(), a.stride(1), a.stride(0), w.data_ptr(), w.stride(1), w.stride(0), M, N, K,
+                                         L, C.byref(e), out.stride(0), bias_bs, _stream()), "pst3r_gemm_bf16_batched")
+    launches += 1
+    return out
+
+
+def layernorm_batched(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
+                      add: Optional[torch.Tensor] = None, out: torch.Tensor) -> torch.Tensor:
+    """out[b] = LN(x[b] + add) * gamma[b] + beta[b] in ONE launch.  x, out: bf16 [L, rows, D] (any batch / row strides);
+    gamma, beta: fp32 [L, D]; add: bf16 [rows, D] shared by all b."""
+    global launches
+    lib = _l.load()
+    _need(x, torch.bfloat16, "layernorm_batched.x")
+    _need(out, torch.bfloat16, "layernorm_batched.out")
+    _need(gamma, torch.float32, "layernorm_batched.gamma")
+    _need(beta, torch.float32, "layernorm_batched.beta")
+    if x.dim() != 3 or tuple(out.shape) != tuple(x.shape) or x.stride(-1) != 1 or out.stride(-1) != 1:
+        raise _l.Pst3rError("layernorm_batched: expected [L, rows, D] in/out with contiguous last dim")
+    L, rows, D = x.shape
+    if tuple(gamma.shape) != (L, D) or tuple(beta.shape) != (L, D) or gamma.stride() != beta.stride() or gamma.stride(1) != 1:
+        raise _l.Pst3rError("layernorm_batched: gamma/beta must be [L, D] with equal strides")
+    ld_add = 0
+    if add is not None:
+        _need(add, torch.bfloat16, "layernorm_batched.add")
+        r2, c2, ld_add = _rows2d(add, "layernorm_batched.add")
+        if (r2, c2) != (rows, D):
+            raise _l.Pst3rError("layernorm_batched: add must be [rows, D]")
+    _l.check(lib.pst3r_layernorm_batched(x.data_ptr(), x.stride(1), x.stride(0), _ptr(add), ld_add, gamma.data_ptr(),
+                                         beta.data_ptr(), gamma.stride(0), eps, out.data_ptr(), out.stride(1), out.stride(0),
+                                         rows, L, D, _stream()), "pst3r_layernorm_batched")
+    launches += 1
+    return out
+
+
+def set_sm_budget(n: int) -> int:
+    """Limit the SMs subsequent launches may fill (0 = all); returns the previous budget."""
+    return _l.load().pst3r_set_sm_budget(int(n))
+
+
+def num_sms() -> int:
+    return _l.load().pst3r_num_sms()
+
+
+class sm_budget:
+    """with ops.sm_budget(n): launches inside size their persistent grids / wave heuristics for n SMs."""
+
+    def __init__(self, n: int):
+        self.n = n
+
+    def __enter__(self):
+        self.prev = set_sm_budget(self.n)
+        return self
+
+    def __exit__(self, *exc):
+        set_sm_budget(0 if self.prev >= num_sms() else self.prev)
+        return False
+
+
 _ws_cache = {}
 
 
@@ -499,6 +581,8 @@ def _attn_kind(a, k):
 
 
 gemm = _wrap(gemm, _gemm_kind)
+gemm_batched = _wrap(gemm_batched, lambda a, k: "gemm_batched")
+layernorm_batched = _wrap(layernorm_batched, lambda a, k: "layernorm_batched")
 attention = _wrap(attention, _attn_kind)
 for _n in ("layernorm", "rope2d_", "add_bcast", "to_bf16", "to_f32", "patchify", "dino_preprocess_patchify", "center_pool8",
            "attn_mask_bits", "l2norm_rows", "nhwc_to_nchw_f32", "conv3x3_nhwc", "loftup_guidance", "loftup_fourier_gn",

@@ -8,9 +8,10 @@
 
 Orchestration follows engine/must3r.py:28-69 (sequential memory build, mem_batches [2,1,1,...]) and :71-94
 (render of every view against the final memory).  B200-first choices: the three feature producers write straight
-into one (V, N, 2816) bf16 buffer (the torch.cat at panoptic_decoder.py:44-47 disappears), DINOv2 runs on a side
-stream concurrently with the MUSt3R encoder/decoder, `max_bs` chunking is unnecessary (everything is one batch,
-results are chunk-invariant for v1) and accepted only for signature parity.
+into one (V, N, 2816) bf16 buffer (the torch.cat at panoptic_decoder.py:44-47 disappears); DINOv2 (throughput-bound,
+needed only by the head) runs on a side stream NEXT TO the sequential memory build (latency-bound chain of small
+kernels that cannot fill the GPU), each on its own share of the SMs (`dino_sms`, pst3r_set_sm_budget); `max_bs`
+chunking is unnecessary (everything is one batch, results are chunk-invariant for v1) and accepted only for signature parity.
 Multi-GPU: see panst3r_b200/dist.py (views sharded across ranks, one all-gather of encoder tokens).
 """
 from __future__ import annotations
@@ -46,6 +47,9 @@ class PanSt3R(nn.Module):
         self.postprocess_default = postprocess_default
         self.qubo_enabled = qubo_enabled
         self.overlap_dino = True
+        # SMs given to DINOv2 while it runs next to the memory build (the build gets the rest); 0 = no partition.
+        # Measured (profiles/r01_stage_times.md): partitioning costs more than it hides on one GPU, plain fork wins.
+        self.dino_sms = 0
         self._side_stream: Optional[torch.cuda.Stream] = None
 
     # ---- reference helper methods ----------------------------------------------------------------
@@ -96,27 +100,38 @@ class PanSt3R(nn.Module):
         cat = torch.empty((B, V, N, ENC_DIM + DEC_DIM + DINO_DIM), device=imgs.device, dtype=torch.bfloat16)
         rows = cat.view(B * V * N, -1)
         cur = torch.cuda.current_stream()
+        x, pos = self.forward_must3r_encoder(imgs, true_shape, out=rows[:, :ENC_DIM])
         if self.overlap_dino:  # also legal under CUDA-graph capture: the side stream forks from / joins the capturing one
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream()
             side = self._side_stream
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
+            side.wait_stream(cur)  # fork after the encoder: DINOv2 shares the GPU with the memory build that follows
+            with torch.cuda.stream(side), ops.sm_budget(self.dino_sms):
                 self.forward_dino(imgs, true_shape, out=rows[:, ENC_DIM + DEC_DIM:])
-            x, pos = self.forward_must3r_encoder(imgs, true_shape, out=rows[:, :ENC_DIM])
             join = side
         else:
             self.forward_dino(imgs, true_shape, out=rows[:, ENC_DIM + DEC_DIM:])
-            x, pos = self.forward_must3r_encoder(imgs, true_shape, out=rows[:, :ENC_DIM])
             join = None
         return cat, rows, x, pos, join
+
+    def _build_memory_shared(self, x, pos, true_shape, join):
+        """Memory build on the SMs DINOv2 leaves free; joins the side stream before returning so that the
+        full-width render pass that follows has the GPU to itself."""
+        if join is None or not self.dino_sms:
+            return self.build_memory(x, pos, true_shape)
+        with ops.sm_budget(max(ops.num_sms() - self.dino_sms, 8)):
+            mem = self.build_memory(x, pos, true_shape)
+        torch.cuda.current_stream().wait_stream(join)
+        return mem
 
     @torch.no_grad()
     def forward(self, imgs, true_shape, classes, max_bs=None, outdevice=None):
         """imgs fp32 (1, V, 3, H, W) in [-1, 1] on CUDA; true_shape (1, V, 2) (H, W); returns (panout, pointmaps)."""
         ts = true_shape.cpu() if true_shape.is_cuda else true_shape
         cat, rows, x, pos, join = self._features(imgs, ts)
-        _, pointmaps, _ = self.forward_must3r_decoder(x, pos, ts, feats_out=rows[:, ENC_DIM:ENC_DIM + DEC_DIM])
+        mem = self._build_memory_shared(x, pos, ts, join)
+        _, pointmaps, _ = self.must3r_decoder(x, pos, ts, mem, render=True, return_feats="last",
+                                              feats_out=rows[:, ENC_DIM:ENC_DIM + DEC_DIM])
         if join is not None:
             torch.cuda.current_stream().wait_stream(join)
         panout = self.panoptic_decoder(None, imgs, pos, ts, classes, outdevice=outdevice, cat_feats=cat)
@@ -146,7 +161,7 @@ class PanSt3R(nn.Module):
         k = num_keyframes
         cat, rows, x, pos, join = self._features(im, ts_all)
         Ntok = x.shape[2]
-        mem = self.build_memory(x[:, :k], pos[:, :k], ts_all[:, :k])
+        mem = self._build_memory_shared(x[:, :k], pos[:, :k], ts_all[:, :k], join)
         # render keyframes and the rest in one batch against the final memory (identical per-view results)
         _, pointmaps, _ = self.must3r_decoder(x, pos, ts_all, mem, render=True, return_feats="last",
                                               feats_out=rows[:, ENC_DIM:ENC_DIM + DEC_DIM])

@@ -61,6 +61,56 @@ def test_gemm_epilogues(ops):
     assert outbuf[:, :N].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("L,M,N,K", [(12, 768, 1536, 768), (3, 200, 72, 96), (5, 130, 264, 64), (1, 64, 64, 64)])
+def test_gemm_batched(ops, L, M, N, K):
+    """One launch for L equally shaped problems (the per-layer K|V projections of a memory update); operands are
+    strided views of larger buffers, rows beyond M of one problem must never leak into the next."""
+    abuf, obuf = rnd(L, M + 7, K + 8), torch.zeros(L, M + 3, N + 8, device="cuda", dtype=torch.bfloat16)
+    a, out = abuf[:, 2:2 + M, 8:], obuf[:, 1:1 + M, :N]
+    w, bias = rnd(L, N, K, scale=K ** -0.5), torch.randn(L, N, device="cuda")
+    ops.gemm_batched(a, w, bias=bias, out=out)
+    ref = torch.einsum("lmk,lnk->lmn", a.float(), w.float()) + bias[:, None]
+    assert relmax(out, ref) < TOL_BF16
+    assert obuf[:, 0].abs().max().item() == 0 and obuf[:, 1 + M:].abs().max().item() == 0 and obuf[:, :, N:].abs().max().item() == 0
+    o32 = torch.empty(L, M, N, device="cuda")
+    ops.gemm_batched(a, w, bias=bias, act=ops.ACT_GELU, out=o32)
+    assert relmax(o32, torch.nn.functional.gelu(ref)) < TOL_F32
+    # identical to L single launches (same kernel, same tiles): bit-exact
+    for l in range(L):
+        assert torch.equal(ops.gemm(a[l], w[l], bias=bias[l]), out[l])
+
+
+def test_layernorm_batched(ops):
+    L, rows, D = 12, 300, 768
+    xbuf, ybuf = rnd(L, rows + 5, D), torch.zeros(L, 2, rows + 4, D, device="cuda", dtype=torch.bfloat16)
+    x, y = xbuf[:, 3:3 + rows], ybuf[:, 1, 4:]
+    g, b, add = torch.randn(L, D, device="cuda"), torch.randn(L, D, device="cuda"), rnd(rows, D)
+    ops.layernorm_batched(x, g, b, 1e-6, add=add, out=y)
+    ref = torch.stack([torch.nn.functional.layer_norm(x[l].float() + add.float(), (D,), g[l], b[l], 1e-6) for l in range(L)])
+    assert relmax(y, ref) < TOL_BF16
+    assert ybuf[:, 0].abs().max().item() == 0 and ybuf[:, 1, :4].abs().max().item() == 0
+    for l in range(L):  # same arithmetic as the single-matrix entry point
+        assert torch.equal(ops.layernorm(x[l], g[l], b[l], 1e-6, add=add), y[l])
+    y2 = torch.empty(L, rows, D, device="cuda", dtype=torch.bfloat16)
+    ops.layernorm_batched(x, g, b, 1e-6, out=y2)
+    assert relmax(y2, torch.stack([torch.nn.functional.layer_norm(x[l].float(), (D,), g[l], b[l], 1e-6) for l in range(L)])) < TOL_BF16
+
+
+def test_sm_budget_keeps_results(ops):
+    """A reduced SM budget only changes grid sizes / split heuristics, never results."""
+    a, w = rnd(3000, 1024), rnd(2048, 1024, scale=1 / 32)
+    q, k, v = rnd(1, 768, 12, 64), rnd(1, 4096, 12, 64), rnd(1, 4096, 12, 64)
+    full = ops.gemm(a, w)
+    assert ops.set_sm_budget(0) == ops.num_sms()
+    with ops.sm_budget(40):
+        assert torch.equal(ops.gemm(a, w), full)
+        att = ops.attention(q, k, v)
+    assert ops.set_sm_budget(0) == ops.num_sms()
+    ref = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2).float(), k.transpose(1, 2).float(),
+                                                           v.transpose(1, 2).float()).transpose(1, 2).reshape(1, 768, 768)
+    assert relmax(att, ref) < TOL_ATTN
+
+
 def test_gemm_row_remap_store(ops):
     b, N, T, D, K = 3, 10, 11, 64, 64
     a, w = rnd(b * N, K), rnd(D, K)
