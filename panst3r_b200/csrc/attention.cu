@@ -19,6 +19,7 @@
 #include "../../include/panst3r_b200.h"
 
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace pst3r {
 
@@ -378,6 +379,7 @@ __global__ void attention_combine_kernel(const float* __restrict__ ws_o, const f
 
 }  // namespace pst3r
 #include "attention2.cuh"
+#include "attention3.cuh"
 namespace pst3r {
 
 static int make_qkv_map(CUtensorMap* m, const void* ptr, int hd, long long n, int H, int B, long long sn,
@@ -415,10 +417,19 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
   dim3 grid((a->Nq + ATT_BM - 1) / ATT_BM, a->B * a->H, splits);
   if (HD == 64 && !a->mask_bits) {
     // second-generation kernel: 256 queries per CTA
-    static bool cfg2 = false;
-    if (!cfg2) { PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_DYN_BYTES)); cfg2 = true; }
+    // third-generation kernel (P in tensor memory) unless PST3R_ATT=2 selects the smem-P one
+    static int gen = 0;
+    if (gen == 0) {
+      const char* e = getenv("PST3R_ATT");
+      gen = (e && e[0] == '2') ? 2 : 3;
+      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_DYN_BYTES));
+      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_DYN_BYTES));
+    }
     dim3 grid2((a->Nq + 255) / 256, a->B * a->H, splits);
-    PST3R_CHECK_CUDA(launch_pdl(attention2_fwd_kernel, grid2, dim3(AT2_THREADS), AT2_DYN_BYTES, stream, tmQ, tmK, tmV, p));
+    if (gen == 3)
+      PST3R_CHECK_CUDA(launch_pdl(attention3_fwd_kernel, grid2, dim3(AT3_THREADS), AT3_DYN_BYTES, stream, tmQ, tmK, tmV, p));
+    else
+      PST3R_CHECK_CUDA(launch_pdl(attention2_fwd_kernel, grid2, dim3(AT2_THREADS), AT2_DYN_BYTES, stream, tmQ, tmK, tmV, p));
   } else if (a->mask_bits) {
     auto kern = attention_fwd_kernel<HD, true>;
     static bool cfg = false;
