@@ -196,6 +196,25 @@ int pst3r_l2norm_rows(const float* x, int64_t ldx, void* y, int32_t y_f32, int64
 /* bf16 pixel-major [B, HW, C] -> fp32 channel-major [B, C, HW] (reference NCHW layout of mask_feats / fpn) */
 int pst3r_nhwc_to_nchw_f32(const void* x, int32_t B, int32_t HW, int32_t C, float* y, pst3r_stream_t stream);
 
+/* ---- Panoptic post-processing front half (engine/postprocess.py:18-27, 38-45, 63-120) ------------------
+ * scores[q] = max_k sigmoid(logits[q][k]), labels[q] = first arg max (postprocess.py:39). */
+int pst3r_class_scores(const float* logits, int64_t ldl, int32_t Q, int32_t K, float* scores, int32_t* labels,
+                       pst3r_stream_t stream);
+/* Fused sigmoid -> bilinear resize (align_corners=False, postprocess.py:24-25) -> score-weighted argmax over the
+ * kept queries (:63, :77) for V equally shaped views.  masks fp32 [V][Q][hm][wm] (strides in elements); keep_idx /
+ * keep_scores [nkeep]: surviving query indices (ascending) and their class scores.  Per output pixel:
+ * ids = position in keep_idx of the winning query (first on ties), win = that query's mask probability.
+ * area_half[k] += #pixels with probability >= 0.5 (:84), area_won[k] += #pixels query k wins with probability >=
+ * mask_threshold (:85-86); the caller zeroes both before the first view group of a round. */
+int pst3r_panoptic_argmax(const float* masks, int64_t view_stride, int64_t query_stride, int32_t V, int32_t hm, int32_t wm,
+                          const int32_t* keep_idx, const float* keep_scores, int32_t nkeep, int32_t H, int32_t W,
+                          float mask_threshold, int32_t* ids, float* win, int64_t out_view_stride, int32_t out_row_stride,
+                          int32_t* area_half, int32_t* area_won, pst3r_stream_t stream);
+/* pan[i] = lut[ids[i]] if win[i] >= mask_threshold else 0; conf[i] = win[i] where pan[i] != 0 else void_confidence
+ * (:103-105); lut[k] = segment id of kept query k or 0 if it was filtered out. */
+int pst3r_panoptic_finalize(const int32_t* ids, const float* win, const int32_t* lut, int32_t nkeep, float mask_threshold,
+                            float void_confidence, int32_t* pan, float* conf, int64_t n, pst3r_stream_t stream);
+
 /* ---- LoftUp guidance path (model/upscalers/loftup.py:9-79,122-130,152-157) ------------------------ */
 int64_t pst3r_loftup_workspace_bytes(int32_t V, int32_t C, int32_t groups);
 /* img fp32 [V,3,H,W] -> half fp32 [V,3,H/2,W/2] (bilinear x0.5) and minmax fp32 [3][2] = per-channel (min, max)

@@ -87,5 +87,33 @@ def main():
     print("wrote argmax_v1_V2_32x48.pt")
 
 
+def make_postprocess_golden(ref=None):
+    """Golden outputs of the REFERENCE's panoptic_inference_v2 / _v1 (engine/postprocess.py) on the deterministic
+    synthetic scenes of oracle/postprocess.py::synthetic_scene (inputs are regenerated from the seed at test time)."""
+    import numpy as np
+    from . import postprocess as op
+    ref = ref or ref_import.load_reference()
+    cases = []
+    for (V, Q, K, h, w, seed, sizes) in [(3, 12, 7, 24, 32, 0, None), (2, 40, 10, 16, 24, 1, None), (4, 200, 100, 24, 32, 2, None),
+                                         (3, 12, 7, 24, 32, 5, [(48, 64), (40, 56), (48, 64)])]:
+        cls, logits = op.synthetic_scene(V, Q, K, h, w, seed)
+        masks = [logits[0, i][None].clone() for i in range(V)]
+        if sizes is not None:  # mixed aspect ratios: crop the low-resolution masks to half the image size
+            masks = [m[..., :H // 2, :W // 2].contiguous() for m, (H, W) in zip(masks, sizes)]
+        ts = np.array(sizes if sizes is not None else [[2 * h, 2 * w]] * V)
+        out = {}
+        for name, fn in (("v2", ref.postprocess.panoptic_inference_v2), ("v1", ref.postprocess.panoptic_inference_v1)):
+            r = fn(cls.clone(), [m.clone() for m in masks], ts, label_mode="sigmoid", device="cpu", multi_ar=True)[0]
+            out[name] = {"pan": [p.to(torch.int16) for p in r["pan"]], "conf": r["conf"], "segments_info": r["segments_info"]}
+        cases.append({"scene": (V, Q, K, h, w, seed), "sizes": ts.tolist(), "out": out})
+    torch.save(cases, os.path.join(GOLDEN, "postprocess_synthetic.pt"))
+    print("wrote postprocess_synthetic.pt", [(c["scene"], len(c["out"]["v2"]["segments_info"])) for c in cases])
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "postprocess":
+        make_postprocess_golden()
+    else:
+        main()
+        make_postprocess_golden()

@@ -22,7 +22,7 @@ ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
                 "-I", INCLUDE, "-I", CSRC]
 
-SOURCES = ["host_util.cu", "gemm.cu", "attention.cu", "elementwise.cu", "loftup.cu"]
+SOURCES = ["host_util.cu", "gemm.cu", "attention.cu", "elementwise.cu", "loftup.cu", "postprocess.cu"]
 
 
 def _headers_mtime() -> float:

@@ -1,0 +1,221 @@
+// Panoptic post-processing front half on the GPU (reference src/panst3r/engine/postprocess.py:18-27, 38-45, 63-120):
+//   class scores            scores / labels = max over classes of sigmoid(class logits)                  (:39)
+//   fused argmax            sigmoid(mask logits) -> bilinear resize (align_corners=False) -> score-weighted
+//                           argmax over the kept queries, per pixel, plus the two per-query pixel counts the
+//                           reference's filtering loop needs (>= 0.5 area; >= mask_threshold area that wins)   (:24-25, :63, :77-85)
+//   finalize                segment ids / confidences from the winner map and a per-query lookup table     (:103-105)
+// The reference materialises the (V, Q, H, W) fp32 probability tensor (629 MB at 16 views of 512x384, several
+// copies of it) and walks the queries from Python with .item() calls; here every mask-logit plane is read once
+// per round (HBM-bound: V*Qkept*h*w*4 bytes) and only (V, H, W) maps + 2*Qkept counters leave the kernel.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/panst3r_b200.h"
+
+namespace pst3r {
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// one warp per query row; ties keep the first class (torch.max semantics on the sigmoid values)
+__global__ void class_scores_kernel(const float* __restrict__ logits, long long ldl, int Q, int K,
+                                    float* __restrict__ scores, int* __restrict__ labels) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const int lane = threadIdx.x & 31;
+  float best = -1.0f;
+  int bi = 0x7fffffff;
+  for (int k = lane; k < K; k += 32) {
+    const float s = sigmoid_f(logits[(long long)q * ldl + k]);
+    if (s > best) { best = s; bi = k; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) { scores[q] = best; labels[q] = bi; }
+}
+
+// PyTorch's source index for align_corners=False (area_pixel_compute_source_index + guard_index_and_lambda)
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float s = scale * ((float)dst + 0.5f) - 0.5f;
+  s = s < 0.0f ? 0.0f : s;
+  i0 = min((int)s, in_size - 1);
+  i1 = min(i0 + 1, in_size - 1);
+  l1 = fminf(fmaxf(s - (float)i0, 0.0f), 1.0f);
+}
+
+constexpr int PA_TW = 32, PA_TH = 32;   // output tile
+constexpr int PA_ROWS = 4;              // output rows per thread (256 threads: 8 x 32)
+constexpr int PA_SMAX = 36;             // max source-tile extent per axis (scale <= 1, i.e. the mask is never finer than the image)
+
+struct PanArgmaxParams {
+  const float* masks;            // [V][Q][hm][wm]
+  long long view_stride, query_stride;
+  int hm, wm, V;
+  const int* keep_idx;           // [nkeep] query indices, in reference (ascending) order
+  const float* keep_scores;      // [nkeep]
+  int nkeep;
+  int H, W;
+  float scale_h, scale_w;        // (float)hm / H, (float)wm / W
+  float mask_threshold;
+  int* ids;                      // [V][out_view_stride], row pitch out_row_stride; index into keep_idx
+  float* win;                    // winning query's mask probability
+  long long out_view_stride;
+  int out_row_stride;
+  int* area_half;                // [nkeep] += #pixels with probability >= 0.5
+  int* area_won;                 // [nkeep] += #pixels won with probability >= mask_threshold
+};
+
+__global__ void __launch_bounds__(256) panoptic_argmax_kernel(const PanArgmaxParams p) {
+  extern __shared__ int smem_i[];
+  int* h_half = smem_i;                       // [nkeep]
+  int* h_won = smem_i + p.nkeep;              // [nkeep]
+  float* tile = reinterpret_cast<float*>(smem_i + 2 * p.nkeep);  // [2][PA_SMAX * PA_SMAX]
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int v = blockIdx.z;
+  const int x = blockIdx.x * PA_TW + tx;
+  const int y_base = blockIdx.y * PA_TH;
+  for (int i = tid; i < 2 * p.nkeep; i += 256) smem_i[i] = 0;
+
+  // source window of this output tile
+  int sx0, sx1, sy0, sy1, d0, d1;
+  float dl;
+  src_index(blockIdx.x * PA_TW, p.scale_w, p.wm, sx0, d1, dl);
+  src_index(min(blockIdx.x * PA_TW + PA_TW - 1, p.W - 1), p.scale_w, p.wm, d0, sx1, dl);
+  src_index(y_base, p.scale_h, p.hm, sy0, d1, dl);
+  src_index(min(y_base + PA_TH - 1, p.H - 1), p.scale_h, p.hm, d0, sy1, dl);
+  const int sw = sx1 - sx0 + 1, sh = sy1 - sy0 + 1;
+
+  // this thread's pixels: column x, rows y_base + ty + 8 * i
+  int xi0, xi1;
+  float xl1;
+  src_index(min(x, p.W - 1), p.scale_w, p.wm, xi0, xi1, xl1);
+  xi0 -= sx0; xi1 -= sx0;
+  const float xl0 = 1.0f - xl1;
+  int yo0[PA_ROWS], yo1[PA_ROWS];
+  float yl1[PA_ROWS];
+  bool valid[PA_ROWS];
+#pragma unroll
+  for (int i = 0; i < PA_ROWS; ++i) {
+    const int y = y_base + ty + 8 * i;
+    valid[i] = (x < p.W) && (y < p.H);
+    int a, b;
+    src_index(min(y, p.H - 1), p.scale_h, p.hm, a, b, yl1[i]);
+    yo0[i] = (a - sy0) * sw;
+    yo1[i] = (b - sy0) * sw;
+  }
+  float best[PA_ROWS], bestv[PA_ROWS];
+  int bestk[PA_ROWS];
+#pragma unroll
+  for (int i = 0; i < PA_ROWS; ++i) { best[i] = -CUDART_INF_F; bestv[i] = 0.0f; bestk[i] = 0; }
+
+  const float* vbase = p.masks + (long long)v * p.view_stride + (long long)sy0 * p.wm + sx0;
+  auto load_tile = [&](int k, float* dst) {
+    const float* src = vbase + (long long)p.keep_idx[k] * p.query_stride;
+    for (int i = tid; i < sh * sw; i += 256) {
+      const int r = i / sw, c = i - r * sw;
+      dst[i] = sigmoid_f(__ldg(src + (long long)r * p.wm + c));
+    }
+  };
+  if (p.nkeep > 0) load_tile(0, tile);
+  __syncthreads();
+  for (int k = 0; k < p.nkeep; ++k) {
+    const float* cur = tile + (k & 1) * (PA_SMAX * PA_SMAX);
+    if (k + 1 < p.nkeep) load_tile(k + 1, tile + ((k + 1) & 1) * (PA_SMAX * PA_SMAX));
+    const float sc = __ldg(p.keep_scores + k);
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < PA_ROWS; ++i) {
+      const float t0 = xl0 * cur[yo0[i] + xi0] + xl1 * cur[yo0[i] + xi1];
+      const float t1 = xl0 * cur[yo1[i] + xi0] + xl1 * cur[yo1[i] + xi1];
+      const float val = (1.0f - yl1[i]) * t0 + yl1[i] * t1;
+      const float pr = sc * val;
+      if (pr > best[i]) { best[i] = pr; bestv[i] = val; bestk[i] = k; }  // strict: ties keep the first query
+      cnt += (valid[i] && val >= 0.5f) ? 1 : 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (tx == 0 && cnt) atomicAdd(&h_half[k], cnt);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < PA_ROWS; ++i) {
+    if (!valid[i]) continue;
+    const long long o = (long long)v * p.out_view_stride + (long long)(y_base + ty + 8 * i) * p.out_row_stride + x;
+    p.ids[o] = bestk[i];
+    p.win[o] = bestv[i];
+    if (p.nkeep > 0 && bestv[i] >= p.mask_threshold) atomicAdd(&h_won[bestk[i]], 1);
+  }
+  __syncthreads();
+  for (int i = tid; i < p.nkeep; i += 256) {
+    if (h_half[i]) atomicAdd(&p.area_half[i], h_half[i]);
+    if (h_won[i]) atomicAdd(&p.area_won[i], h_won[i]);
+  }
+}
+
+__global__ void panoptic_finalize_kernel(const int* __restrict__ ids, const float* __restrict__ win,
+                                         const int* __restrict__ lut, int nkeep, float thr, float void_conf,
+                                         int* __restrict__ pan, float* __restrict__ conf, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = ids[i];
+  const float w = win[i];
+  const int seg = (nkeep > 0 && k < nkeep && w >= thr) ? lut[k] : 0;
+  pan[i] = seg;
+  conf[i] = seg ? w : void_conf;
+}
+
+}  // namespace pst3r
+
+using namespace pst3r;
+
+extern "C" int pst3r_class_scores(const float* logits, int64_t ldl, int32_t Q, int32_t K, float* scores, int32_t* labels,
+                                  pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(logits && scores && labels && Q > 0 && K > 0 && ldl >= K, "class_scores: bad args");
+  class_scores_kernel<<<(Q + 7) / 8, 256, 0, s>>>(logits, ldl, Q, K, scores, labels);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_panoptic_argmax(const float* masks, int64_t view_stride, int64_t query_stride, int32_t V, int32_t hm,
+                                     int32_t wm, const int32_t* keep_idx, const float* keep_scores, int32_t nkeep,
+                                     int32_t H, int32_t W, float mask_threshold, int32_t* ids, float* win,
+                                     int64_t out_view_stride, int32_t out_row_stride, int32_t* area_half,
+                                     int32_t* area_won, pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(masks && ids && win && V > 0 && hm > 0 && wm > 0 && H > 0 && W > 0 && nkeep >= 0,
+                  "panoptic_argmax: bad args");
+  PST3R_CHECK_ARG(nkeep == 0 || (keep_idx && keep_scores && area_half && area_won), "panoptic_argmax: null keep list / counters");
+  PST3R_CHECK_ARG(hm <= H && wm <= W, "panoptic_argmax: the mask grid (%d x %d) must not be finer than the image (%d x %d)",
+                  hm, wm, H, W);
+  PST3R_CHECK_ARG(out_row_stride >= W && out_view_stride >= (int64_t)out_row_stride * H, "panoptic_argmax: bad output strides");
+  PST3R_CHECK_ARG(nkeep <= 4096, "panoptic_argmax: at most 4096 kept queries");
+  PanArgmaxParams p;
+  p.masks = masks; p.view_stride = view_stride; p.query_stride = query_stride;
+  p.hm = hm; p.wm = wm; p.V = V;
+  p.keep_idx = keep_idx; p.keep_scores = keep_scores; p.nkeep = nkeep;
+  p.H = H; p.W = W;
+  p.scale_h = (float)hm / (float)H; p.scale_w = (float)wm / (float)W;
+  p.mask_threshold = mask_threshold;
+  p.ids = ids; p.win = win; p.out_view_stride = out_view_stride; p.out_row_stride = out_row_stride;
+  p.area_half = area_half; p.area_won = area_won;
+  const size_t smem = (size_t)2 * nkeep * sizeof(int) + 2 * PA_SMAX * PA_SMAX * sizeof(float);
+  dim3 grid((W + PA_TW - 1) / PA_TW, (H + PA_TH - 1) / PA_TH, V);
+  panoptic_argmax_kernel<<<grid, 256, smem, s>>>(p);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_panoptic_finalize(const int32_t* ids, const float* win, const int32_t* lut, int32_t nkeep,
+                                       float mask_threshold, float void_confidence, int32_t* pan, float* conf, int64_t n,
+                                       pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(ids && win && pan && conf && n > 0 && (nkeep == 0 || lut), "panoptic_finalize: bad args");
+  panoptic_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, win, lut, nkeep, mask_threshold, void_confidence,
+                                                                      pan, conf, n);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}

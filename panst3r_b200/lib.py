@@ -87,6 +87,10 @@ SIGNATURES = {
     "pst3r_attn_mask_bits": (C.c_int, [_p, _i64, _i32, _i32, _p, _p]),
     "pst3r_l2norm_rows": (C.c_int, [_p, _i64, _p, _i32, _i64, _i32, _i32, _f, _p]),
     "pst3r_nhwc_to_nchw_f32": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
+    "pst3r_class_scores": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p]),
+    "pst3r_panoptic_argmax": (C.c_int, [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _i32, _i32, _i32, _f, _p, _p, _i64, _i32,
+                                        _p, _p, _p]),
+    "pst3r_panoptic_finalize": (C.c_int, [_p, _p, _p, _i32, _f, _f, _p, _p, _i64, _p]),
 }
 
 _lib = None

@@ -435,6 +435,66 @@ def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def class_scores(logits: torch.Tensor):
+    """fp32 [Q, K] class logits -> (scores fp32 [Q], labels int32 [Q]) = max / argmax of sigmoid(logits)."""
+    global launches
+    lib = _l.load()
+    _need(logits, torch.float32, "class_scores.logits")
+    Q, K, ld = _rows2d(logits, "class_scores.logits")
+    scores = torch.empty(Q, device=logits.device, dtype=torch.float32)
+    labels = torch.empty(Q, device=logits.device, dtype=torch.int32)
+    _l.check(lib.pst3r_class_scores(logits.data_ptr(), ld, Q, K, scores.data_ptr(), labels.data_ptr(), _stream()), "pst3r_class_scores")
+    launches += 1
+    return scores, labels
+
+
+def panoptic_argmax(masks: torch.Tensor, keep_idx: torch.Tensor, keep_scores: torch.Tensor, size: Tuple[int, int],
+                    mask_threshold: float, area_half: torch.Tensor, area_won: torch.Tensor):
+    """masks fp32 [V, Q, hm, wm] mask logits -> (ids int32 [V, H, W], win fp32 [V, H, W]); accumulates the per-query
+    pixel counts into area_half / area_won (int32 [nkeep], zeroed by the caller)."""
+    global launches
+    lib = _l.load()
+    _need(masks, torch.float32, "panoptic_argmax.masks")
+    if masks.dim() != 4 or masks.stride(-1) != 1 or masks.stride(-2) != masks.shape[-1]:
+        raise _l.Pst3rError("panoptic_argmax.masks: expected [V, Q, hm, wm] with dense planes")
+    V, Q, hm, wm = masks.shape
+    H, W = int(size[0]), int(size[1])
+    nkeep = keep_idx.numel()
+    if nkeep:
+        _need(keep_idx, torch.int32, "panoptic_argmax.keep_idx")
+        _need(keep_scores, torch.float32, "panoptic_argmax.keep_scores")
+        _need(area_half, torch.int32, "panoptic_argmax.area_half")
+        _need(area_won, torch.int32, "panoptic_argmax.area_won")
+    ids = torch.empty((V, H, W), device=masks.device, dtype=torch.int32)
+    win = torch.empty((V, H, W), device=masks.device, dtype=torch.float32)
+    _l.check(lib.pst3r_panoptic_argmax(masks.data_ptr(), masks.stride(0), masks.stride(1), V, hm, wm, _ptr(keep_idx) if nkeep else None,
+                                       _ptr(keep_scores) if nkeep else None, nkeep, H, W, float(mask_threshold), ids.data_ptr(),
+                                       win.data_ptr(), H * W, W, _ptr(area_half) if nkeep else None,
+                                       _ptr(area_won) if nkeep else None, _stream()), "pst3r_panoptic_argmax")
+    launches += 1
+    return ids, win
+
+
+def panoptic_finalize(ids: torch.Tensor, win: torch.Tensor, lut: Optional[torch.Tensor], mask_threshold: float,
+                      void_confidence: float):
+    """(ids, win) winner maps + lut int32 [nkeep] (segment id or 0) -> (pan int32, conf fp32) of the same shape."""
+    global launches
+    lib = _l.load()
+    _need(ids, torch.int32, "panoptic_finalize.ids")
+    _need(win, torch.float32, "panoptic_finalize.win")
+    if not (ids.is_contiguous() and win.is_contiguous()):
+        raise _l.Pst3rError("panoptic_finalize: expected contiguous maps")
+    nkeep = 0 if lut is None else lut.numel()
+    if nkeep:
+        _need(lut, torch.int32, "panoptic_finalize.lut")
+    pan, conf = torch.empty_like(ids), torch.empty_like(win)
+    _l.check(lib.pst3r_panoptic_finalize(ids.data_ptr(), win.data_ptr(), _ptr(lut) if nkeep else None, nkeep, float(mask_threshold),
+                                         float(void_confidence), pan.data_ptr(), conf.data_ptr(), ids.numel(), _stream()),
+             "pst3r_panoptic_finalize")
+    launches += 1
+    return pan, conf
+
+
 def conv3x3_nhwc(x: torch.Tensor, w: torch.Tensor, cpad: int, *, bias: Optional[torch.Tensor] = None,
                  act: int = ACT_NONE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """3x3 / stride 1 / zero-pad 1 convolution of a pixel-major bf16 map x [V, H, W, ld>=C] with tap-major weights
