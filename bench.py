@@ -184,9 +184,21 @@ def run_ours(args):
         runner = model
     host_imgs, ts = make_inputs(V, dev, pinned=True)
     dev_imgs = host_imgs.to(dev)
+    keyframes = args.keyframes if 0 < args.keyframes < V else 0
+    if keyframes and world > 1:
+        raise SystemExit("--keyframes (BASELINE config 3) is a single-GPU workload")
 
     def step_device():
+        if keyframes:  # BASELINE config 3: K keyframes build the memory, the other frames are render-only
+            pms, pan = model.forward_inference_multi_ar(list(dev_imgs[0]), ts[0], CLASSES, num_keyframes=keyframes)
+            return pan, pms
         return runner(dev_imgs, ts, CLASSES)
+
+    def flat(o):  # the tensors a caller reads back: class logits, per-view mask logits, pointmaps
+        pan, pm = o
+        masks = pan["pred_masks"]
+        return [pan["pred_logits"]] + (list(masks) if isinstance(masks, (list, tuple)) else [masks]) + \
+            (list(pm) if isinstance(pm, (list, tuple)) else [pm])
 
     def barrier():
         if world > 1:
@@ -243,11 +255,11 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    value = V * args.steps / (ms_total / 1e3)
+    units = keyframes or V  # the metric counts keyframe views
+    value = units * args.steps / (ms_total / 1e3)
 
     # ---- e2e: host buffers in, host buffers out, through the public forward() ----
-    panout, pointmaps = out
-    res_dev = [panout["pred_logits"], panout["pred_masks"], pointmaps]
+    res_dev = flat(out)
     res_host = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res_dev]
     h2d = host_imgs.numel() * host_imgs.element_size()
     d2h = sum(r.numel() * r.element_size() for r in res_dev)
@@ -274,7 +286,7 @@ def run_ours(args):
             dev_imgs.copy_(in_stage[b_], non_blocking=True)
             o = run_step()
             main.wait_event(ev_out[b_])             # staging buffer b_ must have been drained (step i-2)
-            for st, r in zip(out_stage[b_], [o[0]["pred_logits"], o[0]["pred_masks"], o[1]]):
+            for st, r in zip(out_stage[b_], flat(o)):
                 st.copy_(r, non_blocking=True)
             ev_staged[b_].record(main)
             with torch.cuda.stream(s_out):          # device -> host of this step's results
@@ -295,18 +307,39 @@ def run_ours(args):
     t = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = V * args.steps / (float(t.item()) / 1e3)
+    e2e_value = units * args.steps / (float(t.item()) / 1e3)
 
     # ---- per-kernel-kind profile of one eager step + roofline of the dominant kernel ----
     roofline, breakdown = None, None
     with ops.profiler() as prof:  # every rank runs the step (it contains collectives); rank 0 reports
         step_device()
     barrier()
+    att_roof = None
     if rank == 0:
         peaks, peak_src = _peaks()
         breakdown = prof.summary()
         roofline = dominant_roofline(ops, torch, V, peaks, peak_src, breakdown)
+        att_roof = attention_roofline(ops, torch, V, peaks, peak_src)
     barrier()
+
+    # ---- N > 1 only: the same GPUs running one independent scene each (no collective), for comparison ----
+    scene_parallel = None
+    if world > 1 and args.scene_parallel:
+        try:
+            for _ in range(2):
+                model(dev_imgs, ts, CLASSES)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                model(dev_imgs, ts, CLASSES)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            scene_parallel = {"value": world * V * args.steps / (float(t.item()) / 1e3), "unit": UNIT, "scaling": "weak",
+                              "note": "one independent 16-keyframe scene per GPU, eager launches, no data-path collective"}
+        except Exception as e:  # noqa: BLE001
+            scene_parallel = {"error": repr(e)}
 
     if rank == 0:
         cpu_base = None
@@ -316,8 +349,12 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{V}-keyframe 512x384 batch, {args.variant} PixelShuffle head, bf16, PanSt3R.forward()",
-                       "views": V, "variant": args.variant, "classes": len(CLASSES), "parallelism": f"views sharded x{world}",
+            "config": {"workload": (f"{V}-keyframe 512x384 batch" if not keyframes else
+                                    f"{keyframes} keyframes + {V - keyframes} render-only frames at 512x384 (memory-query path)") +
+                                   f", {'v1 PixelShuffle' if args.variant == 'v1' else 'v2 InputMixer + LoftUp'} head, bf16, " +
+                                   ("PanSt3R.forward()" if not keyframes else "PanSt3R.forward_inference_multi_ar()"),
+                       "views": V, "keyframes": keyframes or V, "variant": args.variant, "classes": len(CLASSES),
+                       "parallelism": f"views sharded x{world}",
                        "cuda_graph": graph is not None,
                        "l2": "per-step working set (1.7 GB bf16 weights + >2 GB activations) exceeds the 126 MB L2; no flush needed"},
             "clocks": clocks,
@@ -325,6 +362,9 @@ def run_ours(args):
                     "wall_ms_per_step": 1e3 * wall / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,
+            "attention_roofline": att_roof,
+            "total_views_per_s": V * args.steps / (ms_total / 1e3),
+            "scene_parallel": scene_parallel,
             "kernel_breakdown_ms": breakdown,
             "cpu_baseline": cpu_base,
         }
@@ -366,9 +406,39 @@ def dominant_roofline(ops, torch, V, peaks, peak_src, breakdown):
     ms = e0.elapsed_time(e1) / reps
     ach = flops / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops", 1590.0))
+    # DRAM bytes per launch of this kernel at this shape from the committed `ncu --set full` capture
+    # (profiles/r01_ncu_full_key_kernels_v2.md): dram__bytes_read.sum + dram__bytes_write.sum
+    traffic = {"gemm": 34.19e6 + 48.33e6, "attention": 57.09e6 + 7.11e6}.get("attention" if dom.startswith("attention") else "gemm")
+    if V != 16:
+        traffic = None
     return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "traffic": None, "peak_source": peak_src + ", burst figure (kernel timed alone)", "kernel_ms": ms,
+            "traffic": traffic, "peak_source": peak_src + ", burst figure (kernel timed alone)", "kernel_ms": ms,
             "share_of_step": breakdown[dom]["share"] if breakdown and dom in breakdown else None}
+
+
+def attention_roofline(ops, torch, V, peaks, peak_src):
+    """The north star's 'achieved fraction of the attention-GEMM roofline': QK^T + PV FLOPs of the render
+    cross-attention (the largest attention call of the step) / its CUDA-event time / the bf16 tensor peak."""
+    B, Hh, Nq, Nk, hd = V, 12, 768, V * 768, 64
+    q = torch.randn(B, Nq, Hh, hd, device="cuda").bfloat16()
+    k = torch.randn(1, Nk, Hh, hd, device="cuda").bfloat16()
+    v = torch.randn(1, Nk, Hh, hd, device="cuda").bfloat16()
+    for _ in range(3):
+        ops.attention(q, k, v)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.attention(q, k, v)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    ach = 4.0 * B * Hh * Nq * Nk * hd / (ms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    return {"kernel": f"attention3_fwd_kernel B{B} H{Hh} Nq{Nq} Nk{Nk} hd{hd} (render cross-attention over keyframe memory)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "kernel_ms": ms,
+            "bound": "MUFU ex2 (16/clk/SM) at head_dim 64: ceiling ~1150 TFLOP/s; ncu: XU pipe 59 %, tensor pipe 29 %",
+            "peak_source": peak_src}
 
 
 def cpu_baseline_leg(args):
@@ -404,6 +474,9 @@ def main():
     ap.add_argument("--views", type=int, default=16)
     ap.add_argument("--variant", default="v1", choices=["v1", "v2"])
     ap.add_argument("--ref-views", type=int, default=2)
+    ap.add_argument("--keyframes", type=int, default=0,
+                    help="BASELINE config 3: this many keyframes, the remaining --views frames are render-only (e.g. --views 64 --keyframes 8)")
+    ap.add_argument("--no-scene-parallel", dest="scene_parallel", action="store_false")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

@@ -85,6 +85,17 @@ typedef struct pst3r_gemm_epilogue {
   const int32_t* rope_pos; /* [M][2] (y, x) */
   int32_t rope_cols;
   int32_t rope_maxpos;
+  /* LayerNorm folded into the GEMM (nn.LayerNorm directly ahead of an nn.Linear: norm1/norm2/norm3 of every croco /
+   * MUSt3R / DINOv2 block).  A holds the RAW rows x [M, K]; B holds gamma-scaled weights bf16(gamma[k] * W[n][k]);
+   * bias holds bias + W beta.  The epilogue computes rstd[m] * (acc - mean[m] * ln_colsum[n]) + bias[n], with
+   * mean / rstd of row m from ln_stats[m][0 .. K/32) = per-32-column (sum x, sum x^2) partial sums (float2) written
+   * by the GEMM that produced x (its stats_out).  ln_colsum[n] = sum_k B[n][k] (fp32). */
+  const void* ln_stats;    /* float2 [M][K/32] or NULL */
+  int32_t ln_slots;        /* K / 32 */
+  const float* ln_colsum;  /* [N] */
+  float ln_eps;
+  /* Producer side: float2 [M][N/32] partial sums of the bf16 values this GEMM stores (PLAIN bf16 store, N % 32 == 0). */
+  void* stats_out;
 } pst3r_gemm_epilogue;
 
 int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,

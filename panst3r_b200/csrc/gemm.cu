@@ -45,7 +45,32 @@ struct GemmEpi {
   // out + b * out_bs with bias + b * bias_bs (PLAIN store only)
   int batches;
   long long out_bs, bias_bs;
+  // LayerNorm folded into this GEMM: A holds the RAW rows x, B the gamma-scaled weights, and the epilogue applies
+  //   y = rstd * (acc - mu * ln_colsum[col]) (+ bias', which already contains beta W^T)
+  // with (mu, rstd) of each row from the per-32-column partial sums (sum x, sum x^2) its producer left behind.
+  const float2* ln_stats;
+  int ln_slots;
+  const float* ln_colsum;
+  float ln_inv_dim, ln_eps;
+  // producer side: partial (sum, sum of squares) of every stored bf16 32-column chunk, stats_out[row][col / 32]
+  float2* stats_out;
+  int stats_slots;
 };
+
+// (mean, rstd) of row `row` from the partial sums of its producer (fixed summation order: deterministic)
+__device__ __forceinline__ float2 ln_row_stats(const GemmEpi& ep, int row, int M) {
+  if (!ep.ln_stats || row >= M) return make_float2(0.0f, 1.0f);
+  const float4* s = reinterpret_cast<const float4*>(ep.ln_stats + (long long)row * ep.ln_slots);
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int i = 0; i < (ep.ln_slots >> 1); ++i) {
+    const float4 t = __ldg(s + i);
+    s1 += t.x + t.z;
+    s2 += t.y + t.w;
+  }
+  const float mu = s1 * ep.ln_inv_dim;
+  const float var = fmaxf(s2 * ep.ln_inv_dim - mu * mu, 0.0f);
+  return make_float2(mu, rsqrtf(var + ep.ln_eps));
+}
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -63,7 +88,7 @@ struct GemmSmem {
 
 // ---- epilogue for one 32-column chunk owned by one thread (one output row) --------------------
 __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32], int row, int col0, int M, int N,
-                                               int bidx = 0) {
+                                               int bidx = 0, float2 ln = make_float2(0.0f, 1.0f)) {
   if (row >= M || col0 >= N) return;
   const int ncols = min(32, N - col0);
   const bool full = (ncols == 32);
@@ -71,6 +96,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
   if (ep.alpha != 1.0f) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= ep.alpha;
+  }
+  if (ep.ln_colsum) {  // folded LayerNorm (host guarantees N % 32 == 0)
+    const float4* u4 = reinterpret_cast<const float4*>(ep.ln_colsum + col0);
+    const float nm = -ln.x;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 u = __ldg(u4 + i);
+      v[4 * i + 0] = ln.y * fmaf(nm, u.x, v[4 * i + 0]);
+      v[4 * i + 1] = ln.y * fmaf(nm, u.y, v[4 * i + 1]);
+      v[4 * i + 2] = ln.y * fmaf(nm, u.z, v[4 * i + 2]);
+      v[4 * i + 3] = ln.y * fmaf(nm, u.w, v[4 * i + 3]);
+    }
   }
   if (ep.bias) {
     const float* bias = ep.bias + bidx * ep.bias_bs;
@@ -157,6 +194,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
       } else {
         bf16* o = reinterpret_cast<bf16*>(ep.out) + roff + col0;
         if (full && ((ep.ldo & 7) == 0) && ((ep.batch_stride & 7) == 0)) {
+          float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 u;
@@ -165,7 +203,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
             u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
             u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
             reinterpret_cast<uint4*>(o)[i] = u;
+            if (ep.stats_out) {  // statistics of the values as stored (bf16-rounded): what the consumer's A operand holds
+              float2 f;
+              f = unpack_bf16x2(u.x); s1 += f.x + f.y; s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+              f = unpack_bf16x2(u.y); s1 += f.x + f.y; s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+              f = unpack_bf16x2(u.z); s1 += f.x + f.y; s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+              f = unpack_bf16x2(u.w); s1 += f.x + f.y; s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+            }
           }
+          if (ep.stats_out) ep.stats_out[(long long)row * ep.stats_slots + (col0 >> 5)] = make_float2(s1, s2);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -370,15 +416,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n_blk = trem / num_m_blocks;
       const int acc = local & 1;
       const uint32_t acc_ph = (local >> 1) & 1;
-      mbar_wait(&tfull_bar[acc], acc_ph);
-      tc_fence_after();
       int row = m_blk * GEMM_BM + quad * 32 + lane;
       int m_lim = M;
+      const float2 ln = ln_row_stats(ep, row, M);  // before the accumulator wait: overlaps the main loop
       if (ep.conv_cblocks > 0) {
         const int xcol = (m_blk % ep.conv_tpr) * GEMM_BM + quad * 32 + lane;
         row = (m_blk / ep.conv_tpr) * ep.conv_w + xcol;
         m_lim = xcol < ep.conv_w ? 0x7fffffff : 0;  // segment tail beyond the image row: nothing to store
       }
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       const int n_rem = N - n_blk * BN;
 #pragma unroll 1
@@ -390,7 +437,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_chunk(ep, v, row, n_blk * BN + c * 32, m_lim, N, bidx);
+        epilogue_chunk(ep, v, row, n_blk * BN + c * 32, m_lim, N, bidx, ln);
       }
       tc_fence_before();
       __syncwarp();
@@ -465,6 +512,17 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   ep.rope_cols = e->rope_cols; ep.rope_maxpos = e->rope_maxpos;
   ep.conv_cblocks = 0; ep.conv_w = ep.conv_h = ep.conv_tpr = 0;
   ep.batches = 1; ep.out_bs = 0; ep.bias_bs = 0;
+  ep.ln_stats = reinterpret_cast<const float2*>(e->ln_stats); ep.ln_slots = e->ln_slots; ep.ln_colsum = e->ln_colsum;
+  ep.ln_inv_dim = K > 0 ? 1.0f / (float)K : 0.0f; ep.ln_eps = e->ln_eps;
+  ep.stats_out = reinterpret_cast<float2*>(e->stats_out); ep.stats_slots = (N + 31) / 32;
+  if (e->ln_stats || e->ln_colsum)
+    PST3R_CHECK_ARG(e->ln_stats && e->ln_colsum && e->ln_slots == (K + 31) / 32 && (K % 64) == 0 && (N % 32) == 0 && !conv &&
+                        (reinterpret_cast<uintptr_t>(e->ln_stats) & 15) == 0 && (reinterpret_cast<uintptr_t>(e->ln_colsum) & 15) == 0,
+                    "gemm: folded LayerNorm needs stats [M][K/32] + colsum [N], K %% 64 == 0, N %% 32 == 0");
+  if (e->stats_out)
+    PST3R_CHECK_ARG(e->store_mode == PST3R_STORE_PLAIN && e->rows_per_batch == 0 && !e->out_f32 && (N % 32) == 0 &&
+                        (e->ldo % 8) == 0 && !conv && (reinterpret_cast<uintptr_t>(e->stats_out) & 7) == 0,
+                    "gemm: stats_out needs a plain bf16 store with N %% 32 == 0 and ldo %% 8 == 0");
   const int nb = bat ? bat->batches : 1;
   if (nb > 1) {
     ep.batches = nb; ep.out_bs = bat->out_bs; ep.bias_bs = bat->bias_bs;

@@ -178,9 +178,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int n_blk = tile / num_m_blocks;
       const int acc = local & 1;
       const uint32_t acc_ph = (local >> 1) & 1;
+      const int row = m_blk * 256 + (int)rank * 128 + quad * 32 + lane;
+      const float2 ln = ln_row_stats(ep, row, M);
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
-      const int row = m_blk * 256 + (int)rank * 128 + quad * 32 + lane;
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = cgrp; c < BN / 32; c += 2) {
@@ -190,7 +191,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_chunk(ep, v, row, n_blk * BN + c * 32, M, N);
+        epilogue_chunk(ep, v, row, n_blk * BN + c * 32, M, N, 0, ln);
       }
       tc_fence_before();
       __syncwarp();

@@ -39,6 +39,11 @@ class GemmEpilogue(C.Structure):
         ("rope_pos", C.c_void_p),
         ("rope_cols", C.c_int32),
         ("rope_maxpos", C.c_int32),
+        ("ln_stats", C.c_void_p),
+        ("ln_slots", C.c_int32),
+        ("ln_colsum", C.c_void_p),
+        ("ln_eps", C.c_float),
+        ("stats_out", C.c_void_p),
     ]
 
 

@@ -6,7 +6,7 @@ passes call only panst3r_b200.ops (the C ABI).  Weights are converted once to th
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Sequence, Tuple
+from typing import Callable, Dict, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
@@ -114,25 +114,79 @@ def bias_of(lin: nn.Linear):
     return None if lin.bias is None else f32(lin.bias)
 
 
-def self_attention(x: torch.Tensor, blk, B: int, N: int, rope, in_place: bool = True) -> torch.Tensor:
-    """x (+)= proj(attn(rope(qkv(norm1(x)))));  x bf16 [B*N, D].  rope = (table, pos_i32 [B*N, 2]) or None."""
+# Folding pays where the chain is latency bound (M = 768 rows per step of the sequential memory build: one ~4 us
+# LayerNorm launch less per Linear).  Measured on B200 (profiles/r01_stage_times.md): at M = 12288 the heavier
+# epilogues cost more (+0.6 ms per 24-block encoder) than the LayerNorm kernels they replace, so large problems keep
+# the stand-alone kernel.
+FOLD_LN_MAX_ROWS = 3072
+
+
+def fold_stats(rows: int, dim: int, device, count: int = 1):
+    """`count` statistics buffers for a residual stream of `rows` rows, or Nones when folding is not worthwhile."""
+    if rows > FOLD_LN_MAX_ROWS or dim % 64 != 0:
+        return (None,) * count if count > 1 else None
+    bufs = tuple(ops.new_stats(rows, dim, device) for _ in range(count))
+    return bufs if count > 1 else bufs[0]
+
+
+def folded_ln(norm: nn.LayerNorm, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]]):
+    """LayerNorm folded into the Linear(s) that consume it:  LN(x) W^T + b = rstd (x (gamma o W)^T - mu colsum) + (W beta + b).
+    Returns (bf16 gamma-scaled weights [N, K], fp32 colsum [N] of exactly those bf16 weights, fp32 bias' [N]);
+    several Linears (q | k | v) are concatenated along N.  Cached per parameter version."""
+    ps = [norm.weight, norm.bias] + list(weights) + [b for b in biases if b is not None]
+    for p in ps:
+        _check_cuda(p)
+
+    def build():
+        W = torch.cat([w.detach().reshape(w.shape[0], -1).float() for w in weights], 0)
+        b = torch.cat([(bb.detach().float() if bb is not None else torch.zeros(w.shape[0], device=W.device))
+                       for w, bb in zip(weights, biases)], 0)
+        wf = (W * norm.weight.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+        return wf, wf.float().sum(1).contiguous(), (W @ norm.bias.detach().float() + b).contiguous()
+
+    return prepared("folded_ln", ps, build)
+
+
+def ln_linear(x: torch.Tensor, stats: Optional[torch.Tensor], norm: nn.LayerNorm, weights, biases, eps: float,
+              plain_w=None, plain_b=None, **gemm_kw) -> torch.Tensor:
+    """Linear(LayerNorm(x)).  With `stats` (partial row sums left by the GEMM that produced x) the normalisation is
+    folded into the GEMM epilogue and never materialised; without, LayerNorm runs as its own kernel."""
+    if stats is None:
+        h = ops.layernorm(x, f32(norm.weight), f32(norm.bias), eps)
+        w = plain_w() if plain_w is not None else w16(weights[0])
+        b = plain_b() if plain_b is not None else (None if biases[0] is None else f32(biases[0]))
+        return ops.gemm(h, w, bias=b, **gemm_kw)
+    wf, colsum, bf = folded_ln(norm, weights, biases)
+    return ops.gemm(x, wf, bias=bf, ln=(stats, colsum, eps), **gemm_kw)
+
+
+def self_attention(x: torch.Tensor, blk, B: int, N: int, rope, in_place: bool = True,
+                   stats: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x (+)= proj(attn(rope(qkv(norm1(x)))));  x bf16 [B*N, D].  rope = (table, pos_i32 [B*N, 2]) or None.
+    stats: LayerNorm statistics of x (norm1 folds into the QKV GEMM); stats_out: receives those of the result."""
     D, H = blk.dim, blk.num_heads
-    h = ops.layernorm(x, f32(blk.norm1.weight), f32(blk.norm1.bias), blk.eps)
-    qkv = ops.gemm(h, w16(blk.attn.qkv.weight), bias=bias_of(blk.attn.qkv),
-                   rope=None if rope is None else (rope[0], rope[1], 2 * D))
+    qkv = ln_linear(x, stats, blk.norm1, [blk.attn.qkv.weight], [blk.attn.qkv.bias], blk.eps,
+                    rope=None if rope is None else (rope[0], rope[1], 2 * D))
     q5 = qkv.view(B, N, 3, H, D // H)
     o = ops.attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2])
     return ops.gemm(o.view(B * N, D), w16(blk.attn.proj.weight), bias=bias_of(blk.attn.proj), residual=x,
-                    out=x if in_place else None)
+                    out=x if in_place else None, stats_out=stats_out)
 
 
-def mlp_residual(x: torch.Tensor, norm: nn.LayerNorm, mlp, eps: float, out=None, act: int = ops.ACT_GELU) -> torch.Tensor:
+def mlp_residual(x: torch.Tensor, norm: nn.LayerNorm, mlp, eps: float, out=None, act: int = ops.ACT_GELU,
+                 stats: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = x + fc2(act(fc1(norm(x))))  (in place when out is None)"""
-    h = ops.layernorm(x, f32(norm.weight), f32(norm.bias), eps)
-    h = ops.gemm(h, w16(mlp.fc1.weight), bias=bias_of(mlp.fc1), act=act)
-    return ops.gemm(h, w16(mlp.fc2.weight), bias=bias_of(mlp.fc2), residual=x, out=x if out is None else out)
+    h = ln_linear(x, stats, norm, [mlp.fc1.weight], [mlp.fc1.bias], eps, act=act)
+    return ops.gemm(h, w16(mlp.fc2.weight), bias=bias_of(mlp.fc2), residual=x, out=x if out is None else out,
+                    stats_out=stats_out)
 
 
-def vit_block(x: torch.Tensor, blk: ViTBlockParams, B: int, N: int, rope) -> torch.Tensor:
-    x = self_attention(x, blk, B, N, rope)
-    return mlp_residual(x, blk.norm2, blk.mlp, blk.eps)
+def vit_block(x: torch.Tensor, blk: ViTBlockParams, B: int, N: int, rope, stats=None, stats_pair=None):
+    """One croco Block.  With `stats` (+ two scratch statistics buffers) both LayerNorms are folded into the GEMMs
+    that consume them; returns (x, stats of x)."""
+    if stats is None:
+        x = self_attention(x, blk, B, N, rope)
+        return mlp_residual(x, blk.norm2, blk.mlp, blk.eps), None
+    s1, s2 = stats_pair  # rotate: stats is one of them, always the one written last
+    x = self_attention(x, blk, B, N, rope, stats=stats, stats_out=s1)
+    return mlp_residual(x, blk.norm2, blk.mlp, blk.eps, stats=s1, stats_out=s2), s2

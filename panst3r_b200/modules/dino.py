@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .common import bias_of, cat_f32, cat_w16, f32, prepared, w16
+from .common import bias_of, cat_f32, cat_w16, f32, fold_stats, ln_linear, prepared, w16
 
 
 class _Holder(nn.Module):
@@ -115,17 +115,24 @@ class DinoV2Encoder(nn.Module):
         ops.gemm(a, self._patch_weight(), bias=f32(proj.bias), residual=patch_pos, res_mod_rows=N, out=x[:, 1:],
                  rows_per_batch=N, batch_stride=T * D, out_ld=D)
         xr = x.view(b * T, D)
+        # LayerNorms are folded into the GEMMs that consume them (common.ln_linear); the residual GEMMs leave the row
+        # statistics behind.  Only the first norm1 runs as a kernel: its input (CLS row + remapped patch rows) has no
+        # single producing GEMM.
+        s1, s2 = fold_stats(b * T, D, dev, 2)
+        st = None
         for lyr in self.dinov2.encoder.layer:
-            h = ops.layernorm(xr, f32(lyr.norm1.weight), f32(lyr.norm1.bias), self.eps)
-            qkv = ops.gemm(h, lyr.qkv_weight(), bias=lyr.qkv_bias()).view(b, T, 3, Hh, D // Hh)
+            a_ = lyr.attention.attention
+            qkv = ln_linear(xr, st, lyr.norm1, [a_.query.weight, a_.key.weight, a_.value.weight],
+                            [a_.query.bias, a_.key.bias, a_.value.bias], self.eps, plain_w=lyr.qkv_weight,
+                            plain_b=lyr.qkv_bias).view(b, T, 3, Hh, D // Hh)
             o = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2])
             dense = lyr.attention.output.dense
             ops.gemm(o.view(b * T, D), w16(dense.weight), bias=bias_of(dense), col_scale=f32(lyr.layer_scale1.lambda1),
-                     residual=xr, out=xr)
-            h = ops.layernorm(xr, f32(lyr.norm2.weight), f32(lyr.norm2.bias), self.eps)
-            h = ops.gemm(h, w16(lyr.mlp.fc1.weight), bias=bias_of(lyr.mlp.fc1), act=ops.ACT_GELU)
+                     residual=xr, out=xr, stats_out=s1)
+            h = ln_linear(xr, s1, lyr.norm2, [lyr.mlp.fc1.weight], [lyr.mlp.fc1.bias], self.eps, act=ops.ACT_GELU)
             ops.gemm(h, w16(lyr.mlp.fc2.weight), bias=bias_of(lyr.mlp.fc2), col_scale=f32(lyr.layer_scale2.lambda1),
-                     residual=xr, out=xr)
+                     residual=xr, out=xr, stats_out=s2)
+            st = s2
         if out is None:
             out = torch.empty((b * N, D), device=dev, dtype=torch.bfloat16)
         ln = self.dinov2.layernorm

@@ -20,8 +20,8 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .common import (ViTBlockParams, b16, bias_of, cat_f32, cat_w16, f32, mlp_residual, pos_grid, prepared, rope_table,
-                     self_attention, vit_block, w16)
+from .common import (ViTBlockParams, b16, bias_of, cat_f32, cat_w16, f32, fold_stats, ln_linear, mlp_residual, pos_grid,
+                     prepared, rope_table, self_attention, vit_block, w16)
 
 
 def _hw(true_shape) -> tuple:
@@ -60,9 +60,13 @@ class Dust3rEncoder(nn.Module):
         pos_rows = pos32.repeat(b, 1) if b > 1 else pos32
         rope = (rope_table(max(h, w), D // self.num_heads, self.rope_base, img.device), pos_rows)
         a = ops.patchify(img.float(), P)
-        x = ops.gemm(a, w16(self.patch_embed.proj.weight), bias=f32(self.patch_embed.proj.bias))
+        # every LayerNorm that feeds a Linear is folded into that GEMM: the GEMM producing the residual stream leaves
+        # per-row partial sums behind (stats), the consuming GEMM normalises in its epilogue
+        s1, s2 = fold_stats(b * N, D, img.device, 2)
+        x = ops.gemm(a, w16(self.patch_embed.proj.weight), bias=f32(self.patch_embed.proj.bias), stats_out=s2)
+        st = s2
         for blk in self.blocks_enc:
-            x = vit_block(x, blk, b, N, rope)
+            x, st = vit_block(x, blk, b, N, rope, stats=st, stats_pair=(s1, s2))
         if out is None:
             out = torch.empty((b * N, D), device=img.device, dtype=torch.bfloat16)
         ops.layernorm(x, f32(self.norm_enc.weight), f32(self.norm_enc.bias), 1e-6, out=out)
@@ -172,12 +176,12 @@ class MUSt3R(nn.Module):
         return prepared("head_b", [bs], lambda: bs.detach().view(C, P, P).permute(1, 2, 0).reshape(-1).float().contiguous())
 
     # ---- pieces -----------------------------------------------------------------------------------
-    def _cross_attention(self, x, blk: _DecBlock, B, n, N, kv_list, mask_bits):
-        """x += proj(attn(q = projq(norm2 x), K|V));  kv_list[b]: bf16 (1, Nk, 2D) shared by the n views of batch b."""
+    def _cross_attention(self, x, blk: _DecBlock, B, n, N, kv_list, mask_bits, stats=None, stats_out=None):
+        """x += proj(attn(q = projq(norm2 x), K|V));  kv_list[b]: bf16 (1, Nk, 2D) shared by the n views of batch b.
+        stats / stats_out: LayerNorm statistics of x (norm2 folds into the q projection) / of the result."""
         D, H = self.embed_dim, self.num_heads
         hd = D // H
-        hq = ops.layernorm(x, f32(blk.norm2.weight), f32(blk.norm2.bias), 1e-6)
-        q = ops.gemm(hq, w16(blk.cross_attn.projq.weight), bias=bias_of(blk.cross_attn.projq)).view(B, n, N, H, hd)
+        q = ln_linear(x, stats, blk.norm2, [blk.cross_attn.projq.weight], [blk.cross_attn.projq.bias], 1e-6).view(B, n, N, H, hd)
         o = torch.empty((B * n, N, D), device=x.device, dtype=torch.bfloat16)
         for b in range(B):
             kv = kv_list[b]
@@ -186,7 +190,7 @@ class MUSt3R(nn.Module):
             v = kv[:, :, D:].unflatten(-1, (H, hd))
             ops.attention(q[b], k, v, mask_bits=mask_bits, out=o[b * n:(b + 1) * n])
         return ops.gemm(o.view(B * n * N, D), w16(blk.cross_attn.proj.weight), bias=bias_of(blk.cross_attn.proj),
-                        residual=x, out=x)
+                        residual=x, out=x, stats_out=stats_out)
 
     @staticmethod
     def _own_view_mask(n: int, N: int, n_mem: int, device) -> torch.Tensor:
@@ -223,14 +227,18 @@ class MUSt3R(nn.Module):
         stack = None if render else torch.empty((L, rows, D), device=dev, dtype=torch.bfloat16)
         hx = torch.empty((B, n, N, D), device=dev, dtype=torch.bfloat16) if render else stack[0].view(B, n, N, D)
         we = w16(self.feat_embed_enc_to_dec.weight)
+        # LayerNorm statistics of the residual stream (three scratch buffers rotate through the block)
+        sa, sb, sc = fold_stats(rows, D, dev, 3)
+        sa4 = None if sa is None else sa.view(B, n, N, -1, 2)
         first_untagged = mem is None and not render
         if first_untagged:
             for b in range(B):
-                ops.gemm(xin[b, 0], we, bias=self._embed_bias(False), out=hx[b, 0])
+                ops.gemm(xin[b, 0], we, bias=self._embed_bias(False), out=hx[b, 0], stats_out=None if sa is None else sa4[b, 0])
                 if n > 1:
-                    ops.gemm(xin[b, 1:], we, bias=self._embed_bias(True), out=hx[b, 1:])
+                    ops.gemm(xin[b, 1:], we, bias=self._embed_bias(True), out=hx[b, 1:],
+                             stats_out=None if sa is None else sa4[b, 1:])
         else:
-            ops.gemm(xin, we, bias=self._embed_bias(True), out=hx)
+            ops.gemm(xin, we, bias=self._embed_bias(True), out=hx, stats_out=sa)
         cur = hx.view(rows, D)
 
         bank: Optional[MemoryBank] = None
@@ -258,10 +266,11 @@ class MUSt3R(nn.Module):
         if render:
             for l, blk in enumerate(self.blocks_dec):
                 in_place = not keep_all
-                cur = self_attention(cur, blk, B * n, N, rope, in_place=in_place)
-                cur = self._cross_attention(cur, blk, B, n, N, stored_kv(l), None)
+                cur = self_attention(cur, blk, B * n, N, rope, in_place=in_place, stats=sa, stats_out=sb)
+                cur = self._cross_attention(cur, blk, B, n, N, stored_kv(l), None, stats=sb, stats_out=sc)
                 last = l == L - 1
-                cur = mlp_residual(cur, blk.norm3, blk.mlp, 1e-6, out=feats_out if (last and feats_out is not None) else None)
+                cur = mlp_residual(cur, blk.norm3, blk.mlp, 1e-6, out=feats_out if (last and feats_out is not None) else None,
+                                   stats=sc, stats_out=sa)
                 if keep_all:
                     feats.append(cur.view(B, n, N, D) if cur.is_contiguous() else cur.unflatten(0, (B, n, N)))
             new_mem = mem
@@ -270,7 +279,7 @@ class MUSt3R(nn.Module):
             mask_bits = self._own_view_mask(n, N, n_mem, dev) if n > 1 else None
             for l, blk in enumerate(self.blocks_dec):
                 layer_in.append(cur)
-                nxt = self_attention(cur, blk, B * n, N, rope, in_place=False)
+                nxt = self_attention(cur, blk, B * n, N, rope, in_place=False, stats=sa, stats_out=sb)
                 if n == 1:
                     if n_mem == 0:
                         raise ops._l.Pst3rError("a single first view has nothing to attend to (init needs >= 2 views)")
@@ -282,9 +291,10 @@ class MUSt3R(nn.Module):
                     old = stored_kv(l) if n_mem > 0 else None
                     for b in range(B):
                         kvs.append(kvf[b:b + 1] if old is None else torch.cat([old[b], kvf[b:b + 1]], dim=1))
-                nxt = self._cross_attention(nxt, blk, B, n, N, kvs, mask_bits)
+                nxt = self._cross_attention(nxt, blk, B, n, N, kvs, mask_bits, stats=sb, stats_out=sc)
                 cur = mlp_residual(nxt, blk.norm3, blk.mlp, 1e-6,
-                                   out=stack[l + 1] if l < L - 1 else (feats_out if feats_out is not None else None))
+                                   out=stack[l + 1] if l < L - 1 else (feats_out if feats_out is not None else None),
+                                   stats=sc, stats_out=sa)
                 if keep_all:
                     feats.append(cur.view(B, n, N, D) if cur.is_contiguous() else cur.unflatten(0, (B, n, N)))
             # feedback + memory write: stored_l = norm_y_l(layer_in_l + feedback(x_L)); K|V projected once, here

@@ -383,7 +383,7 @@ class InputMixer(nn.Module):
         rope = (rope_table(max(hs, ws), self.hidden_dim // self.num_heads, 100.0, x.device), pos32.repeat(V, 1))
         h = ops.gemm(x, w16(self.in_proj.weight), bias=bias_of(self.in_proj))
         for blk in self.mixer_blk:
-            h = vit_block(h, blk, V, N, rope)
+            h, _ = vit_block(h, blk, V, N, rope)
         return ops.layernorm(h, f32(self.mixer_norm.weight), f32(self.mixer_norm.bias), 1e-5)
 
     def forward(self, x, pos):

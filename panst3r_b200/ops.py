@@ -61,9 +61,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          store_mode: int = STORE_PLAIN, rows_per_batch: int = 0, batch_stride: int = 0, ldt: int = 0,
          grid: Tuple[int, int] = (0, 0), d2s: Tuple[int, int] = (0, 0),
          rope: Optional[Tuple[torch.Tensor, torch.Tensor, int]] = None, res_mod_rows: int = 0,
-         out_ld: int = 0) -> torch.Tensor:
+         out_ld: int = 0, ln: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None,
+         stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epilogue(a @ w.T).  a: bf16 [..., K] (row-strided), w: bf16 [N, K].
-    PLAIN store with rows_per_batch > 0: `out` is only a base pointer, rows are remapped (pass out_ld)."""
+    PLAIN store with rows_per_batch > 0: `out` is only a base pointer, rows are remapped (pass out_ld).
+    ln = (stats fp32 [M, K/32, 2], colsum fp32 [N], eps): LayerNorm(a) folded into the GEMM (w = gamma-scaled weights,
+    bias includes W beta); stats_out fp32 [M, N/32, 2]: per-chunk (sum, sum^2) of the stored bf16 rows for the next fold."""
     global launches
     lib = _l.load()
     _need(a, torch.bfloat16, "gemm.a")
@@ -110,6 +113,18 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     e.rows_per_batch, e.batch_stride, e.ldt = rows_per_batch, batch_stride, ldt
     e.grid_h, e.grid_w = grid
     e.d2s_patch, e.d2s_ch = d2s
+    if ln is not None:
+        st, colsum, eps = ln
+        _need(st, torch.float32, "gemm.ln_stats")
+        _need(colsum, torch.float32, "gemm.ln_colsum")
+        if not st.is_contiguous() or st.numel() != M * ((K + 31) // 32) * 2 or colsum.numel() != N:
+            raise _l.Pst3rError(f"gemm: ln stats must be contiguous [M, K/32, 2] (got {tuple(st.shape)} for M={M} K={K})")
+        e.ln_stats, e.ln_slots, e.ln_colsum, e.ln_eps = st.data_ptr(), (K + 31) // 32, colsum.data_ptr(), eps
+    if stats_out is not None:
+        _need(stats_out, torch.float32, "gemm.stats_out")
+        if not stats_out.is_contiguous() or stats_out.numel() != M * ((N + 31) // 32) * 2:
+            raise _l.Pst3rError("gemm: stats_out must be contiguous [M, N/32, 2]")
+        e.stats_out = stats_out.data_ptr()
     if rope is not None:
         cs, pos, rope_cols = rope
         _need(cs, torch.float32, "gemm.rope_cs")
@@ -200,6 +215,11 @@ class sm_budget:
     def __exit__(self, *exc):
         set_sm_budget(0 if self.prev >= num_sms() else self.prev)
         return False
+
+
+def new_stats(rows: int, cols: int, device) -> torch.Tensor:
+    """Per-row partial LayerNorm statistics buffer for `gemm(..., stats_out=)`: fp32 [rows, cols/32, 2]."""
+    return torch.empty((rows, (cols + 31) // 32, 2), device=device, dtype=torch.float32)
 
 
 _ws_cache = {}

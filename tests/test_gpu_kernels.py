@@ -96,6 +96,32 @@ def test_layernorm_batched(ops):
     assert relmax(y2, torch.stack([torch.nn.functional.layer_norm(x[l].float(), (D,), g[l], b[l], 1e-6) for l in range(L)])) < TOL_BF16
 
 
+@pytest.mark.parametrize("M,K,N", [(768, 768, 2304), (1000, 1024, 4096), (12288, 1024, 1024), (130, 768, 768)])
+def test_gemm_folded_layernorm(ops, M, K, N):
+    """Linear(LayerNorm(x)) with the normalisation folded into the GEMM epilogue: the GEMM producing x leaves per-row
+    partial sums (stats_out), the consumer runs on the raw rows with gamma-scaled weights."""
+    a0, w0 = rnd(M, 256), rnd(K, 256, scale=1 / 16)
+    res = rnd(M, K, scale=3.0) + 1.5  # a residual stream with a non-zero row mean
+    stats = ops.new_stats(M, K, "cuda")
+    x = ops.gemm(a0, w0, residual=res, stats_out=stats)  # producer: stores bf16 x and its statistics
+    xf = x.float()
+    got = stats.sum(1)
+    assert torch.allclose(got[:, 0], xf.sum(1), rtol=1e-4, atol=1e-2) and torch.allclose(got[:, 1], (xf * xf).sum(1), rtol=1e-4)
+    gamma, beta = torch.randn(K, device="cuda") * 0.5 + 1, torch.randn(K, device="cuda") * 0.3
+    W, b = torch.randn(N, K, device="cuda") * K ** -0.5, torch.randn(N, device="cuda")
+    wf = (W * gamma[None]).bfloat16()
+    colsum, bfold = wf.float().sum(1), W @ beta + b
+    ref = torch.nn.functional.layer_norm(xf, (K,), gamma, beta, 1e-6) @ W.t() + b
+    y = ops.gemm(x, wf, bias=bfold, ln=(stats, colsum, 1e-6), out_dtype=torch.float32)
+    assert relmax(y, ref) < 4e-3  # bf16 weights; the explicit path additionally rounds LN(x) to bf16
+    explicit = ops.gemm(ops.layernorm(x, gamma, beta, 1e-6), W.bfloat16(), bias=b, out_dtype=torch.float32)
+    assert relmax(y, ref) <= relmax(explicit, ref) * 1.5 + 1e-4
+    yg = ops.gemm(x, wf, bias=bfold, ln=(stats, colsum, 1e-6), act=ops.ACT_GELU)
+    assert relmax(yg, torch.nn.functional.gelu(ref)) < TOL_BF16 + 4e-3
+    with pytest.raises(ops._l.Pst3rError):
+        ops.gemm(x, wf, bias=bfold, ln=(stats[:, :-1].contiguous(), colsum, 1e-6))
+
+
 def test_sm_budget_keeps_results(ops):
     """A reduced SM budget only changes grid sizes / split heuristics, never results."""
     a, w = rnd(3000, 1024), rnd(2048, 1024, scale=1 / 32)
