@@ -160,6 +160,10 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    wd = int(os.environ.get("PST3R_BENCH_WATCHDOG", "0"))
+    if wd > 0:  # debugging aid: dump every thread's stack and exit if the run has not finished after `wd` seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

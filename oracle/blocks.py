@@ -143,6 +143,11 @@ class PatchEmbedDust3R(nn.Module):
 
     def forward(self, x, true_shape=None):
         B, C, H, W = x.shape
+        # Batches are stored landscape (W >= H); a portrait view (true_shape H > W) is the transposed picture: it is
+        # embedded in its true orientation, as dust3r's ManyAR_PatchEmbed does (the convention the reference's own
+        # `dinov2_transpose` / `transpose_to_landscape` wrappers assume, model/dino.py:25-33, utils.py:36-49).
+        if true_shape is not None and int(true_shape.reshape(-1, 2)[0, 0]) > int(true_shape.reshape(-1, 2)[0, 1]):
+            x = x.transpose(2, 3)
         x = self.proj(x)
         h, w = x.shape[-2:]
         ys, xs = torch.meshgrid(torch.arange(h, device=x.device), torch.arange(w, device=x.device), indexing="ij")

@@ -144,6 +144,8 @@ class MUSt3R(nn.Module):
             feats.append(hv.view(B, n, N, -1))
 
         pointmaps = self.head_dec(self.norm_dec(hv), (H, W)).view(B, n, H, W, -1)
+        if H > W:  # portrait: predicted in the true orientation, returned in the landscape storage convention
+            pointmaps = pointmaps.transpose(2, 3)
 
         if not render:
             # feedback ('single_mlp'): one MLP of the last-layer tokens is added to what every layer stores

@@ -70,6 +70,8 @@ class ShardedPanSt3R:
         s, e = parts[self.rank]
         nv = e - s
         ts = true_shape.cpu() if true_shape.is_cuda else true_shape
+        if int(ts.reshape(-1, 2)[0, 0]) != H or int(ts.reshape(-1, 2)[0, 1]) != W:
+            raise ops._l.Pst3rError("the sharded runner handles landscape scenes (true_shape == tensor shape) only")
         P = m.must3r_encoder.patch_size
         hs, ws = H // P, W // P
         N = hs * ws

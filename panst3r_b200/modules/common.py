@@ -116,14 +116,15 @@ def bias_of(lin: nn.Linear):
 
 # Folding pays where the chain is latency bound (M = 768 rows per step of the sequential memory build: one ~4 us
 # LayerNorm launch less per Linear).  Measured on B200 (profiles/r01_stage_times.md): at M = 12288 the heavier
-# epilogues cost more (+0.6 ms per 24-block encoder) than the LayerNorm kernels they replace, so large problems keep
-# the stand-alone kernel.
+# epilogues cost more (+0.6 ms per 24-block encoder) than the LayerNorm kernels they replace, so the per-view stages
+# (encoder, DINOv2, render) keep the stand-alone kernel — for every batch size, so that a rank holding a shard of the
+# views computes bit-identical per-view results to a single GPU holding all of them (tests/test_gpu_dist.py).
 FOLD_LN_MAX_ROWS = 3072
 
 
-def fold_stats(rows: int, dim: int, device, count: int = 1):
-    """`count` statistics buffers for a residual stream of `rows` rows, or Nones when folding is not worthwhile."""
-    if rows > FOLD_LN_MAX_ROWS or dim % 64 != 0:
+def fold_stats(rows: int, dim: int, device, count: int = 1, enable: bool = True):
+    """`count` statistics buffers for a residual stream of `rows` rows, or Nones when folding is not used."""
+    if not enable or rows > FOLD_LN_MAX_ROWS or dim % 64 != 0:
         return (None,) * count if count > 1 else None
     bufs = tuple(ops.new_stats(rows, dim, device) for _ in range(count))
     return bufs if count > 1 else bufs[0]

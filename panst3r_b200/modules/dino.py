@@ -17,6 +17,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from .common import bias_of, cat_f32, cat_w16, f32, fold_stats, ln_linear, prepared, w16
+from .must3r import oriented
 
 
 class _Holder(nn.Module):
@@ -57,6 +58,7 @@ class DinoV2Encoder(nn.Module):
         super().__init__()
         self.output_stride, self.patch_size, self.embed_dim, self.num_heads = output_stride, patch_size, hidden_size, num_heads
         self.eps = eps
+        self.fold_ln = False  # per-view stage: stand-alone LayerNorm kernels (see common.FOLD_LN_MAX_ROWS)
         self.kpad = ((3 * patch_size * patch_size + 7) // 8) * 8  # 588 -> 592: TMA row pitch must be 16 B aligned
         npos = (image_size // patch_size) ** 2
         d = self.dinov2 = _Holder()
@@ -100,7 +102,8 @@ class DinoV2Encoder(nn.Module):
     def forward(self, image: torch.Tensor, true_shape, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """image fp32 (b,3,H,W) in [-1,1] -> bf16 (b, N, D) patch tokens (CLS dropped).  `out`: optional bf16
         destination rows (b*N, D) with any row stride."""
-        b, _, H, W = image.shape
+        image, H, W = oriented(image, true_shape)  # portrait views are stored transposed (model/dino.py:25-33)
+        b = image.shape[0]
         P, D, Hh = self.patch_size, self.embed_dim, self.num_heads
         gh, gw = H // self.output_stride, W // self.output_stride
         N = gh * gw
@@ -118,7 +121,7 @@ class DinoV2Encoder(nn.Module):
         # LayerNorms are folded into the GEMMs that consume them (common.ln_linear); the residual GEMMs leave the row
         # statistics behind.  Only the first norm1 runs as a kernel: its input (CLS row + remapped patch rows) has no
         # single producing GEMM.
-        s1, s2 = fold_stats(b * T, D, dev, 2)
+        s1, s2 = fold_stats(b * T, D, dev, 2, enable=self.fold_ln)
         st = None
         for lyr in self.dinov2.encoder.layer:
             a_ = lyr.attention.attention

@@ -25,15 +25,27 @@ from .common import (ViTBlockParams, b16, bias_of, cat_f32, cat_w16, f32, fold_s
 
 
 def _hw(true_shape) -> tuple:
+    """True (H, W) of the views of a call (all equal).  H > W: portrait views — by the reference's storage convention
+    (model/dino.py:25-33, utils.py:36-49) their image / dense-output tensors are kept transposed (landscape)."""
     ts = true_shape.reshape(-1, 2)
     if ts.is_cuda:
         ts = ts.cpu()
     H, W = int(ts[0, 0]), int(ts[0, 1])
     if not bool((ts == ts[0:1]).all()):
-        raise ops._l.Pst3rError("all views of a call must share one true_shape (single aspect-ratio batches)")
-    if W < H:
-        raise ops._l.Pst3rError("portrait batches are not implemented on the CUDA path yet (landscape only)")
+        raise ops._l.Pst3rError("all views of a call must share one true_shape (stack views by aspect ratio first)")
     return H, W
+
+
+def oriented(img: torch.Tensor, true_shape) -> tuple:
+    """Stored image batch (b, 3, Hs, Ws) -> (image batch in the true orientation, H, W).  Portrait views are stored
+    transposed; transposing back is pure data movement."""
+    H, W = _hw(true_shape)
+    Hs, Ws = img.shape[-2:]
+    if (Hs, Ws) == (H, W):
+        return img, H, W
+    if (Hs, Ws) == (W, H):
+        return img.transpose(-1, -2).contiguous(), H, W
+    raise ops._l.Pst3rError(f"image tensor {Hs}x{Ws} matches neither true_shape {H}x{W} nor its transpose")
 
 
 class Dust3rEncoder(nn.Module):
@@ -47,12 +59,14 @@ class Dust3rEncoder(nn.Module):
         self.patch_embed.proj = nn.Conv2d(3, embed_dim, kernel_size=patch_size, stride=patch_size)
         self.blocks_enc = nn.ModuleList([ViTBlockParams(embed_dim, num_heads, mlp_ratio, eps=1e-6) for _ in range(depth)])
         self.norm_enc = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.fold_ln = False  # per-view stage: stand-alone LayerNorm kernels (see common.FOLD_LN_MAX_ROWS)
 
     @torch.no_grad()
     def forward(self, img: torch.Tensor, true_shape, out: Optional[torch.Tensor] = None):
         """img fp32 (b,3,H,W) in [-1,1] -> (x bf16 (b,N,D), pos int64 (b,N,2)).  `out`: optional bf16 destination
         (b*N rows, D columns, any row stride) for the normalised tokens."""
-        b, _, H, W = img.shape
+        img, H, W = oriented(img, true_shape)
+        b = img.shape[0]
         P, D = self.patch_size, self.embed_dim
         h, w = H // P, W // P
         N = h * w
@@ -62,7 +76,7 @@ class Dust3rEncoder(nn.Module):
         a = ops.patchify(img.float(), P)
         # every LayerNorm that feeds a Linear is folded into that GEMM: the GEMM producing the residual stream leaves
         # per-row partial sums behind (stats), the consuming GEMM normalises in its epilogue
-        s1, s2 = fold_stats(b * N, D, img.device, 2)
+        s1, s2 = fold_stats(b * N, D, img.device, 2, enable=self.fold_ln)
         x = ops.gemm(a, w16(self.patch_embed.proj.weight), bias=f32(self.patch_embed.proj.bias), stats_out=s2)
         st = s2
         for blk in self.blocks_enc:
@@ -142,6 +156,7 @@ class MUSt3R(nn.Module):
         self.head_dec = nn.Module()
         self.head_dec.proj = nn.Linear(embed_dim, head_channels * patch_size * patch_size)
         self.reserve_views = 0  # capacity hint (views) for the memory bank, set by the caller
+        self.fold_ln_render = False  # LayerNorm folding is for the sequential memory build; render is a per-view stage
 
     # ---- prepared (fused / permuted) parameters -------------------------------------------------
     def _embed_bias(self, tagged: bool):
@@ -228,7 +243,7 @@ class MUSt3R(nn.Module):
         hx = torch.empty((B, n, N, D), device=dev, dtype=torch.bfloat16) if render else stack[0].view(B, n, N, D)
         we = w16(self.feat_embed_enc_to_dec.weight)
         # LayerNorm statistics of the residual stream (three scratch buffers rotate through the block)
-        sa, sb, sc = fold_stats(rows, D, dev, 3)
+        sa, sb, sc = fold_stats(rows, D, dev, 3, enable=(not render) or self.fold_ln_render)
         sa4 = None if sa is None else sa.view(B, n, N, -1, 2)
         first_untagged = mem is None and not render
         if first_untagged:
@@ -336,6 +351,8 @@ class MUSt3R(nn.Module):
             pointmaps = torch.empty((B, n, H, W, self.head_channels), device=dev, dtype=torch.float32)
             ops.gemm(hn, self._head_weight(), bias=self._head_bias(), out=pointmaps, store_mode=ops.STORE_D2S,
                      grid=(h_, w_), d2s=(self.patch_size, self.head_channels))
+            if H > W:  # portrait: predicted in the true orientation, returned in the landscape storage convention
+                pointmaps = pointmaps.transpose(2, 3)
         if return_feats == "last":
             feats = [cur.view(B, n, N, D) if cur.is_contiguous() else cur.unflatten(0, (B, n, N))]
         return new_mem, pointmaps, (feats if return_feats else None)

@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from .. import ops
 from .common import b16, bias_of, cat_f32, cat_w16, f32, prepared, w16
-from .must3r import _hw
+from .must3r import _hw, oriented
 
 
 class _Mlp(nn.Module):
@@ -196,7 +196,13 @@ class MaskTransformer(nn.Module):
         bv = prepared("mt_bv", bs, lambda: torch.cat([b.detach()[2 * d:] for b in bs], 0).float().contiguous())
         return wk, bk, wv, bv
 
-    def _pos(self, h, w, device):
+    def _pos(self, h, w, device, portrait: bool = False):
+        """Sine PE rows for the (h, w) token grid of one view.  Portrait views (stored transposed): the reference
+        embeds the transposed map and applies its rows, in THAT map's raster order, to the stored tokens as they are
+        (get_pe_with_transpose, mask_transformer.py:106-119) — restated literally."""
+        if portrait:
+            return prepared(f"mt_pe_{h}x{w}_p", [self.level_embed.weight],
+                            lambda: sine_pe(w, h, self.hidden_dim // 2).to(device=device, dtype=torch.bfloat16).contiguous())
         return prepared(f"mt_pe_{h}x{w}", [self.level_embed.weight],
                         lambda: sine_pe(h, w, self.hidden_dim // 2).to(device=device, dtype=torch.bfloat16).contiguous())
 
@@ -246,7 +252,7 @@ class MaskTransformer(nn.Module):
     @torch.no_grad()
     def forward_nhwc(self, src: torch.Tensor, mask_feats: torch.Tensor, hw, cls_emb: torch.Tensor,
                      deep_supervision: bool = True, pooled: Optional[torch.Tensor] = None,
-                     mask_override: Optional[List[torch.Tensor]] = None):
+                     mask_override: Optional[List[torch.Tensor]] = None, portrait: bool = False):
         """src bf16 (V*h*w, C) = stride-16 features + level_embed, views flattened view-major (batch 1);
         mask_feats bf16 (V', Hm, Wm, Cm) — the views whose full-resolution masks this call produces (all V, or this
         rank's shard); pooled bf16 (V*h*w, Cm): centre-pooled mask features of ALL views (computed from mask_feats
@@ -256,7 +262,7 @@ class MaskTransformer(nn.Module):
         hd = d // H
         Nk = src.shape[0]
         dev = src.device
-        pos = self._pos(h, w, dev)
+        pos = self._pos(h, w, dev, portrait)
         src_pos = ops.add_bcast(src, pos)  # key = memory + pos (pos of view 0 tiled over views, :139-141)
         wk, bk, wv, bv = self._kv_weights()
         k_all = ops.gemm(src_pos, wk, bias=bk).view(1, Nk, self.num_layers, H, hd)
@@ -334,7 +340,8 @@ class PanopticDecoder(nn.Module):
         B, V, N, Cc = cat_feats.shape
         if B != 1:
             raise ops._l.Pst3rError("CUDA PanopticDecoder supports batch size 1 (one scene per call)")
-        H, W = _hw(true_shape)
+        H, W = _hw(true_shape)  # true size; portrait (H > W) views are predicted in their true orientation and
+        portrait = H > W        # returned in the landscape storage convention (utils.transpose_to_landscape, dims=(2, 3))
         P = self.upscaler.patch_size
         hs, ws = H // P, W // P
         dev = cat_feats.device
@@ -342,12 +349,18 @@ class PanopticDecoder(nn.Module):
         if self.input_mixer is not None:
             x = self.input_mixer.forward_rows(x, V, hs, ws)
         mt = self.mask_transformer
-        src, mask_f = self.upscaler.forward_nhwc(x, V, hs, ws, f16_extra_bias=mt.level_embed.weight) \
-            if isinstance(self.upscaler, PixelShuffleUpscaler) else \
-            self.upscaler.forward_nhwc(x, in_imgs.reshape(V, 3, H, W), V, hs, ws, f16_extra_bias=mt.level_embed.weight)
+        if isinstance(self.upscaler, PixelShuffleUpscaler):
+            src, mask_f = self.upscaler.forward_nhwc(x, V, hs, ws, f16_extra_bias=mt.level_embed.weight)
+        else:
+            imgs_t, _, _ = oriented(in_imgs.reshape(V, 3, *in_imgs.shape[-2:]), true_shape)
+            src, mask_f = self.upscaler.forward_nhwc(x, imgs_t, V, hs, ws, f16_extra_bias=mt.level_embed.weight)
+        if portrait:  # swap the spatial dims of both outputs (pure data movement); the head then sees a (ws, hs) grid
+            src = src.view(V, hs, ws, -1).transpose(1, 2).contiguous().view(V * N, -1)
+            mask_f = mask_f.transpose(1, 2).contiguous()
+            hs, ws = ws, hs
         cls_emb = self.text_encoder(classes, device=dev)
         if memory_queries is None:
-            out = mt.forward_nhwc(src, mask_f, (hs, ws), cls_emb, deep_supervision=self.deep_supervision)
+            out = mt.forward_nhwc(src, mask_f, (hs, ws), cls_emb, deep_supervision=self.deep_supervision, portrait=portrait)
         else:
             q = memory_queries.reshape(mt.num_queries, mt.hidden_dim)
             q = q if q.dtype == torch.bfloat16 else ops.to_bf16(q.float().contiguous())

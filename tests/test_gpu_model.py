@@ -52,6 +52,14 @@ def test_encoder_dino_parity(pair):
     assert xm.dtype == torch.bfloat16 and torch.equal(posm.cpu(), poso)
     assert relmax(xm, xo) < TOL
     assert relmax(m.forward_dino(imgs.cuda(), ts), o.forward_dino(imgs, ts)) < TOL
+    # the same stages with every LayerNorm folded into the consuming GEMM (off by default for per-view stages)
+    m.must3r_encoder.fold_ln = m.dino_encoder.fold_ln = True
+    try:
+        xf, _ = m.forward_must3r_encoder(imgs.cuda(), ts)
+        assert relmax(xf, xo) < TOL and relmax(xf, xm) < TOL
+        assert relmax(m.forward_dino(imgs.cuda(), ts), o.forward_dino(imgs, ts)) < TOL
+    finally:
+        m.must3r_encoder.fold_ln = m.dino_encoder.fold_ln = False
 
 
 def test_decoder_memory_and_render_parity(pair):
@@ -74,6 +82,13 @@ def test_decoder_memory_and_render_parity(pair):
     plain = ([t.clone() for t in memm[0]], memm[1], memm[2], None, None)
     _, pm2, _ = m.must3r_decoder(xc[:, 1:2], pc[:, 1:2], ts[:, 1:2], plain, render=True, return_feats="last")
     assert relmax(pm2, pm1) < 1e-6
+    # render with folded LayerNorms (the memory build above already runs folded)
+    m.must3r_decoder.fold_ln_render = True
+    try:
+        _, pmf, ff = m.must3r_decoder(xc, pc, ts, memm, render=True, return_feats="last")
+        assert relmax(ff[-1], yo) < TOL and relmax(pmf, pmo) < TOL
+    finally:
+        m.must3r_decoder.fold_ln_render = False
 
 
 @pytest.mark.parametrize("path", golden_files("head_v1*.pt"))
@@ -81,17 +96,19 @@ def test_head_against_reference_golden(path):
     """CUDA PanopticDecoder vs outputs of the REFERENCE's own modules (tests/golden, oracle/make_golden.py)."""
     from panst3r_b200.modules.panoptic import PanopticDecoder, PixelShuffleUpscaler
     g = torch.load(path)
-    if g["portrait"]:
-        pytest.skip("portrait batches are not implemented on the CUDA path yet")
     m = PanopticDecoder(upscaler=PixelShuffleUpscaler(input_dim=2816)).eval()
     o = build_oracle_head("v1")
     m.load_state_dict(o.state_dict(), strict=True)
     m = m.cuda()
     m.text_encoder.class_embeddings = o.text_encoder.class_embeddings
-    feats, imgs, pos, ts = head_inputs(g["V"], g["H"], g["W"], g["input_seed"])
+    feats, imgs, pos, ts = head_inputs(g["V"], g["H"], g["W"], g["input_seed"], portrait=g["portrait"])
     out = m(tuple(f.cuda() for f in feats), imgs.cuda(), pos.cuda(), ts, CLASSES)
     V, H, Wd = g["V"], g["H"], g["W"]
-    f16, f2 = m.upscaler((torch.cat(feats, -1)[0].cuda(), None), (H, Wd))
+    if g["portrait"]:  # predicted in the true (48 x 32) orientation, stored transposed (utils.transpose_to_landscape)
+        f16, f2 = m.upscaler((torch.cat(feats, -1)[0].cuda(), None), (Wd, H))
+        f16, f2 = [f16[0].swapaxes(2, 3)], f2.swapaxes(2, 3)
+    else:
+        f16, f2 = m.upscaler((torch.cat(feats, -1)[0].cuda(), None), (H, Wd))
     assert relmax(f16[0], g["fpn0"]) < TOL and relmax(f2, g["mask_feats"]) < TOL
     assert out["pred_masks"].shape == g["pred_masks"].shape and out["pred_masks"].dtype == torch.float32
     assert relmax(out["aux_outputs"][0]["pred_masks"], g["aux0_masks"]) < TOL
@@ -223,6 +240,24 @@ def test_forward_and_multi_ar_vs_oracle(pair):
     # outdevice: results land on the host like the reference's demo (tools/demo_panst3r.py:232-233)
     pan_c, pm_c = m(imgs.cuda(), ts, classes, outdevice="cpu")
     assert pm_c.device.type == "cpu" and pan_c["pred_masks"].device.type == "cpu" and torch.equal(pm_c, pm.cpu())
+
+
+def test_forward_portrait_vs_oracle(pair):
+    """All-portrait scene: tensors stored landscape (64 x 96), true_shape (96, 64) — the reference's convention
+    (model/dino.py:25-33, utils.py:36-49).  Every stage runs in the true orientation; dense outputs come back in the
+    landscape storage layout."""
+    o, m, imgs, ts, classes = pair
+    tsp = ts.flip(-1)
+    pan_o, pm_o = o(imgs, tsp, classes)
+    pan, pm = m(imgs.cuda(), tsp, classes)
+    assert pm.shape == pm_o.shape == (1, imgs.shape[1], 64, 96, 7) and relmax(pm, pm_o) < TOL
+    assert pan["pred_masks"].shape == pan_o["pred_masks"].shape
+    assert relmax(pan["aux_outputs"][0]["pred_masks"], pan_o["aux_outputs"][0]["pred_masks"]) < TOL
+    assert relmax(pan["aux_outputs"][0]["pred_logits"], pan_o["aux_outputs"][0]["pred_logits"]) < TOL
+    # not the landscape result in disguise
+    _, pm_l = m(imgs.cuda(), ts, classes)
+    assert relmax(pm, pm_l) > 0.05
+    assert relmax(m.forward_dino(imgs.cuda(), tsp), o.forward_dino(imgs, tsp)) < TOL
 
 
 def test_full_depth_full_resolution_properties():
