@@ -374,7 +374,14 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down: drop the captured graph (it references the NCCL communicator) and leave through os._exit once every
+        # rank is here.  destroy_process_group() was observed to block forever after NCCL collectives had been captured
+        # into a CUDA graph (profiles/r01_multi_gpu.md); process exit releases the communicator just as well.
+        del graph
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def dominant_roofline(ops, torch, V, peaks, peak_src, breakdown):

@@ -110,10 +110,39 @@ def make_postprocess_golden(ref=None):
     print("wrote postprocess_synthetic.pt", [(c["scene"], len(c["out"]["v2"]["segments_info"])) for c in cases])
 
 
+MULTI_AR_STACKS = [(2, 32, 48, 5, False), (1, 32, 64, 6, False), (1, 32, 48, 8, True)]  # (views, H, W, input seed, portrait)
+
+
+def multi_ar_head_inputs():
+    """The panoptic head's multi_ar=True argument lists for three stacks (two landscape shapes + one portrait)."""
+    per = [head_inputs(V, H, Wd, seed=sd, portrait=pt) for V, H, Wd, sd, pt in MULTI_AR_STACKS]
+    in_feats = tuple([st[0][i] for st in per] for i in range(3))
+    return in_feats, [st[1] for st in per], [st[2] for st in per], [st[3] for st in per]
+
+
+def make_multi_ar_golden(ref=None):
+    """Outputs of the REFERENCE PanopticDecoder with multi_ar=True (panoptic_decoder.py:41-77, mask_transformer.py:121-275)."""
+    ref = ref or ref_import.load_reference()
+    m = build_ref_head(ref, "v1")
+    args = multi_ar_head_inputs()
+    with torch.no_grad():
+        out = m(*args, CLASSES, multi_ar=True, outdevice="cpu")
+        mq = m(*args, CLASSES, multi_ar=True, outdevice="cpu", memory_queries=out["out_queries"])
+    blob = {"stacks": MULTI_AR_STACKS, "classes": CLASSES, "weight_seed": 1, "pred_logits": out["pred_logits"],
+            "pred_masks": [t.half() for t in out["pred_masks"]], "out_queries": out["out_queries"],
+            "aux0_masks": [t.half() for t in out["aux_outputs"][0]["pred_masks"]], "aux0_logits": out["aux_outputs"][0]["pred_logits"],
+            "memq_masks_equal_full": all(torch.equal(a, b) for a, b in zip(mq["pred_masks"], out["pred_masks"]))}
+    torch.save(blob, os.path.join(GOLDEN, "head_v1_multi_ar.pt"))
+    print("wrote head_v1_multi_ar.pt", [tuple(t.shape) for t in blob["pred_masks"]], blob["memq_masks_equal_full"])
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "postprocess":
         make_postprocess_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "multi_ar":
+        make_multi_ar_golden()
     else:
         main()
         make_postprocess_golden()
+        make_multi_ar_golden()

@@ -256,23 +256,32 @@ class MaskTransformer(nn.Module):
 
     def forward_prediction_heads(self, output, mask_feats, cls_embeddings, attn_mask_target_size=None):
         """output (Q, B, C); mask_feats (B, V, Cm, Hm, Wm).  Returns class logits (B,Q,K), mask logits (B,V,Q,Hm,Wm),
-        boolean attention mask (B*heads, Q, V*h*w) with True = blocked (or None)."""
+        boolean attention mask (B*heads, Q, V*h*w) with True = blocked (or None).
+        Multi aspect ratio (mask_transformer.py:215-275 with multi_ar=True): mask_feats and attn_mask_target_size are
+        lists with one entry per stack; mask logits come back as a list, the attention mask covers the concatenated
+        tokens of all stacks in stack order."""
+        multi = isinstance(mask_feats, (list, tuple))
+        mfs = list(mask_feats) if multi else [mask_feats]
+        sizes = (list(attn_mask_target_size) if multi else [attn_mask_target_size]) if attn_mask_target_size is not None else None
         dec = self.decoder_norm(output).transpose(0, 1)
         lang = self.lang_embed(dec)
         lang = lang / (lang.norm(dim=-1, keepdim=True) + 1e-7)
         logits = self.cls_logit_scale.exp() * lang @ cls_embeddings.unsqueeze(0).transpose(1, 2)
         emb = self.mask_embed(dec)
-        masks = torch.einsum("bqc,bvchw->bvqhw", emb, mask_feats)
+        masks = [torch.einsum("bqc,bvchw->bvqhw", emb, mf) for mf in mfs]
         attn_mask = None
-        if attn_mask_target_size is not None:
-            B, V, Q, _, _ = masks.shape
-            small = F.interpolate(masks.flatten(0, 1), size=tuple(attn_mask_target_size), mode="bilinear", align_corners=False)
-            small = small.view(B, V, Q, -1).permute(0, 2, 1, 3).flatten(2)  # (B, Q, V*h*w)
+        if sizes is not None:
+            smalls = []
+            for mk, size in zip(masks, sizes):
+                B, V, Q, _, _ = mk.shape
+                small = F.interpolate(mk.flatten(0, 1), size=tuple(size), mode="bilinear", align_corners=False)
+                smalls.append(small.view(B, V, Q, -1).permute(0, 2, 1, 3).flatten(2))  # (B, Q, V*h*w)
+            small = torch.cat(smalls, dim=2)
             attn_mask = (small.sigmoid().unsqueeze(1).repeat(1, self.num_heads, 1, 1).flatten(0, 1) < 0.5).bool().detach()
-        return logits, masks, attn_mask
+        return logits, (masks if multi else masks[0]), attn_mask
 
-    def forward(self, fpn_f, mask_feats, true_shape, cls_embeddings, deep_supervision=True):
-        f = fpn_f[0]  # (B, V, C, h, w)
+    def _stack_tokens(self, f, true_shape):
+        """One stack f (B, V, C, h, w) -> (memory tokens (V*h*w, B, C) + level embedding, their positional encoding)."""
         B, V, Cc, h, w = f.shape
         Ht, Wt = int(true_shape[0, 0, 0]), int(true_shape[0, 0, 1])
         if Wt >= Ht:
@@ -282,16 +291,30 @@ class MaskTransformer(nn.Module):
             pe = sine_position_embedding(w, h, self.hidden_dim // 2, f.device).flatten(1)
         pos = pe.t()[:, None, :].expand(h * w, B, Cc).repeat(V, 1, 1)  # (V*h*w, B, C)
         src = f.permute(0, 2, 1, 3, 4).flatten(2).permute(2, 0, 1) + self.level_embed.weight[0][None, None]
+        return src, pos
+
+    def forward(self, fpn_f, mask_feats, true_shape, cls_embeddings, deep_supervision=True, multi_ar=False):
+        """multi_ar: fpn_f[0], mask_feats, true_shape are lists with one entry per stack (mask_transformer.py:126-146)."""
+        if multi_ar:
+            toks = [self._stack_tokens(f, ts) for f, ts in zip(fpn_f[0], true_shape)]
+            src, pos = torch.cat([t[0] for t in toks], 0), torch.cat([t[1] for t in toks], 0)
+            B = fpn_f[0][0].shape[0]
+            size = [tuple(f.shape[-2:]) for f in fpn_f[0]]
+        else:
+            src, pos = self._stack_tokens(fpn_f[0], true_shape)
+            B = fpn_f[0].shape[0]
+            size = tuple(fpn_f[0].shape[-2:])
+        h, w = size if not multi_ar else (None, None)
         query_embed = self.query_embed.weight.unsqueeze(1).repeat(1, B, 1)
         output = self.query_feat.weight.unsqueeze(1).repeat(1, B, 1)
-        cls, msk, attn_mask = self.forward_prediction_heads(output, mask_feats, cls_embeddings, (h, w))
+        cls, msk, attn_mask = self.forward_prediction_heads(output, mask_feats, cls_embeddings, size)
         pred_cls, pred_msk = ([cls], [msk]) if deep_supervision else ([], [])
         for i in range(self.num_layers):
             attn_mask[torch.where(attn_mask.sum(-1) == attn_mask.shape[-1])] = False
             output = self.cross_attn_layers[i](output, src, attn_mask, pos, query_embed)
             output = self.self_attn_layers[i](output, query_embed)
             output = self.ffn_layers[i](output)
-            cls, msk, attn_mask = self.forward_prediction_heads(output, mask_feats, cls_embeddings, (h, w))
+            cls, msk, attn_mask = self.forward_prediction_heads(output, mask_feats, cls_embeddings, size)
             if deep_supervision or i == self.num_layers - 1:
                 pred_cls.append(cls)
                 pred_msk.append(msk)
@@ -317,8 +340,8 @@ class PanopticDecoder(nn.Module):
                                                 num_feature_levels=len(fpn_dim), landscape_only=landscape_only)
         self.deep_supervision = deep_supervision
 
-    def forward(self, in_feats, in_imgs, pos, true_shape, classes, max_bs=None, outdevice=None, memory_queries=None):
-        cat = torch.cat(in_feats, dim=-1)  # (B, V, N, 2816)
+    def _stack_features(self, cat, in_imgs, pos, true_shape):
+        """One stack of equally shaped views: cat (B, V, N, 2816) -> ([fpn (B, V, C, h, w)], mask_f (B, V, Cm, Hm, Wm))."""
         B, V = cat.shape[:2]
         x = cat.flatten(0, 1)
         if self.input_mixer is not None:
@@ -331,11 +354,23 @@ class PanopticDecoder(nn.Module):
             # storage convention (utils.transpose_to_landscape, dims=(2,3); utils.py:46-49)
             fpn, mask_f = self.upscaler((x, in_imgs.flatten(0, 1)), (H, W))
             fpn, mask_f = [t.swapaxes(2, 3) for t in fpn], mask_f.swapaxes(2, 3)
-        fpn = [t.unflatten(0, (B, V)) for t in fpn]
-        mask_f = mask_f.unflatten(0, (B, V))
-        cls_emb = self.text_encoder(classes).to(mask_f.device)
+        return [t.unflatten(0, (B, V)) for t in fpn], mask_f.unflatten(0, (B, V))
+
+    def forward(self, in_feats, in_imgs, pos, true_shape, classes, max_bs=None, outdevice=None, memory_queries=None,
+                multi_ar=False):
+        """multi_ar (panoptic_decoder.py:44-45, 53-76): every tensor argument is a list with one entry per stack of
+        equally shaped views; `pred_masks` comes back as a list with one tensor per stack."""
+        if multi_ar:
+            cats = [torch.cat(parts, dim=-1) for parts in zip(*in_feats)]
+            per = [self._stack_features(c, im, p, ts) for c, im, p, ts in zip(cats, in_imgs, pos, true_shape)]
+            fpn = [[st[0][lvl] for st in per] for lvl in range(len(per[0][0]))]
+            mask_f = [st[1] for st in per]
+        else:
+            fpn, mask_f = self._stack_features(torch.cat(in_feats, dim=-1), in_imgs, pos, true_shape)
+        cls_emb = self.text_encoder(classes).to(mask_f[0].device if multi_ar else mask_f.device)
         if memory_queries is None:
-            return self.mask_transformer(fpn, mask_f, true_shape, cls_emb, deep_supervision=self.deep_supervision)
+            return self.mask_transformer(fpn, mask_f, true_shape, cls_emb, deep_supervision=self.deep_supervision,
+                                         multi_ar=multi_ar)
         logits, masks, _ = self.mask_transformer.forward_prediction_heads(memory_queries, mask_f, cls_emb)
         return {"pred_logits": logits, "pred_masks": masks}
 

@@ -61,7 +61,10 @@ class PanSt3R(nn.Module):
 
     @torch.no_grad()
     def forward_inference_multi_ar(self, imgs, true_shape, classes, num_keyframes=None, max_bs=None, outdevice=None):
-        """imgs: list of (3,H,W) tensors sharing one shape; true_shape (N,2).  Returns (pointmaps list, panout)."""
+        """imgs: list of (3,H,W) tensors; true_shape (N,2).  Returns (pointmaps list, panout).  Views of different
+        shape / orientation go through the per-view restatement below (panst3r.py:169-284 with must3r's stack_views)."""
+        if len({(tuple(t), tuple(im.shape[-2:])) for im, t in zip(imgs, true_shape.tolist())}) > 1:
+            return self._forward_inference_mixed(imgs, true_shape, classes, num_keyframes)
         N = len(imgs)
         if num_keyframes is None or num_keyframes > N:
             num_keyframes = N
@@ -91,6 +94,59 @@ class PanSt3R(nn.Module):
         inv = np.argsort(order)
         return [pointmaps[i] for i in inv], {"pred_logits": pan["pred_logits"], "pred_masks": [masks[i] for i in inv],
                                               "out_queries": pan["out_queries"]}
+
+
+def _mixed(self, imgs, true_shape, classes, num_keyframes=None):
+    """Mixed aspect ratios, view by view: encoder / DINOv2 / render are per-view independent; the memory build walks the
+    keyframes in order (mem_batches [2, 1, 1, ...]); the head sees one stack per distinct shape (keyframes first)."""
+    N = len(imgs)
+    if num_keyframes is None or num_keyframes > N:
+        num_keyframes, keyframes = N, list(range(N))
+    else:
+        keyframes = np.linspace(0, N - 1, num_keyframes, dtype=int).tolist()
+    order = keyframes + sorted(set(range(N)).difference(keyframes))
+    k = num_keyframes
+    im = [imgs[i][None, None] for i in order]                      # (1, 1, 3, H, W) each
+    ts = [true_shape[i][None, None] for i in order]                # (1, 1, 2)
+    enc = [self.forward_must3r_encoder(a, t) for a, t in zip(im, ts)]
+    x, pos = [e[0] for e in enc], [e[1] for e in enc]
+    edges = [0] + np.cumsum(self.get_must3r_mem_batches(k)).tolist()
+    mem = None
+    for a, b in zip(edges[:-1], edges[1:]):
+        mem, _, _ = self.must3r_decoder(torch.cat(x[a:b], 1), torch.cat(pos[a:b], 1), torch.cat(ts[a:b], 1), mem,
+                                        render=False, return_feats=True)
+    ren = [self.render(x[p], pos[p], ts[p], mem) for p in range(N)]
+    dino = [self.forward_dino(im[p], ts[p]) for p in range(N)]
+    stacks = {}
+    for p in range(N):
+        stacks.setdefault((tuple(ts[p].flatten().tolist()), tuple(im[p].shape[-2:])), []).append(p)
+    stacks = list(stacks.values())
+
+    def head(sel, queries=None):
+        groups = [[p for p in idx if sel(p)] for idx in stacks]
+        groups = [g_ for g_ in groups if g_]
+        cat1 = lambda lst, g_: torch.cat([lst[p] for p in g_], 1)  # noqa: E731
+        feats = tuple([cat1(src, g_) for g_ in groups] for src in (x, [r[1] for r in ren], dino))
+        out = self.panoptic_decoder(feats, [cat1(im, g_) for g_ in groups], [cat1(pos, g_) for g_ in groups],
+                                    [cat1(ts, g_) for g_ in groups], classes, multi_ar=True, memory_queries=queries)
+        return groups, out
+
+    gk, pan = head(lambda p: p < k)
+    masks = [None] * N
+    for g_, mk in zip(gk, pan["pred_masks"]):
+        for j, p in enumerate(g_):
+            masks[p] = mk[0, j]
+    if k < N:
+        gn, out_n = head(lambda p: p >= k, pan["out_queries"])
+        for g_, mk in zip(gn, out_n["pred_masks"]):
+            for j, p in enumerate(g_):
+                masks[p] = mk[0, j]
+    inv = np.argsort(order)
+    return [ren[i][0][0, 0] for i in inv], {"pred_logits": pan["pred_logits"], "pred_masks": [masks[i] for i in inv],
+                                            "out_queries": pan["out_queries"]}
+
+
+PanSt3R._forward_inference_mixed = torch.no_grad()(_mixed)
 
 
 def build_panst3r(variant: str = "v1", enc_depth=24, dec_depth=12, dino_depth=24, mixer_layers=3) -> PanSt3R:

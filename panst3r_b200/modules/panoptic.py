@@ -229,10 +229,14 @@ class MaskTransformer(nn.Module):
             e = ops.gemm(e, w16(l.weight), bias=bias_of(l), act=ops.ACT_RELU if i < nl - 1 else ops.ACT_NONE)
         masks = None
         if want_masks:
-            V, Hm, Wm, Cm = mask_feats.shape
-            masks = torch.empty((V, Q, Hm, Wm), device=output.device, dtype=torch.float32)
-            ops.gemm(mask_feats.view(V * Hm * Wm, Cm), e, out=masks, store_mode=ops.STORE_TRANSPOSED,
-                     rows_per_batch=Hm * Wm, batch_stride=Q * Hm * Wm, ldt=Hm * Wm)
+            def plane_major(mf):
+                V, Hm, Wm, Cm = mf.shape
+                mk = torch.empty((V, Q, Hm, Wm), device=output.device, dtype=torch.float32)
+                ops.gemm(mf.view(V * Hm * Wm, Cm), e, out=mk, store_mode=ops.STORE_TRANSPOSED,
+                         rows_per_batch=Hm * Wm, batch_stride=Q * Hm * Wm, ldt=Hm * Wm)
+                return mk
+            # several aspect-ratio stacks (multi_ar): one mask tensor per stack, as the reference returns them
+            masks = [plane_major(mf) for mf in mask_feats] if isinstance(mask_feats, (list, tuple)) else plane_major(mask_feats)
         bits = None
         if pooled is not None:
             nk = pooled.shape[0]
@@ -250,26 +254,34 @@ class MaskTransformer(nn.Module):
         return ops.gemm(o.view(-1, d), w16(m.out_proj.weight), bias=bias_of(m.out_proj), residual=residual)
 
     @torch.no_grad()
-    def forward_nhwc(self, src: torch.Tensor, mask_feats: torch.Tensor, hw, cls_emb: torch.Tensor,
+    def forward_nhwc(self, src, mask_feats, hw, cls_emb: torch.Tensor,
                      deep_supervision: bool = True, pooled: Optional[torch.Tensor] = None,
-                     mask_override: Optional[List[torch.Tensor]] = None, portrait: bool = False):
+                     mask_override: Optional[List[torch.Tensor]] = None, portrait=False):
         """src bf16 (V*h*w, C) = stride-16 features + level_embed, views flattened view-major (batch 1);
         mask_feats bf16 (V', Hm, Wm, Cm) — the views whose full-resolution masks this call produces (all V, or this
         rank's shard); pooled bf16 (V*h*w, Cm): centre-pooled mask features of ALL views (computed from mask_feats
-        when omitted).  Returns the reference's output dict (batch dim 1)."""
-        h, w = hw
+        when omitted).  Returns the reference's output dict (batch dim 1).
+        Multi aspect ratio (mask_transformer.py:126-146 with multi_ar=True): src / mask_feats / hw / portrait are
+        LISTS with one entry per stack of equally shaped views; the memory tokens of all stacks are concatenated in
+        stack order (each with the PE of its own grid) and `pred_masks` comes back as a list with one tensor per stack."""
+        multi = isinstance(src, (list, tuple))
+        srcs, mfs, hws = (list(src), list(mask_feats), list(hw)) if multi else ([src], [mask_feats], [hw])
+        ports = list(portrait) if isinstance(portrait, (list, tuple)) else [portrait] * len(srcs)
         d, H, Q = self.hidden_dim, self.num_heads, self.num_queries
         hd = d // H
+        dev = srcs[0].device
+        # key = memory + pos (pos of view 0 of each stack tiled over its views, :139-141)
+        src_pos = [ops.add_bcast(s_, self._pos(h_, w_, dev, p_)) for s_, (h_, w_), p_ in zip(srcs, hws, ports)]
+        src = srcs[0] if len(srcs) == 1 else torch.cat(srcs, 0)
+        src_pos = src_pos[0] if len(src_pos) == 1 else torch.cat(src_pos, 0)
         Nk = src.shape[0]
-        dev = src.device
-        pos = self._pos(h, w, dev, portrait)
-        src_pos = ops.add_bcast(src, pos)  # key = memory + pos (pos of view 0 tiled over views, :139-141)
         wk, bk, wv, bv = self._kv_weights()
         k_all = ops.gemm(src_pos, wk, bias=bk).view(1, Nk, self.num_layers, H, hd)
         v_all = ops.gemm(src, wv, bias=bv).view(1, Nk, self.num_layers, H, hd)
-        Vn, Hm, Wm, Cm = mask_feats.shape
         if pooled is None:
-            pooled = ops.center_pool8(mask_feats).view(Vn * (Hm // 8) * (Wm // 8), Cm)
+            pl = [ops.center_pool8(mf).view(-1, mf.shape[-1]) for mf in mfs]
+            pooled = pl[0] if len(pl) == 1 else torch.cat(pl, 0)
+        mask_feats = mfs if multi else mfs[0]
         qe = b16(self.query_embed.weight)
         output = b16(self.query_feat.weight)
         pred_cls, pred_msk = [], []
@@ -301,10 +313,11 @@ class MaskTransformer(nn.Module):
             if deep_supervision or last:
                 pred_cls.append(cls)
                 pred_msk.append(msk)
+        b1 = (lambda t: [x[None] for x in t]) if multi else (lambda t: t[None])  # batch dim 1 (per stack when multi_ar)
         return {
             "pred_logits": pred_cls[-1][None],
-            "pred_masks": pred_msk[-1][None],
-            "aux_outputs": [{"pred_logits": a[None], "pred_masks": b_[None]} for a, b_ in zip(pred_cls[:-1], pred_msk[:-1])],
+            "pred_masks": b1(pred_msk[-1]),
+            "aux_outputs": [{"pred_logits": a[None], "pred_masks": b1(b_)} for a, b_ in zip(pred_cls[:-1], pred_msk[:-1])],
             "out_queries": output.view(Q, 1, d),
         }
 
@@ -332,7 +345,38 @@ class PanopticDecoder(nn.Module):
         `cat_feats`: optional pre-concatenated bf16 (B, V, N, 2816) buffer the producers already wrote into
         (then in_feats is ignored).  B must be 1 on the CUDA path."""
         if multi_ar:
-            raise ops._l.Pst3rError("multi aspect-ratio batches are not implemented on the CUDA path yet")
+            return self._forward_multi_ar(in_feats, in_imgs, pos, true_shape, classes, outdevice, memory_queries, cat_feats)
+        src, mask_f, grid, portrait, dev = self._stack_features(in_feats, in_imgs, true_shape, cat_feats)
+        mt = self.mask_transformer
+        cls_emb = self.text_encoder(classes, device=dev)
+        if memory_queries is None:
+            out = mt.forward_nhwc(src, mask_f, grid, cls_emb, deep_supervision=self.deep_supervision, portrait=portrait)
+        else:
+            logits, masks, _ = mt.prediction_heads(self._queries(memory_queries), mask_f, None, cls_emb, want_masks=True)
+            out = {"pred_logits": logits[None], "pred_masks": masks[None]}
+        return self._to_device(out, outdevice, dev)
+
+    def _queries(self, memory_queries):
+        mt = self.mask_transformer
+        q = memory_queries.reshape(mt.num_queries, mt.hidden_dim)
+        return q if q.dtype == torch.bfloat16 else ops.to_bf16(q.float().contiguous())
+
+    @staticmethod
+    def _to_device(out, outdevice, dev):
+        if outdevice is None or torch.device(outdevice) == dev:
+            return out
+
+        def mv(v):
+            if torch.is_tensor(v):
+                return v.to(outdevice)
+            if isinstance(v, dict):
+                return {k: mv(x) for k, x in v.items()}
+            return [mv(x) for x in v]
+        return {k: mv(v) for k, v in out.items()}
+
+    def _stack_features(self, in_feats, in_imgs, true_shape, cat_feats):
+        """One stack of equally shaped views -> (stride-16 tokens + level_embed (V*N, 768), mask features
+        (V, Hm, Wm, Cm) pixel-major, token grid, portrait flag, device), both in the landscape storage convention."""
         if cat_feats is None:
             # producers that did not write into a shared buffer: concatenate (pure data movement)
             parts = [t if t.dtype == torch.bfloat16 else ops.to_bf16(t.float().contiguous()) for t in in_feats]
@@ -358,18 +402,28 @@ class PanopticDecoder(nn.Module):
             src = src.view(V, hs, ws, -1).transpose(1, 2).contiguous().view(V * N, -1)
             mask_f = mask_f.transpose(1, 2).contiguous()
             hs, ws = ws, hs
+        return src, mask_f, (hs, ws), portrait, dev
+
+    def _forward_multi_ar(self, in_feats, in_imgs, pos, true_shape, classes, outdevice, memory_queries, cat_feats):
+        """panoptic_decoder.py:44-45, 53-76 with multi_ar=True: every argument is a list with one entry per stack of
+        equally shaped views; `pred_masks` (and the aux masks) come back as lists with one (1, n_i, Q, h_i, w_i) tensor
+        per stack.  LoftUp's batch-global MinMaxScaler stays per stack, as in the reference (each stack is one
+        `batched_map` call, utils.py:90-160)."""
+        n_st = len(true_shape)
+        cats = cat_feats if cat_feats is not None else [None] * n_st
+        feats = [tuple(f[i] for f in in_feats) if in_feats is not None else None for i in range(n_st)]
+        st = [self._stack_features(feats[i], in_imgs[i], true_shape[i], cats[i]) for i in range(n_st)]
+        dev = st[0][4]
+        mt = self.mask_transformer
         cls_emb = self.text_encoder(classes, device=dev)
         if memory_queries is None:
-            out = mt.forward_nhwc(src, mask_f, (hs, ws), cls_emb, deep_supervision=self.deep_supervision, portrait=portrait)
+            out = mt.forward_nhwc([s_[0] for s_ in st], [s_[1] for s_ in st], [s_[2] for s_ in st], cls_emb,
+                                  deep_supervision=self.deep_supervision, portrait=[s_[3] for s_ in st])
         else:
-            q = memory_queries.reshape(mt.num_queries, mt.hidden_dim)
-            q = q if q.dtype == torch.bfloat16 else ops.to_bf16(q.float().contiguous())
-            logits, masks, _ = mt.prediction_heads(q, mask_f, None, cls_emb, want_masks=True)
-            out = {"pred_logits": logits[None], "pred_masks": masks[None]}
-        if outdevice is not None and torch.device(outdevice) != dev:
-            out = {k: (v.to(outdevice) if torch.is_tensor(v) else
-                       [{kk: vv.to(outdevice) for kk, vv in a.items()} for a in v]) for k, v in out.items()}
-        return out
+            logits, masks, _ = mt.prediction_heads(self._queries(memory_queries), [s_[1] for s_ in st], None, cls_emb,
+                                                   want_masks=True)
+            out = {"pred_logits": logits[None], "pred_masks": [m_[None] for m_ in masks]}
+        return self._to_device(out, outdevice, dev)
 
 
 # =====================================================================================================

@@ -143,8 +143,10 @@ class PanSt3R(nn.Module):
     def forward_inference_multi_ar(self, imgs: List[torch.Tensor], true_shape, classes, num_keyframes=None,
                                    use_retrieval=False, max_bs=None, outdevice=None, amp=False):
         """Keyframes build the memory and run the full panoptic head; the remaining frames are rendered against the
-        frozen memory and decoded with the keyframes' final queries (panst3r.py:254-277, panoptic_decoder.py:70-76).
-        All images must share one shape on the CUDA path (single aspect ratio)."""
+        frozen memory and decoded with the keyframes' final queries (panst3r.py:169-284, panoptic_decoder.py:70-76).
+        Views may differ in aspect ratio / orientation: they are grouped into stacks of equal `true_shape`
+        (must3r `stack_views`, panst3r.py:203-206, 257-263), every per-view stage runs once per stack, the memory
+        build walks the keyframes in order (the two views of the initialisation pair must share a shape)."""
         if use_retrieval:
             raise NotImplementedError("retrieval keyframe selection needs asmk + a retrieval checkpoint (out of scope)")
         N = len(imgs)
@@ -156,24 +158,86 @@ class PanSt3R(nn.Module):
         not_keyframes = sorted(set(range(N)).difference(set(keyframes)))
         assert len(keyframes) + len(not_keyframes) == N
         order = keyframes + not_keyframes
-        ts_all = (true_shape.cpu() if true_shape.is_cuda else true_shape)[order][None]
-        im = torch.stack([imgs[i] for i in order])[None]
+        ts_o = (true_shape.cpu() if true_shape.is_cuda else true_shape)[order]
+        ims = [imgs[i] for i in order]
         k = num_keyframes
-        cat, rows, x, pos, join = self._features(im, ts_all)
-        Ntok = x.shape[2]
-        mem = self._build_memory_shared(x[:, :k], pos[:, :k], ts_all[:, :k], join)
-        # render keyframes and the rest in one batch against the final memory (identical per-view results)
-        _, pointmaps, _ = self.must3r_decoder(x, pos, ts_all, mem, render=True, return_feats="last",
-                                              feats_out=rows[:, ENC_DIM:ENC_DIM + DEC_DIM])
+        # ---- stacks of equally shaped views (positions in the reordered list, ascending: keyframes first)
+        stacks = {}
+        for p, (im, t) in enumerate(zip(ims, ts_o.tolist())):
+            stacks.setdefault((tuple(t), tuple(im.shape[-2:])), []).append(p)
+        stacks = list(stacks.values())
+        where = {p: (si, j) for si, idx in enumerate(stacks) for j, p in enumerate(idx)}
+        st = []
+        join = None
+        for idx in stacks:  # per-view producers (encoder, DINOv2 on the side stream) per stack
+            im = torch.stack([ims[p] for p in idx])[None]
+            ts_s = ts_o[idx][None]
+            cat, rows, x, pos, join = self._features(im, ts_s)
+            st.append(dict(idx=idx, im=im, ts=ts_s, cat=cat, rows=rows, x=x, pos=pos, kc=sum(1 for p in idx if p < k)))
+        # ---- sequential memory build over the keyframes (engine/must3r.py:28-69)
+        self.must3r_decoder.reserve_views = k
+        edges = [0] + np.cumsum(self.get_must3r_mem_batches(k)).tolist()
+        mem = None
+        for a, b in zip(edges[:-1], edges[1:]):
+            sel = [where[p] for p in range(a, b)]
+            xs = [st[si]["x"][:, j] for si, j in sel]
+            if any(t.shape != xs[0].shape for t in xs) or any(not torch.equal(st[si]["ts"][0, j], st[sel[0][0]]["ts"][0, sel[0][1]])
+                                                              for si, j in sel):
+                raise ops._l.Pst3rError("the views of one memory-update batch (the initialisation pair) must share a shape")
+            si0 = sel[0][0]
+            if len(sel) == 1 or all(si == si0 for si, _ in sel) and [j for _, j in sel] == list(range(sel[0][1], sel[0][1] + len(sel))):
+                j0 = sel[0][1]
+                xb, pb, tb = st[si0]["x"][:, j0:j0 + len(sel)], st[si0]["pos"][:, j0:j0 + len(sel)], st[si0]["ts"][:, j0:j0 + len(sel)]
+            else:
+                xb = torch.stack(xs, 1)
+                pb = torch.stack([st[si]["pos"][:, j] for si, j in sel], 1)
+                tb = torch.stack([st[si]["ts"][:, j] for si, j in sel], 1)
+            mem, _, _ = self.must3r_decoder(xb, pb, tb, mem, render=False, return_feats=False, compute_pointmaps=False)
+        # ---- render every view against the final memory, stack by stack (identical per-view results)
+        for s_ in st:
+            _, s_["pm"], _ = self.must3r_decoder(s_["x"], s_["pos"], s_["ts"], mem, render=True, return_feats="last",
+                                                 feats_out=s_["rows"][:, ENC_DIM:ENC_DIM + DEC_DIM])
         if join is not None:
             torch.cuda.current_stream().wait_stream(join)
-        pan_kf = self.panoptic_decoder(None, im[:, :k], pos[:, :k], ts_all[:, :k], classes, cat_feats=cat[:, :k])
-        masks = list(pan_kf["pred_masks"][0])
-        if N > k:
-            pan_nk = self.panoptic_decoder(None, im[:, k:], pos[:, k:], ts_all[:, k:], classes, cat_feats=cat[:, k:],
-                                           memory_queries=pan_kf["out_queries"])
-            masks += list(pan_nk["pred_masks"][0])
-        pms = list(pointmaps[0])
+        # ---- panoptic head: keyframes (the leading kc views of each stack) with the full query decoder ...
+        kf = [s_ for s_ in st if s_["kc"] > 0]
+        if len(st) == 1:
+            s_ = st[0]
+            kc = s_["kc"]
+            pan_kf = self.panoptic_decoder(None, s_["im"][:, :kc], s_["pos"][:, :kc], s_["ts"][:, :kc], classes,
+                                           cat_feats=s_["cat"][:, :kc])
+            kf_masks = [pan_kf["pred_masks"]]
+        else:
+            pan_kf = self.panoptic_decoder(None, [s_["im"][:, :s_["kc"]] for s_ in kf], [s_["pos"][:, :s_["kc"]] for s_ in kf],
+                                           [s_["ts"][:, :s_["kc"]] for s_ in kf], classes, multi_ar=True,
+                                           cat_feats=[s_["cat"][:, :s_["kc"]] for s_ in kf])
+            kf_masks = pan_kf["pred_masks"]
+        masks = [None] * N
+        for s_, mk in zip(kf, kf_masks):
+            for j in range(s_["kc"]):
+                masks[s_["idx"][j]] = mk[0, j]
+        # ... and the remaining frames with the keyframes' final queries (memory-query path)
+        nk = [s_ for s_ in st if s_["kc"] < len(s_["idx"])]
+        if nk:
+            if len(st) == 1:
+                s_ = nk[0]
+                kc = s_["kc"]
+                pan_nk = self.panoptic_decoder(None, s_["im"][:, kc:], s_["pos"][:, kc:], s_["ts"][:, kc:], classes,
+                                               cat_feats=s_["cat"][:, kc:], memory_queries=pan_kf["out_queries"])
+                nk_masks = [pan_nk["pred_masks"]]
+            else:
+                pan_nk = self.panoptic_decoder(None, [s_["im"][:, s_["kc"]:] for s_ in nk], [s_["pos"][:, s_["kc"]:] for s_ in nk],
+                                               [s_["ts"][:, s_["kc"]:] for s_ in nk], classes, multi_ar=True,
+                                               cat_feats=[s_["cat"][:, s_["kc"]:] for s_ in nk],
+                                               memory_queries=pan_kf["out_queries"])
+                nk_masks = pan_nk["pred_masks"]
+            for s_, mk in zip(nk, nk_masks):
+                for j in range(s_["kc"], len(s_["idx"])):
+                    masks[s_["idx"][j]] = mk[0, j - s_["kc"]]
+        pms = [None] * N
+        for s_ in st:
+            for j, p in enumerate(s_["idx"]):
+                pms[p] = s_["pm"][0, j]
         inv = np.argsort(order)
         panout = {"pred_logits": pan_kf["pred_logits"], "pred_masks": [masks[i] for i in inv],
                   "out_queries": pan_kf["out_queries"]}

@@ -260,6 +260,61 @@ def test_forward_portrait_vs_oracle(pair):
     assert relmax(m.forward_dino(imgs.cuda(), tsp), o.forward_dino(imgs, tsp)) < TOL
 
 
+def test_head_multi_ar_against_reference_golden():
+    """PanopticDecoder(multi_ar=True) — three stacks (two landscape shapes + one portrait) — vs the REFERENCE's output
+    lists (tests/golden/head_v1_multi_ar.pt, oracle/make_golden.py::make_multi_ar_golden)."""
+    from oracle.make_golden import multi_ar_head_inputs
+    from panst3r_b200.modules.panoptic import PanopticDecoder, PixelShuffleUpscaler
+    g = torch.load(os.path.join(GOLDEN, "head_v1_multi_ar.pt"))
+    o = build_oracle_head("v1")
+    m = PanopticDecoder(upscaler=PixelShuffleUpscaler(input_dim=2816)).eval()
+    m.load_state_dict(o.state_dict(), strict=True)
+    m = m.cuda()
+    m.text_encoder.class_embeddings = o.text_encoder.class_embeddings
+    in_feats, imgs, pos, ts = multi_ar_head_inputs()
+    cu = lambda lst: [t.cuda() for t in lst]  # noqa: E731
+    out = m(tuple(cu(f) for f in in_feats), cu(imgs), cu(pos), ts, CLASSES, multi_ar=True)
+    assert len(out["pred_masks"]) == 3 and len(out["aux_outputs"]) == 6
+    for a, b, c, d in zip(out["pred_masks"], g["pred_masks"], out["aux_outputs"][0]["pred_masks"], g["aux0_masks"]):
+        assert a.shape == b.shape and a.dtype == torch.float32
+        assert relmax(c, d) < TOL          # first head: no mask feedback yet
+        assert relmax(a, b) < 0.25         # free-running final head (ill-conditioned with random weights, see module doc)
+    assert relmax(out["aux_outputs"][0]["pred_logits"], g["aux0_logits"]) < TOL
+    # well-conditioned check of the last head on every stack: the reference's final queries through the memory-query path
+    mq = m(tuple(cu(f) for f in in_feats), cu(imgs), cu(pos), ts, CLASSES, multi_ar=True, memory_queries=g["out_queries"].cuda())
+    for a, b in zip(mq["pred_masks"], g["pred_masks"]):
+        assert relmax(a, b) < TOL
+    assert relmax(mq["pred_logits"], g["pred_logits"]) < TOL
+
+
+def test_forward_inference_multi_ar_mixed_shapes_vs_oracle(pair):
+    """Views of different shape and orientation in one scene (must3r stack_views, panst3r.py:203-206, 257-263): per-view
+    stages run per stack, the memory build walks the keyframes in order, the head sees one stack per shape."""
+    o, m, _, _, classes = pair
+    g = torch.Generator().manual_seed(11)
+    shapes = [(64, 96), (64, 96), (64, 64), (64, 96), (64, 96), (64, 64)]
+    ts = torch.tensor([[64, 96], [64, 96], [64, 64], [96, 64], [64, 96], [64, 64]])  # view 3: portrait, stored transposed
+    imgs = [torch.rand(3, *sh, generator=g) * 2 - 1 for sh in shapes]
+    for kf in (None, 4):  # all keyframes; 4 keyframes (linspace -> views 0, 1, 3, 5) + 2 render-only frames
+        pms_o, pan_o = o.forward_inference_multi_ar(imgs, ts, classes, num_keyframes=kf)
+        pms, pan = m.forward_inference_multi_ar([im.cuda() for im in imgs], ts, classes, num_keyframes=kf)
+        assert len(pms) == len(pan["pred_masks"]) == 6
+        for a, b in zip(pms, pms_o):
+            assert a.shape == b.shape and relmax(a, b) < TOL
+        for a, b in zip(pan["pred_masks"], pan_o["pred_masks"]):
+            assert a.shape == b.shape and torch.isfinite(a).all()
+        if kf is not None:  # render-only frames decoded with the ORACLE's final queries: well-conditioned comparison
+            assert relmax(pan["pred_logits"], pan_o["pred_logits"]) < 0.25
+    # same-shape lists keep going through the single-stack path: identical to forward()
+    same = [imgs[i].cuda() for i in (0, 1, 4)]
+    pms1, pan1 = m.forward_inference_multi_ar(same, ts[[0, 1, 4]], classes)
+    pan2, pm2 = m(torch.stack(same)[None], ts[[0, 1, 4]][None], classes)
+    assert torch.equal(torch.stack(pms1), pm2[0]) and torch.equal(torch.stack(pan1["pred_masks"]), pan2["pred_masks"][0])
+    # the initialisation pair must share a shape
+    with pytest.raises(Exception):
+        m.forward_inference_multi_ar([imgs[0].cuda(), imgs[2].cuda(), imgs[1].cuda()], ts[[0, 2, 1]], classes)
+
+
 def test_full_depth_full_resolution_properties():
     """Full-depth model at 512x384 (4 keyframes): finite outputs, reference shapes, render chunk invariance."""
     from panst3r_b200.panst3r import build_panst3r

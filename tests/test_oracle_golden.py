@@ -26,6 +26,39 @@ def test_oracle_head_matches_golden(path):
     assert torch.equal(mq["pred_masks"], out["pred_masks"])  # config-3 reuse path == final prediction head only
 
 
+def test_oracle_multi_ar_head_matches_golden():
+    """multi_ar=True (three stacks: two landscape shapes + one portrait) vs the reference's output lists."""
+    import os
+    from helpers import GOLDEN
+    from oracle.make_golden import multi_ar_head_inputs
+    g = torch.load(os.path.join(GOLDEN, "head_v1_multi_ar.pt"))
+    m = build_oracle_head("v1")
+    args = multi_ar_head_inputs()
+    with torch.no_grad():
+        out = m(*args, CLASSES, multi_ar=True)
+        mq = m(*args, CLASSES, multi_ar=True, memory_queries=out["out_queries"])
+    assert relmax(out["pred_logits"], g["pred_logits"]) < 1e-5 and relmax(out["out_queries"], g["out_queries"]) < 1e-5
+    assert len(out["pred_masks"]) == len(g["pred_masks"]) == 3
+    for a, b, c, d in zip(out["pred_masks"], g["pred_masks"], out["aux_outputs"][0]["pred_masks"], g["aux0_masks"]):
+        assert a.shape == b.shape and relmax(a, b) < 1e-3 and relmax(c, d) < 1e-3
+    assert g["memq_masks_equal_full"] and all(torch.equal(a, b) for a, b in zip(mq["pred_masks"], out["pred_masks"]))
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present (GPU box)")
+def test_oracle_multi_ar_head_equals_reference_modules():
+    from oracle.make_golden import build_ref_head, multi_ar_head_inputs
+    ref = ref_import.load_reference()
+    args = multi_ar_head_inputs()
+    for variant in ("v1", "v2"):
+        r, o = build_ref_head(ref, variant), build_oracle_head(variant)
+        with torch.no_grad():
+            ro = r(*args, CLASSES, multi_ar=True, outdevice="cpu")
+            oo = o(*args, CLASSES, multi_ar=True)
+        assert torch.equal(ro["pred_logits"], oo["pred_logits"]) and torch.equal(ro["out_queries"], oo["out_queries"])
+        for a, b in zip(ro["pred_masks"], oo["pred_masks"]):
+            assert torch.equal(a, b)  # bit-exact, portrait stack included
+
+
 @pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present (GPU box)")
 @pytest.mark.parametrize("variant,portrait", [("v1", False), ("v2", False), ("v1", True), ("v2", True)])
 def test_oracle_head_equals_reference_modules(variant, portrait):
