@@ -30,6 +30,21 @@ constexpr uint32_t AT3_TMEM_S = 0;     // S_A at 0, S_B at 128 (fp32)
 constexpr uint32_t AT3_TMEM_O = 256;   // O_A at 256, O_B at 320 (fp32)
 constexpr uint32_t AT3_TMEM_P = 384;   // P_A at 384, P_B at 448 (bf16 pairs: column c of row r = keys 2c, 2c+1)
 
+// 2^x on the FMA / ALU pipes (FA4-style): round-to-nearest split x = xi + xf by the 1.5 * 2^23 trick, degree-3 minimax
+// polynomial of 2^xf on [-0.5, 0.5] (relative error 1.0e-4, far below the bf16 rounding of P), exponent add.
+// Used for one element in POLY so that the MUFU pipe (16 ex2/clk/SM, the busiest unit of this kernel: ncu XU 59 %)
+// sheds that share of its load.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;
+  const float xf = x - (t - 12582912.0f);
+  float p = fmaf(0.05583828f, xf, 0.24263948f);
+  p = fmaf(p, xf, 0.69313675f);
+  p = fmaf(p, xf, 0.99992454f);
+  return __int_as_float(__float_as_int(p) + ((__float_as_int(t) - 0x4B400000) << 23));
+}
+
+template <int POLY>  // 0: every exponential on the MUFU; n > 0: one element in n through ex2_poly
 __global__ void __launch_bounds__(AT3_THREADS, 1)
 attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -217,9 +232,11 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float e0 = ex2_approx(fmaf(__uint_as_float(rr[i]), c, neg_m));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(rr[i + 1]), c, neg_m));
+            const float x1 = fmaf(__uint_as_float(rr[i + 1]), c, neg_m);
+            const float e1 = (POLY == 2) ? ex2_poly(x1) : ex2_approx(x1);
             const float e2 = ex2_approx(fmaf(__uint_as_float(rr[i + 2]), c, neg_m));
-            const float e3 = ex2_approx(fmaf(__uint_as_float(rr[i + 3]), c, neg_m));
+            const float x3 = fmaf(__uint_as_float(rr[i + 3]), c, neg_m);
+            const float e3 = (POLY == 2 || POLY == 4) ? ex2_poly(x3) : ex2_approx(x3);
             sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
             pk[i >> 1] = pack_bf16x2(e0, e1);
             pk[(i >> 1) + 1] = pack_bf16x2(e2, e3);

@@ -16,7 +16,7 @@ def timed(fn, reps=10):
     return e0.elapsed_time(e1) / reps * 1e3
 
 r = lambda *s: torch.randn(*s, device="cuda").bfloat16()
-print("PST3R_ATT =", os.environ.get("PST3R_ATT", "(default 3)"))
+print("PST3R_ATT =", os.environ.get("PST3R_ATT", "(default 3)"), "PST3R_ATT_POLY =", os.environ.get("PST3R_ATT_POLY", "(default)"))
 for name, B, H, Nq, Nk, shared in [("render cross", 16, 12, 768, 12288, True), ("encoder self", 16, 16, 768, 768, False),
                                    ("dino self", 16, 16, 769, 769, False), ("membuild cross", 1, 12, 768, 11520, True),
                                    ("membuild self", 1, 12, 768, 768, False)]:
