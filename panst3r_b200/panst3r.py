@@ -30,6 +30,26 @@ from .modules.panoptic import PanopticDecoder, PixelShuffleUpscaler
 ENC_DIM, DEC_DIM, DINO_DIM = 1024, 768, 1024
 
 
+def select_keyframes(n_views: int, num_keyframes):
+    """(keyframes, processing order = keyframes + remaining views, k) — panst3r.py:181-196 (linspace selection)."""
+    if num_keyframes is None or num_keyframes > n_views:
+        num_keyframes, keyframes = n_views, list(range(n_views))
+    else:
+        keyframes = np.linspace(0, n_views - 1, num_keyframes, dtype=int).tolist()
+    rest = sorted(set(range(n_views)).difference(set(keyframes)))
+    assert len(keyframes) + len(rest) == n_views
+    return keyframes, keyframes + rest, num_keyframes
+
+
+def stack_views(true_shapes, stored_shapes):
+    """Positions of equally shaped views grouped into stacks, in order of first appearance; positions ascend inside a
+    stack (must3r `stack_views`, panst3r.py:203-206).  A view's shape key is (true (H, W), stored tensor (Hs, Ws))."""
+    stacks = {}
+    for p, (t, s_) in enumerate(zip(true_shapes, stored_shapes)):
+        stacks.setdefault((tuple(int(v) for v in t), tuple(int(v) for v in s_)), []).append(p)
+    return list(stacks.values())
+
+
 class PanSt3R(nn.Module):
     def __init__(self, must3r_encoder: nn.Module, must3r_decoder: nn.Module, dino_encoder: nn.Module,
                  panoptic_decoder: nn.Module, retrieval=None, preserve_gpu_mem: bool = False,
@@ -150,22 +170,11 @@ class PanSt3R(nn.Module):
         if use_retrieval:
             raise NotImplementedError("retrieval keyframe selection needs asmk + a retrieval checkpoint (out of scope)")
         N = len(imgs)
-        if num_keyframes is None or num_keyframes > N:
-            num_keyframes = N
-            keyframes = list(range(N))
-        else:
-            keyframes = np.linspace(0, N - 1, num_keyframes, dtype=int).tolist()
-        not_keyframes = sorted(set(range(N)).difference(set(keyframes)))
-        assert len(keyframes) + len(not_keyframes) == N
-        order = keyframes + not_keyframes
+        keyframes, order, k = select_keyframes(N, num_keyframes)
         ts_o = (true_shape.cpu() if true_shape.is_cuda else true_shape)[order]
         ims = [imgs[i] for i in order]
-        k = num_keyframes
         # ---- stacks of equally shaped views (positions in the reordered list, ascending: keyframes first)
-        stacks = {}
-        for p, (im, t) in enumerate(zip(ims, ts_o.tolist())):
-            stacks.setdefault((tuple(t), tuple(im.shape[-2:])), []).append(p)
-        stacks = list(stacks.values())
+        stacks = stack_views(ts_o.tolist(), [im.shape[-2:] for im in ims])
         where = {p: (si, j) for si, idx in enumerate(stacks) for j, p in enumerate(idx)}
         st = []
         join = None

@@ -105,3 +105,16 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f"{f} imports the oracle"
                 assert "/root/reference" not in txt, f"{f} reads the reference checkout"
+
+
+def test_keyframe_selection_and_view_stacking():
+    """Host logic of forward_inference_multi_ar (reference panst3r.py:181-206): linspace keyframes first, then the
+    remaining views; views grouped into stacks of equal (true shape, stored shape) with ascending positions."""
+    from panst3r_b200.panst3r import select_keyframes, stack_views
+    kf, order, k = select_keyframes(6, 4)
+    assert kf == [0, 1, 3, 5] and order == [0, 1, 3, 5, 2, 4] and k == 4
+    assert select_keyframes(3, None) == ([0, 1, 2], [0, 1, 2], 3) and select_keyframes(3, 9)[2] == 3
+    ts = [(64, 96), (64, 96), (96, 64), (64, 64), (64, 64), (64, 96)]
+    stored = [(64, 96), (64, 96), (64, 96), (64, 64), (64, 64), (64, 96)]
+    assert stack_views(ts, stored) == [[0, 1, 5], [2], [3, 4]]
+    assert stack_views(ts[:2], stored[:2]) == [[0, 1]]
