@@ -32,8 +32,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
   return r;
 }
+// Remote arrive on the leader's barrier.  RELAXED on purpose: the only thing this arrive has to order is the epilogue's
+// tcgen05.ld of the accumulator against the leader's next tcgen05.mma, and that is done by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync on this side and tcgen05.fence::after_thread_sync on the waiter's.  The default
+// .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. every epilogue warp drained its 16 KB of global
+// stores per tile before it could signal (ncu: stall_membar 8.7 % of all samples of the fc1 GEMM).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
