@@ -119,3 +119,46 @@ def test_facade_paths_agree():
     # keyframe subset: order is restored, render-only frames reuse the keyframes' queries
     pms3, pan3 = m.forward_inference_multi_ar(list(imgs[0]), ts[0], classes, num_keyframes=2)
     assert len(pms3) == V and pan3["pred_masks"][1].shape == pan["pred_masks"][0, 1].shape
+
+
+def test_portrait_convention_identities():
+    """Portrait views are stored transposed (the reference's batch convention, model/dino.py:25-33, utils.py:36-49):
+    every stage must see the picture in its true orientation, dense outputs come back in the storage layout."""
+    torch.manual_seed(0)
+    m = build_panst3r("v1", 1, 1, 1)
+    m.load_state_dict(W.synth_state_dict(m, seed=3))
+    classes = ["a", "b", "c"]
+    m.panoptic_decoder.text_encoder.class_embeddings = W.synth_class_embeddings(classes)
+    g = torch.Generator().manual_seed(2)
+    stored = torch.rand(1, 2, 3, 32, 48, generator=g) * 2 - 1          # landscape storage
+    ts_p = torch.tensor([[[48, 32]] * 2])                               # true shape: portrait
+    true = stored.transpose(-1, -2).contiguous()                        # the pictures as they really are (48 x 32)
+    ts_t = torch.tensor([[[32, 48]] * 2])                               # "no transposition needed" flag for `true`
+    with torch.no_grad():
+        # encoder / DINOv2: tokens of the stored-transposed batch == tokens of the pictures embedded as they are
+        xa, pa = m.forward_must3r_encoder(stored, ts_p)
+        xb, pb = m.forward_must3r_encoder(true, ts_t)
+        assert torch.equal(pa, pb) and torch.allclose(xa, xb, atol=1e-5)
+        assert torch.allclose(m.forward_dino(stored, ts_p), m.forward_dino(true, ts_t), atol=1e-4)
+        pan, pm = m(stored, ts_p, classes)
+    assert pm.shape == (1, 2, 32, 48, 7) and pan["pred_masks"].shape == (1, 2, 200, 16, 24)  # storage layout
+    with torch.no_grad():
+        _, pm_l = m(stored, torch.tensor([[[32, 48]] * 2]), classes)
+    assert (pm - pm_l).abs().max() > 1e-3  # and it is not the landscape interpretation of the same tensor
+
+
+def test_multi_ar_facade_reduces_to_single_shape_path():
+    """The per-view mixed-shape restatement equals the stacked single-shape one when all views share a shape."""
+    torch.manual_seed(0)
+    m = build_panst3r("v1", 1, 1, 1)
+    m.load_state_dict(W.synth_state_dict(m, seed=3))
+    classes = ["a", "b", "c"]
+    m.panoptic_decoder.text_encoder.class_embeddings = W.synth_class_embeddings(classes)
+    g = torch.Generator().manual_seed(4)
+    imgs = [torch.rand(3, 32, 48, generator=g) * 2 - 1 for _ in range(4)]
+    ts = torch.tensor([[32, 48]] * 4)
+    with torch.no_grad():
+        a = m.forward_inference_multi_ar(imgs, ts, classes, num_keyframes=2)
+        b = m._forward_inference_mixed(imgs, ts, classes, 2)
+    for x, y in zip(a[0] + a[1]["pred_masks"], b[0] + b[1]["pred_masks"]):
+        assert x.shape == y.shape and torch.allclose(x, y, atol=1e-4, rtol=1e-4)
