@@ -35,6 +35,9 @@ typedef void* pst3r_stream_t; /* cudaStream_t */
 
 /* ---- library ------------------------------------------------------------------------------- */
 const char* pst3r_last_error(void);
+/* ABI version of this header: bumped whenever a struct layout or an entry-point signature changes
+ * (2: pst3r_gemm_epilogue grew the folded-LayerNorm fields; batched GEMM / LayerNorm, SM budget, post-processing). */
+#define PST3R_ABI_VERSION 2
 int pst3r_version(void);
 /* Returns 0 if the current CUDA device is sm_100 (B200); <0 otherwise. */
 int pst3r_check_device(void);

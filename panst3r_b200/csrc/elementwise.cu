@@ -368,7 +368,7 @@ static inline unsigned blocks_for(long long total, int threads) { return (unsign
 using namespace pst3r;
 
 extern "C" const char* pst3r_last_error(void) { return get_last_error(); }
-extern "C" int pst3r_version(void) { return 1; }
+extern "C" int pst3r_version(void) { return PST3R_ABI_VERSION; }
 extern "C" int pst3r_check_device(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) {

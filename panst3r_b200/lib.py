@@ -11,6 +11,9 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libpanst3r_b200.so")
 
 
+ABI_VERSION = 2  # PST3R_ABI_VERSION of include/panst3r_b200.h these ctypes declarations were written against
+
+
 class Pst3rError(RuntimeError):
     pass
 
@@ -116,6 +119,9 @@ def load(path: str | None = None) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
+    if lib.pst3r_version() != ABI_VERSION:  # a stale .so with other struct layouts would misbehave silently
+        raise Pst3rError(f"{p} has ABI version {lib.pst3r_version()}, this package expects {ABI_VERSION}: rebuild it "
+                         f"(python -m panst3r_b200.build)")
     if path is None:
         _lib = lib
     return lib
