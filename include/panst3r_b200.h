@@ -36,8 +36,21 @@ typedef void* pst3r_stream_t; /* cudaStream_t */
 /* ---- library ------------------------------------------------------------------------------- */
 const char* pst3r_last_error(void);
 /* ABI version of this header: bumped whenever a struct layout or an entry-point signature changes
- * (2: pst3r_gemm_epilogue grew the folded-LayerNorm fields; batched GEMM / LayerNorm, SM budget, post-processing). */
-#define PST3R_ABI_VERSION 2
+ * (2: pst3r_gemm_epilogue grew the folded-LayerNorm fields; batched GEMM / LayerNorm, SM budget, post-processing;
+ *  3: reference-precision "split bf16" operands (PST3R_KIND_SPLIT) through the GEMM and the row kernels, masked row
+ *     softmax, TMA-store mask-logit planes). */
+#define PST3R_ABI_VERSION 3
+
+/* Element kinds of a matrix argument.  PST3R_KIND_SPLIT is the reference-precision representation used for the
+ * panoptic head, which the reference runs in fp32 (src/panst3r/panst3r.py:236-245): a value x is held as TWO bf16
+ * numbers hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits, relative error 2^-17).  A split row stores its hi parts
+ * followed, `lo_off` elements later, by its lo parts; unless an entry point says otherwise lo_off == the number of
+ * logical columns, i.e. a row is [hi(0..C) | lo(0..C)] and its stride is >= 2*C bf16 elements. */
+enum {
+  PST3R_KIND_BF16 = 0,
+  PST3R_KIND_F32 = 1,
+  PST3R_KIND_SPLIT = 2
+};
 int pst3r_version(void);
 /* Returns 0 if the current CUDA device is sm_100 (B200); <0 otherwise. */
 int pst3r_check_device(void);
@@ -67,11 +80,11 @@ enum {
 typedef struct pst3r_gemm_epilogue {
   void* out;              /* bf16 or fp32 device pointer */
   int64_t ldo;            /* row stride of out in elements (PLAIN / PIXSHUF2) */
-  int32_t out_f32;        /* 0: bf16 output, 1: fp32 output */
+  int32_t out_kind;       /* PST3R_KIND_*: bf16, fp32 or split bf16 (hi at column c, lo at column c + out_lo_off) */
   int32_t act;            /* PST3R_ACT_* (applied after bias) */
   const float* bias;      /* [N] fp32 or NULL */
   const float* col_scale; /* [N] fp32 or NULL (LayerScale; applied after act) */
-  const void* residual;   /* bf16 [M, ldr] or NULL (added last) */
+  const void* residual;   /* [M, ldr] of res_kind (bf16 unless set) or NULL (added last) */
   int64_t ldr;
   int32_t res_mod_rows;   /* > 0: residual row = row % res_mod_rows (broadcast, e.g. position embeddings) */
   float alpha;            /* accumulator scale (applied first) */
@@ -99,6 +112,17 @@ typedef struct pst3r_gemm_epilogue {
   float ln_eps;
   /* Producer side: float2 [M][N/32] partial sums of the bf16 values this GEMM stores (PLAIN bf16 store, N % 32 == 0). */
   void* stats_out;
+  /* Reference-precision mode (fp32 policy of the panoptic head, panst3r.py:236-245, on bf16 tensor cores):
+   *   split_terms = 0: A, B plain bf16.
+   *   split_terms = 3: A and B are PST3R_KIND_SPLIT; acc = A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T (fp32 in TMEM).
+   *   split_terms = 2: A plain bf16 (exactly representable inputs, e.g. the bf16 trunk features), B split.
+   * a_lo_off / b_lo_off: element distance between the hi and the lo part inside a row of A / B (multiples of 8);
+   * the part is a dimension of the TMA tensor maps.  K stays the logical reduction length. */
+  int32_t split_terms;
+  int64_t a_lo_off, b_lo_off;
+  int64_t out_lo_off;     /* out_kind == PST3R_KIND_SPLIT */
+  int32_t res_kind;       /* PST3R_KIND_* of residual */
+  int64_t res_lo_off;
 } pst3r_gemm_epilogue;
 
 int pst3r_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
@@ -146,15 +170,16 @@ int32_t pst3r_attention_auto_splits(int32_t B, int32_t H, int32_t Nq, int32_t Nk
 int pst3r_attention(const pst3r_attn_args* args, pst3r_stream_t stream);
 
 /* ---- Normalisation / elementwise ------------------------------------------------------------- */
-/* y = LN(x [+ add]) * gamma + beta ; x bf16 or fp32 [rows, dim] (row stride ldx), y bf16 or fp32.
- * If sum_out != NULL the pre-norm sum (x + add) is also written (bf16, row stride ld_sum): fused
+/* y = LN(x [+ add]) * gamma + beta ; x, add, y, sum_out of any PST3R_KIND_* (row strides in elements of the stored
+ * type; split rows are [hi(dim) | lo(dim)]).
+ * If sum_out != NULL the pre-norm sum (x + add) is also written (row stride ld_sum): fused
  * "residual add + post-norm" of the Mask2Former-style query decoder (mask_transformer.py:339-340).
  * If x_rows_per_batch > 0, input row r lives at x + (r / rpb)*x_batch_stride + (r % rpb)*ldx (used to drop the
  * DINOv2 CLS token while normalising, model/dino.py:69). */
-int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const void* add, int64_t ld_add, const float* gamma,
-                    const float* beta, float eps, void* y, int32_t y_f32, int64_t ldy, void* sum_out,
-                    int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rows_per_batch, int64_t x_batch_stride,
-                    pst3r_stream_t stream);
+int pst3r_layernorm(const void* x, int32_t x_kind, int64_t ldx, const void* add, int32_t add_kind, int64_t ld_add,
+                    const float* gamma, const float* beta, float eps, void* y, int32_t y_kind, int64_t ldy, void* sum_out,
+                    int32_t sum_kind, int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rows_per_batch,
+                    int64_t x_batch_stride, pst3r_stream_t stream);
 
 /* Batched LayerNorm over `batches` equally shaped bf16 matrices with per-batch parameters:
  *   y[b][r] = LN(x[b][r] + add[r]) * gamma[b] + beta[b],   x[b] = x + b*x_batch_stride, y[b] = y + b*y_batch_stride,
@@ -171,15 +196,25 @@ int pst3r_layernorm_batched(const void* x, int64_t ldx, int64_t x_batch_stride, 
 int pst3r_rope2d(void* tokens, int64_t s_b, int64_t s_n, int64_t s_h, const int32_t* pos, int32_t B, int32_t N,
                  int32_t H, int32_t D, float base, float fwd, pst3r_stream_t stream);
 
-/* out[r, c] = a[r, c] + b[r % b_rows, c]  (bf16; pos-embedding / level-embedding adds) */
-int pst3r_add_bcast(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_rows, void* out, int64_t ldo,
-                    int32_t rows, int32_t cols, pst3r_stream_t stream);
+/* out[r, c] = a[r, c] + b[r % b_rows, c]  (any PST3R_KIND_*; pos-embedding / level-embedding / query-embedding adds) */
+int pst3r_add_bcast(const void* a, int32_t a_kind, int64_t lda, const void* b, int32_t b_kind, int64_t ldb, int32_t b_rows,
+                    void* out, int32_t out_kind, int64_t ldo, int32_t rows, int32_t cols, pst3r_stream_t stream);
 
 /* fp32 [rows, cols] (ld) -> bf16, and back */
 int pst3r_cast_f32_to_bf16(const float* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols,
                            pst3r_stream_t stream);
 int pst3r_cast_bf16_to_f32(const void* x, int64_t ldx, float* y, int64_t ldy, int32_t rows, int32_t cols,
                            pst3r_stream_t stream);
+/* y = x between any two PST3R_KIND_* (e.g. fp32 -> split bf16 when fp32 features enter the reference-precision head) */
+int pst3r_convert(const void* x, int32_t x_kind, int64_t ldx, void* y, int32_t y_kind, int64_t ldy, int32_t rows,
+                  int32_t cols, pst3r_stream_t stream);
+
+/* Masked row softmax of the reference-precision attention (the query decoder's nn.MultiheadAttention,
+ * mask_transformer.py:314,372,395-398, evaluated as S = QK^T GEMM -> this -> PV GEMM on split operands):
+ * out[r][k] = softmax over the unblocked keys of S[r][0..Nk) (fp32, scale already applied); mask_bits as in
+ * pst3r_attention, row q = r % Q (shared by all heads), NULL = no mask.  out of kind out_kind, row stride ldo. */
+int pst3r_softmax_rows(const float* S, int64_t lds, int32_t rows, int32_t Nk, const uint32_t* mask_bits, int64_t mask_sq,
+                       int32_t Q, void* out, int32_t out_kind, int64_t ldo, pst3r_stream_t stream);
 
 /* Patchify (im2col) for the ViT patch embeddings: img fp32 [B,3,H,W] -> bf16 [B*(H/P)*(W/P), ldo] with
  * column = c*P*P + i*P + j (Conv2d weight flattening).  Columns [3*P*P, ldo) are zero-filled. */
@@ -192,9 +227,10 @@ int pst3r_dino_preprocess_patchify(const float* img, int32_t B, int32_t H, int32
                                    int32_t P, void* out, int64_t ldo, pst3r_stream_t stream);
 
 /* Mean of the centre 2x2 of every 8x8 cell of a pixel-major feature map: feats bf16 [B, Hm, Wm, C] ->
- * bf16 [B, Hm/8, Wm/8, C].  The 8x bilinear downsample (align_corners=False) of the mask logits
+ * bf16 [B, Hm/8, Wm/8, C] (kind: PST3R_KIND_BF16, or PST3R_KIND_SPLIT with [hi(C) | lo(C)] pixel rows in and out).
+ * The 8x bilinear downsample (align_corners=False) of the mask logits
  * (mask_transformer.py:286) is linear in the features, so the attention mask only needs these. */
-int pst3r_center_pool8(const void* feats, int32_t B, int32_t Hm, int32_t Wm, int32_t C, void* out,
+int pst3r_center_pool8(const void* feats, int32_t kind, int32_t B, int32_t Hm, int32_t Wm, int32_t C, void* out,
                        pst3r_stream_t stream);
 
 /* logits_t fp32 [Q, ld] (TRANSPOSED store: row q, column = flattened key token) -> mask bits
@@ -203,12 +239,12 @@ int pst3r_center_pool8(const void* feats, int32_t B, int32_t Hm, int32_t Wm, int
 int pst3r_attn_mask_bits(const float* logits_t, int64_t ld, int32_t Q, int32_t Nk, uint32_t* bits,
                          pst3r_stream_t stream);
 
-/* L2-normalise rows: y = x / (||x|| + eps)  (fp32 in, bf16 or fp32 out; mask_transformer.py:227) */
-int pst3r_l2norm_rows(const float* x, int64_t ldx, void* y, int32_t y_f32, int64_t ldy, int32_t rows, int32_t cols,
+/* L2-normalise rows: y = x / (||x|| + eps)  (fp32 in, y of any PST3R_KIND_*; mask_transformer.py:227) */
+int pst3r_l2norm_rows(const float* x, int64_t ldx, void* y, int32_t y_kind, int64_t ldy, int32_t rows, int32_t cols,
                       float eps, pst3r_stream_t stream);
 
-/* bf16 pixel-major [B, HW, C] -> fp32 channel-major [B, C, HW] (reference NCHW layout of mask_feats / fpn) */
-int pst3r_nhwc_to_nchw_f32(const void* x, int32_t B, int32_t HW, int32_t C, float* y, pst3r_stream_t stream);
+/* bf16 / split-bf16 pixel-major [B, HW, C] -> fp32 channel-major [B, C, HW] (reference NCHW layout of mask_feats / fpn) */
+int pst3r_nhwc_to_nchw_f32(const void* x, int32_t x_kind, int32_t B, int32_t HW, int32_t C, float* y, pst3r_stream_t stream);
 
 /* ---- Panoptic post-processing front half (engine/postprocess.py:18-27, 38-45, 63-120) ------------------
  * scores[q] = max_k sigmoid(logits[q][k]), labels[q] = first arg max (postprocess.py:39). */

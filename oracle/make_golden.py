@@ -32,7 +32,15 @@ def head_inputs(V, H, Wd, seed, portrait=False):
     return feats, imgs, pos, ts
 
 
-def build_ref_head(ref, variant):
+def build_ref_head(ref, variant, cls_logit_scale=None):
+    m = _build_ref_head(ref, variant)
+    if cls_logit_scale is not None:  # conditioned fixture: class logits O(1) instead of O(0.05) with random weights
+        with torch.no_grad():
+            m.mask_transformer.cls_logit_scale.fill_(cls_logit_scale)
+    return m
+
+
+def _build_ref_head(ref, variant):
     if variant == "v1":
         m = ref.PanopticDecoder(upscaler=ref.PixelShuffleUpscaler(input_dim=2816), text_encoder="siglip", fixed_vocab=True)
     else:
@@ -65,11 +73,16 @@ def main():
         blob = {
             "variant": variant, "V": V, "H": H, "W": Wd, "portrait": portrait, "classes": CLASSES, "weight_seed": 1,
             "input_seed": 5,
-            "pred_logits": out["pred_logits"], "pred_masks": out["pred_masks"].half(), "out_queries": out["out_queries"],
-            "aux0_masks": out["aux_outputs"][0]["pred_masks"].half(), "aux0_logits": out["aux_outputs"][0]["pred_logits"],
+            # fp32 throughout: the reference-precision head is checked at 1e-3 of the tensor maximum (north star)
+            "pred_logits": out["pred_logits"], "pred_masks": out["pred_masks"], "out_queries": out["out_queries"],
+            "aux0_masks": out["aux_outputs"][0]["pred_masks"], "aux0_logits": out["aux_outputs"][0]["pred_logits"],
+            "aux_logits": [a["pred_logits"] for a in out["aux_outputs"]],
+            "aux_masks_absmax": [float(a["pred_masks"].abs().max()) for a in out["aux_outputs"]],
             "memq_masks_equal_full": bool(torch.equal(mq["pred_masks"], out["pred_masks"])),
-            "fpn0": fpn[0].half(), "mask_feats": mask_f.half(),
+            "fpn0": fpn[0], "mask_feats": mask_f,
         }
+        if V > 2:  # keep the larger fixture small: upscaler outputs are pinned by the V = 2 cases
+            blob["fpn0"], blob["mask_feats"], blob["aux0_masks"] = fpn[0].half(), mask_f.half(), blob["aux0_masks"].half()
         name = f"head_{variant}_V{V}_{H}x{Wd}{'_portrait' if portrait else ''}.pt"
         torch.save(blob, os.path.join(GOLDEN, name))
         print("wrote", name, {k: tuple(v.shape) for k, v in blob.items() if torch.is_tensor(v)})
@@ -83,8 +96,37 @@ def main():
         up = torch.nn.functional.interpolate(masks, size=(32, 48), mode="bilinear", align_corners=False)
         ids = (scores[None, :, None, None] * up).argmax(1)
         top2 = (scores[None, :, None, None] * up).topk(2, dim=1).values
-    torch.save({"ids": ids.to(torch.int16), "margin": (top2[:, 0] - top2[:, 1]).half()}, os.path.join(GOLDEN, "argmax_v1_V2_32x48.pt"))
+    torch.save({"ids": ids.to(torch.int16), "margin": (top2[:, 0] - top2[:, 1])}, os.path.join(GOLDEN, "argmax_v1_V2_32x48.pt"))
     print("wrote argmax_v1_V2_32x48.pt")
+    make_conditioned_golden(ref)
+
+
+COND = dict(variant="v1", V=3, H=64, W=96, input_seed=21, cls_logit_scale=3.0)
+
+
+def make_conditioned_golden(ref=None):
+    """Well-conditioned fixture for the FREE-RUNNING query decoder: class logits scaled to O(1)
+    (cls_logit_scale = 3 -> exp = 20), fp32 outputs of the REFERENCE head, the post-processing front half's
+    score-weighted argmax ids (engine/postprocess.py:18-27, 63, 77) and their top-2 margins."""
+    ref = ref or ref_import.load_reference()
+    c = COND
+    m = build_ref_head(ref, c["variant"], cls_logit_scale=c["cls_logit_scale"])
+    feats, imgs, pos, ts = head_inputs(c["V"], c["H"], c["W"], seed=c["input_seed"])
+    with torch.no_grad():
+        out = m(feats, imgs, pos, ts, CLASSES)
+        scores = out["pred_logits"].sigmoid().max(-1).values[0]
+        up = torch.nn.functional.interpolate(out["pred_masks"][0].sigmoid(), size=(c["H"], c["W"]), mode="bilinear", align_corners=False)
+        weighted = scores[None, :, None, None] * up
+        top2 = weighted.topk(2, dim=1).values
+    blob = dict(c)
+    blob.update({"classes": CLASSES, "weight_seed": 1, "pred_logits": out["pred_logits"], "pred_masks": out["pred_masks"],
+                 "out_queries": out["out_queries"],
+                 "aux_logits": [a["pred_logits"] for a in out["aux_outputs"]],
+                 "ids": weighted.argmax(1).to(torch.int16), "margin": top2[:, 0] - top2[:, 1]})
+    torch.save(blob, os.path.join(GOLDEN, "head_v1_conditioned.pt"))
+    mg = blob["margin"]
+    print("wrote head_v1_conditioned.pt: |mask logit| max %.2f, |class logit| max %.2f, margin > 1e-4 on %.3f of the pixels"
+          % (out["pred_masks"].abs().max(), out["pred_logits"].abs().max(), (mg > 1e-4).float().mean()))
 
 
 def make_postprocess_golden(ref=None):
@@ -129,8 +171,8 @@ def make_multi_ar_golden(ref=None):
         out = m(*args, CLASSES, multi_ar=True, outdevice="cpu")
         mq = m(*args, CLASSES, multi_ar=True, outdevice="cpu", memory_queries=out["out_queries"])
     blob = {"stacks": MULTI_AR_STACKS, "classes": CLASSES, "weight_seed": 1, "pred_logits": out["pred_logits"],
-            "pred_masks": [t.half() for t in out["pred_masks"]], "out_queries": out["out_queries"],
-            "aux0_masks": [t.half() for t in out["aux_outputs"][0]["pred_masks"]], "aux0_logits": out["aux_outputs"][0]["pred_logits"],
+            "pred_masks": [t for t in out["pred_masks"]], "out_queries": out["out_queries"],
+            "aux0_masks": [t for t in out["aux_outputs"][0]["pred_masks"]], "aux0_logits": out["aux_outputs"][0]["pred_logits"],
             "memq_masks_equal_full": all(torch.equal(a, b) for a, b in zip(mq["pred_masks"], out["pred_masks"]))}
     torch.save(blob, os.path.join(GOLDEN, "head_v1_multi_ar.pt"))
     print("wrote head_v1_multi_ar.pt", [tuple(t.shape) for t in blob["pred_masks"]], blob["memq_masks_equal_full"])
@@ -140,6 +182,8 @@ if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "postprocess":
         make_postprocess_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "conditioned":
+        make_conditioned_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "multi_ar":
         make_multi_ar_golden()
     else:

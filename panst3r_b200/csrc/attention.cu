@@ -378,11 +378,7 @@ __global__ void attention_combine_kernel(const float* __restrict__ ws_o, const f
 }
 
 }  // namespace pst3r
-#include "attention2.cuh"
 #include "attention3.cuh"
-#ifndef PST3R_ATT_POLY_DEFAULT
-#define PST3R_ATT_POLY_DEFAULT 0
-#endif
 namespace pst3r {
 
 static int make_qkv_map(CUtensorMap* m, const void* ptr, int hd, long long n, int H, int B, long long sn,
@@ -419,28 +415,14 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
   }
   dim3 grid((a->Nq + ATT_BM - 1) / ATT_BM, a->B * a->H, splits);
   if (HD == 64 && !a->mask_bits) {
-    // second-generation kernel: 256 queries per CTA
-    // third-generation kernel (P in tensor memory) unless PST3R_ATT=2 selects the smem-P one
-    static int gen = 0, poly = 0;
-    if (gen == 0) {
-      const char* e = getenv("PST3R_ATT");
-      gen = (e && e[0] == '2') ? 2 : 3;
-      const char* ep = getenv("PST3R_ATT_POLY");  // share of the exponentials computed off the MUFU: 0, 4 (1 in 4), 2 (1 in 2)
-      poly = ep ? atoi(ep) : PST3R_ATT_POLY_DEFAULT;
-      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_DYN_BYTES));
-      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention3_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_DYN_BYTES));
-      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention3_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_DYN_BYTES));
-      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention3_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_DYN_BYTES));
+    // 256 queries per CTA, probabilities in tensor memory (attention3.cuh)
+    static bool cfg3 = false;
+    if (!cfg3) {
+      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_DYN_BYTES));
+      cfg3 = true;
     }
     dim3 grid2((a->Nq + 255) / 256, a->B * a->H, splits);
-    if (gen == 3 && poly == 4)
-      PST3R_CHECK_CUDA(launch_pdl(attention3_fwd_kernel<4>, grid2, dim3(AT3_THREADS), AT3_DYN_BYTES, stream, tmQ, tmK, tmV, p));
-    else if (gen == 3 && poly == 2)
-      PST3R_CHECK_CUDA(launch_pdl(attention3_fwd_kernel<2>, grid2, dim3(AT3_THREADS), AT3_DYN_BYTES, stream, tmQ, tmK, tmV, p));
-    else if (gen == 3)
-      PST3R_CHECK_CUDA(launch_pdl(attention3_fwd_kernel<0>, grid2, dim3(AT3_THREADS), AT3_DYN_BYTES, stream, tmQ, tmK, tmV, p));
-    else
-      PST3R_CHECK_CUDA(launch_pdl(attention2_fwd_kernel, grid2, dim3(AT2_THREADS), AT2_DYN_BYTES, stream, tmQ, tmK, tmV, p));
+    PST3R_CHECK_CUDA(launch_pdl(attention3_fwd_kernel, grid2, dim3(AT3_THREADS), AT3_DYN_BYTES, stream, tmQ, tmK, tmV, p));
   } else if (a->mask_bits) {
     auto kern = attention_fwd_kernel<HD, true>;
     static bool cfg = false;

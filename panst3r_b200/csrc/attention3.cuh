@@ -1,18 +1,17 @@
-// Third-generation tcgen05 flash attention for head_dim 64 without a block mask: attention2's 256-query ping-pong
-// with the probabilities kept in TENSOR MEMORY instead of shared memory.
+// tcgen05 flash attention for head_dim 64 without a block mask: 256 queries per CTA as two 128-row sub-tiles that
+// ping-pong on the tensor core, with the probabilities kept in TENSOR MEMORY instead of shared memory.
 //
 //   S_t = Q_t K_j^T       SS MMA (Q, K from swizzled smem)       -> TMEM columns [t*128, t*128+128)   fp32
 //   P_t = 2^((S_t - m) c) softmax warps: tcgen05.ld -> ex2 -> bf16x2 -> tcgen05.st -> TMEM [384 + t*64, +64)
 //   O_t = P_t V_j         TS MMA (A = P from TMEM, B = V from smem, MN-major) -> TMEM [256 + t*64, +64)
 //
-// attention2 wrote P into a swizzled smem tile and appended a ones column to V for the row sums: per 128x128
-// sub-tile step the tensor core then fetched 84 KB of operands from shared memory and the softmax warps stored
-// another 32 KB into it, and its own timeline (profiles/r01_attention_analysis.md) shows the MMA issue stream
+// The previous generation (round 1, removed) wrote P into a swizzled smem tile and appended a ones column to V for the
+// row sums: per 128x128 sub-tile step the tensor core then fetched 84 KB of operands from shared memory and the softmax
+// warps stored another 32 KB into it, and its timeline (profiles/r01_attention_analysis.md) shows the MMA issue stream
 // waiting on exactly that port (P V alone needs 162 B/clk against the 128 B/clk an SM can read).  With P in TMEM
 // the P V product reads only V (16 KB per step), the softmax warps issue 4 tcgen05.st instead of 16 st.shared,
-// and the freed 80 KB of smem deepen the K/V ring to 4 stages.  Row sums are accumulated by the softmax threads
-// (fp32, 4 independent partial sums) since the ones column would need 16 more TMEM columns than remain.
-// Same CTA shape, barriers and split-KV protocol as attention2 (384 threads: TMA warp, MMA warp, 2 idle, 4 + 4 softmax).
+// and the freed 80 KB of smem deepen the K/V ring to 4 stages.  Row sums are accumulated by the softmax threads (fp32).
+// CTA: 384 threads = TMA warp, MMA warp, 2 idle warps, 4 + 4 softmax warps (one per TMEM lane quadrant and sub-tile).
 #pragma once
 
 namespace pst3r {
@@ -30,21 +29,6 @@ constexpr uint32_t AT3_TMEM_S = 0;     // S_A at 0, S_B at 128 (fp32)
 constexpr uint32_t AT3_TMEM_O = 256;   // O_A at 256, O_B at 320 (fp32)
 constexpr uint32_t AT3_TMEM_P = 384;   // P_A at 384, P_B at 448 (bf16 pairs: column c of row r = keys 2c, 2c+1)
 
-// 2^x on the FMA / ALU pipes (FA4-style): round-to-nearest split x = xi + xf by the 1.5 * 2^23 trick, degree-3 minimax
-// polynomial of 2^xf on [-0.5, 0.5] (relative error 1.0e-4, far below the bf16 rounding of P), exponent add.
-// Used for one element in POLY so that the MUFU pipe (16 ex2/clk/SM, the busiest unit of this kernel: ncu XU 59 %)
-// sheds that share of its load.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float t = x + 12582912.0f;
-  const float xf = x - (t - 12582912.0f);
-  float p = fmaf(0.05583828f, xf, 0.24263948f);
-  p = fmaf(p, xf, 0.69313675f);
-  p = fmaf(p, xf, 0.99992454f);
-  return __int_as_float(__float_as_int(p) + ((__float_as_int(t) - 0x4B400000) << 23));
-}
-
-template <int POLY>  // 0: every exponential on the MUFU; n > 0: one element in n through ex2_poly
 __global__ void __launch_bounds__(AT3_THREADS, 1)
 attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -247,9 +231,9 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])), c2, nm2);
             const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3])), c2, nm2);
             const float e0 = ex2_approx(x01.x);
-            const float e1 = (POLY == 2) ? ex2_poly(x01.y) : ex2_approx(x01.y);
+            const float e1 = ex2_approx(x01.y);
             const float e2 = ex2_approx(x23.x);
-            const float e3 = (POLY == 2 || POLY == 4) ? ex2_poly(x23.y) : ex2_approx(x23.y);
+            const float e3 = ex2_approx(x23.y);
             sA = __fadd2_rn(sA, make_float2(e0, e1));
             sB = __fadd2_rn(sB, make_float2(e2, e3));
             pk[i >> 1] = pack_bf16x2(e0, e1);

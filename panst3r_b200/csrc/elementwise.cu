@@ -11,17 +11,32 @@ namespace pst3r {
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, three cached passes (mean, centred variance, normalise).
 // ------------------------------------------------------------------------------------------------
-template <bool X_F32>
-__device__ __forceinline__ float ln_load(const void* x, long long idx) {
-  if (X_F32) return reinterpret_cast<const float*>(x)[idx];
-  return __bfloat162float(reinterpret_cast<const bf16*>(x)[idx]);
+// Kind-aware element access (PST3R_KIND_*): bf16, fp32, or split bf16 (value = hi + lo, lo stored lo_off elements
+// after hi).  The reference-precision head (fp32 policy, panst3r.py:236-245) keeps its activations split.
+__device__ __forceinline__ float kload(const void* p, int kind, long long idx, long long lo_off) {
+  if (kind == PST3R_KIND_F32) return reinterpret_cast<const float*>(p)[idx];
+  const bf16* b = reinterpret_cast<const bf16*>(p);
+  float v = __bfloat162float(b[idx]);
+  if (kind == PST3R_KIND_SPLIT) v += __bfloat162float(b[idx + lo_off]);
+  return v;
+}
+__device__ __forceinline__ void kstore(void* p, int kind, long long idx, long long lo_off, float v) {
+  if (kind == PST3R_KIND_F32) {
+    reinterpret_cast<float*>(p)[idx] = v;
+    return;
+  }
+  bf16* b = reinterpret_cast<bf16*>(p);
+  const bf16 h = __float2bfloat16(v);
+  b[idx] = h;
+  if (kind == PST3R_KIND_SPLIT) b[idx + lo_off] = __float2bfloat16(v - __bfloat162float(h));
 }
 
-template <bool X_F32, bool Y_F32>
-__global__ void layernorm_kernel(const void* __restrict__ x, long long ldx, const bf16* __restrict__ add,
-                                 long long ld_add, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 float eps, void* __restrict__ y, long long ldy, bf16* __restrict__ sum_out,
-                                 long long ld_sum, int rows, int dim, int x_rpb, long long x_bs) {
+// Generic LayerNorm: one warp per row, three passes, any kinds (split rows are [hi(dim) | lo(dim)]).
+__global__ void layernorm_kernel(const void* __restrict__ x, int x_kind, long long ldx, const void* __restrict__ add,
+                                 int add_kind, long long ld_add, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, void* __restrict__ y, int y_kind, long long ldy,
+                                 void* __restrict__ sum_out, int sum_kind, long long ld_sum, int rows, int dim, int x_rpb,
+                                 long long x_bs) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -29,28 +44,24 @@ __global__ void layernorm_kernel(const void* __restrict__ x, long long ldx, cons
   const long long ao = (long long)row * ld_add;
   float s = 0.0f;
   for (int i = lane; i < dim; i += 32) {
-    float v = ln_load<X_F32>(x, xo + i);
-    if (add) v += __bfloat162float(add[ao + i]);
+    float v = kload(x, x_kind, xo + i, dim);
+    if (add) v += kload(add, add_kind, ao + i, dim);
     s += v;
   }
   const float mean = warp_sum(s) / dim;
   float ss = 0.0f;
   for (int i = lane; i < dim; i += 32) {
-    float v = ln_load<X_F32>(x, xo + i);
-    if (add) v += __bfloat162float(add[ao + i]);
+    float v = kload(x, x_kind, xo + i, dim);
+    if (add) v += kload(add, add_kind, ao + i, dim);
     const float d = v - mean;
     ss += d * d;
   }
   const float rstd = rsqrtf(warp_sum(ss) / dim + eps);
   for (int i = lane; i < dim; i += 32) {
-    float v = ln_load<X_F32>(x, xo + i);
-    if (add) v += __bfloat162float(add[ao + i]);
-    if (sum_out) sum_out[(long long)row * ld_sum + i] = __float2bfloat16(v);
-    const float o = (v - mean) * rstd * gamma[i] + beta[i];
-    if (Y_F32)
-      reinterpret_cast<float*>(y)[(long long)row * ldy + i] = o;
-    else
-      reinterpret_cast<bf16*>(y)[(long long)row * ldy + i] = __float2bfloat16(o);
+    float v = kload(x, x_kind, xo + i, dim);
+    if (add) v += kload(add, add_kind, ao + i, dim);
+    if (sum_out) kstore(sum_out, sum_kind, (long long)row * ld_sum + i, dim, v);
+    kstore(y, y_kind, (long long)row * ldy + i, dim, (v - mean) * rstd * gamma[i] + beta[i]);
   }
 }
 
@@ -190,6 +201,68 @@ __global__ void add_bcast_kernel(const bf16* __restrict__ a, long long lda, cons
   const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + (long long)(r % b_rows) * ldb + c));
   *reinterpret_cast<__nv_bfloat162*>(out + (long long)r * ldo + c) = __floats2bfloat162_rn(x.x + y.x, x.y + y.y);
 }
+__global__ void add_bcast_k_kernel(const void* __restrict__ a, int a_kind, long long lda, const void* __restrict__ b,
+                                   int b_kind, long long ldb, int b_rows, void* __restrict__ out, int out_kind,
+                                   long long ldo, int rows, int cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cols) return;
+  const int c = idx % cols;
+  const int r = idx / cols;
+  const float v = kload(a, a_kind, (long long)r * lda + c, cols) + kload(b, b_kind, (long long)(r % b_rows) * ldb + c, cols);
+  kstore(out, out_kind, (long long)r * ldo + c, cols, v);
+}
+__global__ void convert_kernel(const void* __restrict__ x, int x_kind, long long ldx, void* __restrict__ y, int y_kind,
+                               long long ldy, int rows, int cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cols) return;
+  const int c = idx % cols;
+  const int r = idx / cols;
+  kstore(y, y_kind, (long long)r * ldy + c, cols, kload(x, x_kind, (long long)r * ldx + c, cols));
+}
+
+// Masked row softmax of the reference-precision (unfused) attention: P[r][k] = softmax_k(S[r][k]) over the keys the
+// bit mask leaves open (bit k&31 of word [q][k>>5] set => blocked; q = r % Q: the mask is shared by all heads,
+// mask_transformer.py:272).  S fp32 [rows][>=Nk] already carries the 1/sqrt(hd) scale.  One block per row; S stays in L2.
+__global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, int Nk, const uint32_t* __restrict__ bits,
+                                    long long mask_sq, int Q, void* __restrict__ out, int out_kind, long long ldo) {
+  const int r = blockIdx.x;
+  const float* srow = S + (long long)r * lds;
+  const uint32_t* mrow = bits ? bits + (long long)(r % Q) * mask_sq : nullptr;
+  __shared__ float red[33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  auto blocked = [&](int k) { return mrow && ((mrow[k >> 5] >> (k & 31)) & 1u); };
+  float mx = -INFINITY;
+  for (int k = threadIdx.x; k < Nk; k += blockDim.x)
+    if (!blocked(k)) mx = fmaxf(mx, srow[k]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nwarps ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  mx = red[32];
+  __syncthreads();
+  float sum = 0.0f;
+  for (int k = threadIdx.x; k < Nk; k += blockDim.x)
+    if (!blocked(k)) sum += expf(srow[k] - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nwarps ? red[lane] : 0.0f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  const float inv = red[32] > 0.0f ? 1.0f / red[32] : 0.0f;
+  for (int k = threadIdx.x; k < Nk; k += blockDim.x) {
+    const float pv = blocked(k) ? 0.0f : expf(srow[k] - mx) * inv;
+    kstore(out, out_kind, (long long)r * ldo + k, Nk, pv);
+  }
+}
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
                                      int rows, int cols) {
@@ -295,6 +368,28 @@ __global__ void center_pool8_kernel(const bf16* __restrict__ f, int B, int Hm, i
   *reinterpret_cast<__nv_bfloat162*>(out + (((long long)b * gh + Y) * gw + X) * C + c) =
       __floats2bfloat162_rn(acc.x * 0.25f, acc.y * 0.25f);
 }
+// split-bf16 map: pixel rows are [hi(C) | lo(C)], in and out
+__global__ void center_pool8_split_kernel(const bf16* __restrict__ f, int B, int Hm, int Wm, int C, bf16* __restrict__ out) {
+  const int gh = Hm / 8, gw = Wm / 8;
+  const long long total = (long long)B * gh * gw * C;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % C;
+  long long t = idx / C;
+  const int X = t % gw; t /= gw;
+  const int Y = t % gh;
+  const int b = t / gh;
+  const bf16* base = f + (long long)b * Hm * Wm * 2 * C;
+  float acc = 0.0f;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const long long pix = (long long)(8 * Y + 3 + dy) * Wm + (8 * X + 3 + dx);
+      acc += kload(base, PST3R_KIND_SPLIT, pix * 2 * C + c, C);
+    }
+  kstore(out, PST3R_KIND_SPLIT, (((long long)b * gh + Y) * gw + X) * 2 * C + c, C, acc * 0.25f);
+}
 
 // ------------------------------------------------------------------------------------------------
 // mask bits: one block per query row
@@ -335,24 +430,21 @@ __global__ void l2norm_rows_kernel(const float* __restrict__ x, long long ldx, v
   }
   const float inv = 1.0f / (sqrtf(warp_sum(ss)) + eps);
   for (int i = lane; i < cols; i += 32) {
-    const float v = x[(long long)row * ldx + i] * inv;
-    if (y_f32)
-      reinterpret_cast<float*>(y)[(long long)row * ldy + i] = v;
-    else
-      reinterpret_cast<bf16*>(y)[(long long)row * ldy + i] = __float2bfloat16(v);
+    kstore(y, y_f32, (long long)row * ldy + i, cols, x[(long long)row * ldx + i] * inv);  // y_f32 is a PST3R_KIND_*
   }
 }
 
 // bf16 [B, HW, C] -> fp32 [B, C, HW]
-__global__ void nhwc_to_nchw_f32_kernel(const bf16* __restrict__ x, int HW, int C, float* __restrict__ y) {
+__global__ void nhwc_to_nchw_f32_kernel(const bf16* __restrict__ x, int x_kind, int HW, int C, float* __restrict__ y) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const bf16* xb = x + (long long)b * HW * C;
+  const long long ldx = x_kind == PST3R_KIND_SPLIT ? 2 * C : C;
+  const bf16* xb = x + (long long)b * HW * ldx;
   float* yb = y + (long long)b * HW * C;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int p = p0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (p < HW && c < C) ? __bfloat162float(xb[(long long)p * C + c]) : 0.0f;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? kload(xb, x_kind, (long long)p * ldx + c, C) : 0.0f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -387,18 +479,23 @@ extern "C" int pst3r_check_device(void) {
   return PST3R_OK;
 }
 
-static int layernorm_run(const void* x, int32_t x_f32, int64_t ldx, const void* add, int64_t ld_add,
-                         const float* gamma, const float* beta, float eps, void* y, int32_t y_f32, int64_t ldy,
-                         void* sum_out, int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rpb, int64_t x_bs,
-                         int64_t y_bs, int64_t p_bs, int32_t add_mod, pst3r_stream_t s_) {
+static int layernorm_run(const void* x, int32_t x_kind, int64_t ldx, const void* add, int32_t add_kind, int64_t ld_add,
+                         const float* gamma, const float* beta, float eps, void* y, int32_t y_kind, int64_t ldy,
+                         void* sum_out, int32_t sum_kind, int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rpb,
+                         int64_t x_bs, int64_t y_bs, int64_t p_bs, int32_t add_mod, pst3r_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
   PST3R_CHECK_ARG(x && gamma && beta && y && rows > 0 && dim > 0, "layernorm: bad args");
+  auto kind_ok = [](int k) { return k >= 0 && k <= 2; };
+  PST3R_CHECK_ARG(kind_ok(x_kind) && kind_ok(y_kind) && kind_ok(add_kind) && kind_ok(sum_kind), "layernorm: bad element kind");
   const int wpb = 8;
   const unsigned grid = blocks_for(rows, wpb);
   const bf16* a = reinterpret_cast<const bf16*>(add);
   bf16* so = reinterpret_cast<bf16*>(sum_out);
+  const int y_f32 = y_kind == PST3R_KIND_F32;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const bool vec_ok = !x_f32 && (dim % 8) == 0 && dim <= 12 * 256 && (ldx % 8) == 0 && (x_bs % 8) == 0 && al16(x) &&
+  const bool vec_ok = x_kind == PST3R_KIND_BF16 && y_kind != PST3R_KIND_SPLIT && (!add || add_kind == PST3R_KIND_BF16) &&
+                      (!sum_out || sum_kind == PST3R_KIND_BF16) && (dim % 8) == 0 && dim <= 12 * 256 && (ldx % 8) == 0 &&
+                      (x_bs % 8) == 0 && al16(x) &&
                       (!add || ((ld_add % 8) == 0 && al16(add))) && (!sum_out || ((ld_sum % 8) == 0 && al16(sum_out))) &&
                       al16(y) && (ldy % (y_f32 ? 4 : 8)) == 0 && al16(gamma) && al16(beta) &&
                       (y_bs % (y_f32 ? 4 : 8)) == 0 && (p_bs % 4) == 0;
@@ -421,24 +518,18 @@ static int layernorm_run(const void* x, int32_t x_f32, int64_t ldx, const void* 
     return PST3R_OK;
   }
   PST3R_CHECK_ARG(y_bs == 0 && p_bs == 0 && !add_mod, "layernorm_batched: needs bf16 rows, dim %% 8 == 0, 16-byte alignment");
-  if (x_f32 && y_f32)
-    layernorm_kernel<true, true><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs);
-  else if (x_f32)
-    layernorm_kernel<true, false><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs);
-  else if (y_f32)
-    layernorm_kernel<false, true><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs);
-  else
-    layernorm_kernel<false, false><<<grid, wpb * 32, 0, s>>>(x, ldx, a, ld_add, gamma, beta, eps, y, ldy, so, ld_sum, rows, dim, x_rpb, x_bs);
+  layernorm_kernel<<<grid, wpb * 32, 0, s>>>(x, x_kind, ldx, add, add_kind, ld_add, gamma, beta, eps, y, y_kind, ldy, sum_out,
+                                              sum_kind, ld_sum, rows, dim, x_rpb, x_bs);
   PST3R_CHECK_CUDA(cudaGetLastError());
   return PST3R_OK;
 }
 
-extern "C" int pst3r_layernorm(const void* x, int32_t x_f32, int64_t ldx, const void* add, int64_t ld_add,
-                               const float* gamma, const float* beta, float eps, void* y, int32_t y_f32, int64_t ldy,
-                               void* sum_out, int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rpb, int64_t x_bs,
-                               pst3r_stream_t s_) {
-  return layernorm_run(x, x_f32, ldx, add, ld_add, gamma, beta, eps, y, y_f32, ldy, sum_out, ld_sum, rows, dim, x_rpb, x_bs,
-                       0, 0, 0, s_);
+extern "C" int pst3r_layernorm(const void* x, int32_t x_kind, int64_t ldx, const void* add, int32_t add_kind, int64_t ld_add,
+                               const float* gamma, const float* beta, float eps, void* y, int32_t y_kind, int64_t ldy,
+                               void* sum_out, int32_t sum_kind, int64_t ld_sum, int32_t rows, int32_t dim, int32_t x_rpb,
+                               int64_t x_bs, pst3r_stream_t s_) {
+  return layernorm_run(x, x_kind, ldx, add, add_kind, ld_add, gamma, beta, eps, y, y_kind, ldy, sum_out, sum_kind, ld_sum, rows,
+                       dim, x_rpb, x_bs, 0, 0, 0, s_);
 }
 
 extern "C" int pst3r_layernorm_batched(const void* x, int64_t ldx, int64_t x_batch_stride, const void* add, int64_t ld_add,
@@ -446,7 +537,7 @@ extern "C" int pst3r_layernorm_batched(const void* x, int64_t ldx, int64_t x_bat
                                        void* y, int64_t ldy, int64_t y_batch_stride, int32_t rows_per_batch,
                                        int32_t batches, int32_t dim, pst3r_stream_t s_) {
   PST3R_CHECK_ARG(rows_per_batch > 0 && batches > 0 && y_batch_stride != 0, "layernorm_batched: bad args");
-  return layernorm_run(x, 0, ldx, add, ld_add, gamma, beta, eps, y, 0, ldy, nullptr, 0, rows_per_batch * batches, dim,
+  return layernorm_run(x, 0, ldx, add, 0, ld_add, gamma, beta, eps, y, 0, ldy, nullptr, 0, 0, rows_per_batch * batches, dim,
                        rows_per_batch, x_batch_stride, y_batch_stride, param_batch_stride, 1, s_);
 }
 
@@ -461,15 +552,41 @@ extern "C" int pst3r_rope2d(void* tokens, int64_t s_b, int64_t s_n, int64_t s_h,
   return PST3R_OK;
 }
 
-extern "C" int pst3r_add_bcast(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_rows, void* out,
-                               int64_t ldo, int32_t rows, int32_t cols, pst3r_stream_t s_) {
+extern "C" int pst3r_add_bcast(const void* a, int32_t a_kind, int64_t lda, const void* b, int32_t b_kind, int64_t ldb,
+                               int32_t b_rows, void* out, int32_t out_kind, int64_t ldo, int32_t rows, int32_t cols,
+                               pst3r_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
-  PST3R_CHECK_ARG(a && b && out && rows > 0 && cols > 0 && (cols % 2) == 0 && b_rows > 0 && (lda % 2) == 0 &&
-                      (ldb % 2) == 0 && (ldo % 2) == 0,
-                  "add_bcast: bad args");
-  add_bcast_kernel<<<blocks_for((long long)rows * (cols / 2), 256), 256, 0, s>>>(
-      reinterpret_cast<const bf16*>(a), lda, reinterpret_cast<const bf16*>(b), ldb, b_rows, reinterpret_cast<bf16*>(out),
-      ldo, rows, cols);
+  PST3R_CHECK_ARG(a && b && out && rows > 0 && cols > 0 && b_rows > 0, "add_bcast: bad args");
+  if (a_kind == 0 && b_kind == 0 && out_kind == 0 && (cols % 2) == 0 && (lda % 2) == 0 && (ldb % 2) == 0 && (ldo % 2) == 0) {
+    add_bcast_kernel<<<blocks_for((long long)rows * (cols / 2), 256), 256, 0, s>>>(
+        reinterpret_cast<const bf16*>(a), lda, reinterpret_cast<const bf16*>(b), ldb, b_rows, reinterpret_cast<bf16*>(out),
+        ldo, rows, cols);
+  } else {
+    PST3R_CHECK_ARG(a_kind >= 0 && a_kind <= 2 && b_kind >= 0 && b_kind <= 2 && out_kind >= 0 && out_kind <= 2, "add_bcast: bad kind");
+    add_bcast_k_kernel<<<blocks_for((long long)rows * cols, 256), 256, 0, s>>>(a, a_kind, lda, b, b_kind, ldb, b_rows, out,
+                                                                              out_kind, ldo, rows, cols);
+  }
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_convert(const void* x, int32_t x_kind, int64_t ldx, void* y, int32_t y_kind, int64_t ldy, int32_t rows,
+                             int32_t cols, pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(x && y && rows > 0 && cols > 0 && x_kind >= 0 && x_kind <= 2 && y_kind >= 0 && y_kind <= 2, "convert: bad args");
+  convert_kernel<<<blocks_for((long long)rows * cols, 256), 256, 0, s>>>(x, x_kind, ldx, y, y_kind, ldy, rows, cols);
+  PST3R_CHECK_CUDA(cudaGetLastError());
+  return PST3R_OK;
+}
+
+extern "C" int pst3r_softmax_rows(const float* S, int64_t lds, int32_t rows, int32_t Nk, const uint32_t* mask_bits,
+                                  int64_t mask_sq, int32_t Q, void* out, int32_t out_kind, int64_t ldo, pst3r_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  PST3R_CHECK_ARG(S && out && rows > 0 && Nk > 0 && lds >= Nk && out_kind >= 0 && out_kind <= 2 && Q > 0 &&
+                      ldo >= (out_kind == PST3R_KIND_SPLIT ? 2 : 1) * (int64_t)Nk,
+                  "softmax_rows: bad args");
+  if (mask_bits) PST3R_CHECK_ARG(mask_sq * 32 >= Nk, "softmax_rows: mask rows shorter than Nk");
+  softmax_rows_kernel<<<rows, 256, 0, s>>>(S, lds, Nk, mask_bits, mask_sq, Q, out, out_kind, ldo);
   PST3R_CHECK_CUDA(cudaGetLastError());
   return PST3R_OK;
 }
@@ -513,10 +630,18 @@ extern "C" int pst3r_dino_preprocess_patchify(const float* img, int32_t B, int32
   return PST3R_OK;
 }
 
-extern "C" int pst3r_center_pool8(const void* feats, int32_t B, int32_t Hm, int32_t Wm, int32_t C, void* out,
+extern "C" int pst3r_center_pool8(const void* feats, int32_t kind, int32_t B, int32_t Hm, int32_t Wm, int32_t C, void* out,
                                   pst3r_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
-  PST3R_CHECK_ARG(feats && out && B > 0 && (Hm % 8) == 0 && (Wm % 8) == 0 && (C % 2) == 0, "center_pool8: bad args");
+  PST3R_CHECK_ARG(feats && out && B > 0 && (Hm % 8) == 0 && (Wm % 8) == 0 && (C % 2) == 0 &&
+                      (kind == PST3R_KIND_BF16 || kind == PST3R_KIND_SPLIT), "center_pool8: bad args");
+  if (kind == PST3R_KIND_SPLIT) {
+    const long long total = (long long)B * (Hm / 8) * (Wm / 8) * C;
+    center_pool8_split_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const bf16*>(feats), B, Hm, Wm, C,
+                                                                    reinterpret_cast<bf16*>(out));
+    PST3R_CHECK_CUDA(cudaGetLastError());
+    return PST3R_OK;
+  }
   const long long total = (long long)B * (Hm / 8) * (Wm / 8) * (C / 2);
   center_pool8_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const bf16*>(feats), B, Hm, Wm, C,
                                                             reinterpret_cast<bf16*>(out));
@@ -534,20 +659,22 @@ extern "C" int pst3r_attn_mask_bits(const float* logits_t, int64_t ld, int32_t Q
   return PST3R_OK;
 }
 
-extern "C" int pst3r_l2norm_rows(const float* x, int64_t ldx, void* y, int32_t y_f32, int64_t ldy, int32_t rows,
+extern "C" int pst3r_l2norm_rows(const float* x, int64_t ldx, void* y, int32_t y_kind, int64_t ldy, int32_t rows,
                                  int32_t cols, float eps, pst3r_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
-  PST3R_CHECK_ARG(x && y && rows > 0 && cols > 0, "l2norm_rows: bad args");
-  l2norm_rows_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(x, ldx, y, y_f32, ldy, rows, cols, eps);
+  PST3R_CHECK_ARG(x && y && rows > 0 && cols > 0 && y_kind >= 0 && y_kind <= 2, "l2norm_rows: bad args");
+  l2norm_rows_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(x, ldx, y, y_kind, ldy, rows, cols, eps);
   PST3R_CHECK_CUDA(cudaGetLastError());
   return PST3R_OK;
 }
 
-extern "C" int pst3r_nhwc_to_nchw_f32(const void* x, int32_t B, int32_t HW, int32_t C, float* y, pst3r_stream_t s_) {
+extern "C" int pst3r_nhwc_to_nchw_f32(const void* x, int32_t x_kind, int32_t B, int32_t HW, int32_t C, float* y,
+                                      pst3r_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
-  PST3R_CHECK_ARG(x && y && B > 0 && HW > 0 && C > 0, "nhwc_to_nchw_f32: bad args");
+  PST3R_CHECK_ARG(x && y && B > 0 && HW > 0 && C > 0 && (x_kind == PST3R_KIND_BF16 || x_kind == PST3R_KIND_SPLIT),
+                  "nhwc_to_nchw_f32: bad args");
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  nhwc_to_nchw_f32_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const bf16*>(x), HW, C, y);
+  nhwc_to_nchw_f32_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const bf16*>(x), x_kind, HW, C, y);
   PST3R_CHECK_CUDA(cudaGetLastError());
   return PST3R_OK;
 }

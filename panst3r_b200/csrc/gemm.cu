@@ -19,14 +19,16 @@
 
 namespace pst3r {
 
+enum { KIND_BF16 = 0, KIND_F32 = 1, KIND_SPLIT = 2 };
+
 struct GemmEpi {
   void* out;
   long long ldo;
-  int out_f32;
+  int out_kind;  // KIND_*: bf16, fp32, or split bf16 (hi at column c, lo at column c + out_lo_off)
   int act;
   const float* bias;
   const float* col_scale;
-  const bf16* residual;
+  const void* residual;  // res_kind: bf16, fp32 or split bf16 (lo res_lo_off elements after hi)
   long long ldr;
   int res_mod_rows;
   float alpha;
@@ -55,7 +57,27 @@ struct GemmEpi {
   // producer side: partial (sum, sum of squares) of every stored bf16 32-column chunk, stats_out[row][col / 32]
   float2* stats_out;
   int stats_slots;
+  // reference-precision mode: operands held as bf16 pairs x = hi + lo (hi = bf16(x), lo = bf16(x - hi), ~16 mantissa
+  // bits).  The K loop runs split_terms passes over the k-blocks, accumulating into the same TMEM tile:
+  //   3: A_hi B_hi + A_lo B_hi + A_hi B_lo (lo x lo, 2^-16 relative, dropped);  2: A (plain bf16) x (B_hi + B_lo).
+  // The hi / lo part is a dimension of the TMA maps, so the producer only changes one coordinate.
+  int split_terms;
+  long long out_lo_off;
+  int res_kind;
+  long long res_lo_off;
 };
+
+__device__ __forceinline__ void split_pack8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    const float2 f = unpack_bf16x2(h[i]);
+    l[i] = pack_bf16x2(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
 
 // (mean, rstd) of row `row` from the partial sums of its producer (fixed summation order: deterministic)
 __device__ __forceinline__ float2 ln_row_stats(const GemmEpi& ep, int row, int M) {
@@ -154,22 +176,41 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
   }
   if (ep.residual) {
     const int rrow = ep.res_mod_rows > 0 ? row % ep.res_mod_rows : row;
-    const bf16* r = ep.residual + (long long)rrow * ep.ldr + col0;
-    if (full && ((ep.ldr & 7) == 0)) {
-      const uint4* r4 = reinterpret_cast<const uint4*>(r);
+    if (ep.res_kind == KIND_F32) {
+      const float* r = reinterpret_cast<const float*>(ep.residual) + (long long)rrow * ep.ldr + col0;
+      if (full && ((ep.ldr & 3) == 0)) {
+        const float4* r4 = reinterpret_cast<const float4*>(r);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 u = __ldg(r4 + i);
-        float2 f;
-        f = unpack_bf16x2(u.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-        f = unpack_bf16x2(u.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-        f = unpack_bf16x2(u.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-        f = unpack_bf16x2(u.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+        for (int i = 0; i < 8; ++i) {
+          const float4 u = __ldg(r4 + i);
+          v[4 * i + 0] += u.x; v[4 * i + 1] += u.y; v[4 * i + 2] += u.z; v[4 * i + 3] += u.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) v[i] += r[i];
       }
     } else {
+      const bf16* r = reinterpret_cast<const bf16*>(ep.residual) + (long long)rrow * ep.ldr + col0;
+      const int nparts = ep.res_kind == KIND_SPLIT ? 2 : 1;
+      for (int part = 0; part < nparts; ++part, r += ep.res_lo_off) {
+        if (full && ((ep.ldr & 7) == 0) && ((ep.res_lo_off & 7) == 0)) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(r);
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < ncols) v[i] += __bfloat162float(r[i]);
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = __ldg(r4 + i);
+            float2 f;
+            f = unpack_bf16x2(u.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+            f = unpack_bf16x2(u.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+            f = unpack_bf16x2(u.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+            f = unpack_bf16x2(u.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) v[i] += __bfloat162float(r[i]);
+        }
+      }
     }
   }
 
@@ -180,9 +221,28 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
         const long long bb = row / ep.rows_per_batch;
         roff = bb * ep.batch_stride + (row - bb * ep.rows_per_batch) * ep.ldo;
       }
-      if (ep.out_f32) {
+      if (ep.out_kind == KIND_SPLIT) {
+        bf16* o = reinterpret_cast<bf16*>(ep.out) + roff + col0;
+        if (full && ((ep.ldo & 7) == 0) && ((ep.batch_stride & 7) == 0) && ((ep.out_lo_off & 7) == 0) && ((ep.out_bs & 7) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 hi, lo;
+            split_pack8(v + 8 * i, hi, lo);
+            reinterpret_cast<uint4*>(o)[i] = hi;
+            reinterpret_cast<uint4*>(o + ep.out_lo_off)[i] = lo;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) {
+              const bf16 h = __float2bfloat16(v[i]);
+              o[i] = h;
+              o[i + ep.out_lo_off] = __float2bfloat16(v[i] - __bfloat162float(h));
+            }
+        }
+      } else if (ep.out_kind == KIND_F32) {
         float* o = reinterpret_cast<float*>(ep.out) + roff + col0;
-        if (full && ((ep.ldo & 3) == 0) && ((ep.batch_stride & 3) == 0)) {
+        if (full && ((ep.ldo & 3) == 0) && ((ep.batch_stride & 3) == 0) && ((ep.out_bs & 3) == 0)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -223,11 +283,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
       // lanes of a warp hold consecutive rows -> each per-column store is a coalesced 128 B line
       const long long b = row / ep.rows_per_batch;
       const long long r = row - b * ep.rows_per_batch;
-      if (ep.out_f32) {
+      if (ep.out_kind == KIND_F32) {
         float* o = reinterpret_cast<float*>(ep.out) + b * ep.batch_stride + (long long)col0 * ep.ldt + r;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (i < ncols) o[(long long)i * ep.ldt] = v[i];
+      } else if (ep.out_kind == KIND_SPLIT) {
+        bf16* o = reinterpret_cast<bf16*>(ep.out) + b * ep.batch_stride + (long long)col0 * ep.ldt + r;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) {
+            const bf16 h = __float2bfloat16(v[i]);
+            o[(long long)i * ep.ldt] = h;
+            o[(long long)i * ep.ldt + ep.out_lo_off] = __float2bfloat16(v[i] - __bfloat162float(h));
+          }
       } else {
         bf16* o = reinterpret_cast<bf16*>(ep.out) + b * ep.batch_stride + (long long)col0 * ep.ldt + r;
 #pragma unroll
@@ -249,7 +318,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
         const int i = ij >> 1, j = ij & 1;
         const long long orow = ((long long)(b * 2 * gh + 2 * y + i)) * (2 * gw) + 2 * x + j;
         bf16* o = base + orow * ep.ldo + c0;
-        if (full && ((ep.ldo & 7) == 0)) {
+        if (ep.out_kind == KIND_SPLIT) {
+          float t8[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) t8[c] = v[4 * c + ij];
+          if (full && ((ep.ldo & 7) == 0) && ((ep.out_lo_off & 7) == 0)) {
+            uint4 hi, lo;
+            split_pack8(t8, hi, lo);
+            *reinterpret_cast<uint4*>(o) = hi;
+            *reinterpret_cast<uint4*>(o + ep.out_lo_off) = lo;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (4 * c + ij < ncols) {
+                const bf16 h = __float2bfloat16(t8[c]);
+                o[c] = h;
+                o[c + ep.out_lo_off] = __float2bfloat16(t8[c] - __bfloat162float(h));
+              }
+          }
+        } else if (full && ((ep.ldo & 7) == 0)) {
           uint4 u;
           u.x = pack_bf16x2(v[0 * 4 + ij], v[1 * 4 + ij]);
           u.y = pack_bf16x2(v[2 * 4 + ij], v[3 * 4 + ij]);
@@ -310,6 +397,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tiles_per_batch = num_m_blocks * num_n_blocks;
   const int num_tiles = tiles_per_batch * ep.batches;
   const int num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const int terms = ep.split_terms > 1 ? ep.split_terms : 1;
+  const int num_k_iters = num_k_blocks * terms;  // split mode: one pass over the k-blocks per product term
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   if (warp == 0 && lane == 0) {
@@ -346,11 +435,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int trem = tile - bidx * tiles_per_batch;
         const int m_blk = trem % num_m_blocks;
         const int n_blk = trem / num_m_blocks;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int it = 0; it < num_k_iters; ++it) {
+          const int term = it / num_k_blocks;
+          const int kb = it - term * num_k_blocks;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
           uint8_t* a_dst = smem + s * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + L::A_BYTES;
+          if (terms > 1) {
+            // hi / lo part of each operand for this product term: (hi,hi), (lo,hi), (hi,lo) | (A,hi), (A,lo)
+            const int pa = (terms == 3 && term == 1) ? 1 : 0;
+            const int pb = (term == terms - 1) ? 1 : 0;
+            if (ep.batches > 1) {
+              tma_load_4d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM, pa, bidx);
+              tma_load_4d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN, pb, bidx);
+            } else {
+              tma_load_3d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM, pa);
+              tma_load_3d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN, pb);
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+            continue;
+          }
           if (ep.conv_cblocks > 0) {
             // k-block -> (tap, channel block); m-tile -> (view, y, 128-pixel segment of the row)
             const int tap = kb / ep.conv_cblocks, cb = kb - tap * ep.conv_cblocks;
@@ -386,7 +491,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = 0; kb < num_k_iters; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
@@ -490,10 +595,10 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   if (e->store_mode == PST3R_STORE_TRANSPOSED)
     PST3R_CHECK_ARG(e->rows_per_batch > 0 && e->ldt > 0, "gemm: TRANSPOSED store needs rows_per_batch/ldt");
   if (e->store_mode == PST3R_STORE_PIXSHUF2)
-    PST3R_CHECK_ARG(e->grid_h > 0 && e->grid_w > 0 && (N % 4) == 0 && !e->out_f32 && (M % (e->grid_h * e->grid_w)) == 0,
+    PST3R_CHECK_ARG(e->grid_h > 0 && e->grid_w > 0 && (N % 4) == 0 && e->out_kind != PST3R_KIND_F32 && (M % (e->grid_h * e->grid_w)) == 0,
                     "gemm: PIXSHUF2 store needs grid, N%%4==0, bf16 out");
   if (e->store_mode == PST3R_STORE_D2S)
-    PST3R_CHECK_ARG(e->grid_h > 0 && e->grid_w > 0 && e->d2s_patch > 0 && e->d2s_ch > 0 && e->out_f32 &&
+    PST3R_CHECK_ARG(e->grid_h > 0 && e->grid_w > 0 && e->d2s_patch > 0 && e->d2s_ch > 0 && e->out_kind == PST3R_KIND_F32 &&
                         N == e->d2s_patch * e->d2s_patch * e->d2s_ch && (M % (e->grid_h * e->grid_w)) == 0,
                     "gemm: D2S store needs grid/patch/channels, N == P*P*C, fp32 out");
   if (e->rope_cs)
@@ -502,9 +607,9 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
                     "gemm: rope epilogue needs pos, rope_cols %% 64 == 0, maxpos, 16-byte aligned table");
 
   GemmEpi ep;
-  ep.out = e->out; ep.ldo = e->ldo; ep.out_f32 = e->out_f32; ep.act = e->act;
+  ep.out = e->out; ep.ldo = e->ldo; ep.out_kind = e->out_kind; ep.act = e->act;
   ep.bias = e->bias; ep.col_scale = e->col_scale;
-  ep.residual = reinterpret_cast<const bf16*>(e->residual); ep.ldr = e->ldr; ep.res_mod_rows = e->res_mod_rows;
+  ep.residual = e->residual; ep.ldr = e->ldr; ep.res_mod_rows = e->res_mod_rows;
   ep.alpha = e->alpha; ep.store_mode = e->store_mode;
   ep.rows_per_batch = e->rows_per_batch; ep.batch_stride = e->batch_stride; ep.ldt = e->ldt;
   ep.grid_h = e->grid_h; ep.grid_w = e->grid_w; ep.d2s_patch = e->d2s_patch; ep.d2s_ch = e->d2s_ch;
@@ -520,9 +625,20 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
                         (reinterpret_cast<uintptr_t>(e->ln_stats) & 15) == 0 && (reinterpret_cast<uintptr_t>(e->ln_colsum) & 15) == 0,
                     "gemm: folded LayerNorm needs stats [M][K/32] + colsum [N], K %% 64 == 0, N %% 32 == 0");
   if (e->stats_out)
-    PST3R_CHECK_ARG(e->store_mode == PST3R_STORE_PLAIN && e->rows_per_batch == 0 && !e->out_f32 && (N % 32) == 0 &&
+    PST3R_CHECK_ARG(e->store_mode == PST3R_STORE_PLAIN && e->rows_per_batch == 0 && e->out_kind == PST3R_KIND_BF16 && (N % 32) == 0 &&
                         (e->ldo % 8) == 0 && !conv && (reinterpret_cast<uintptr_t>(e->stats_out) & 7) == 0,
                     "gemm: stats_out needs a plain bf16 store with N %% 32 == 0 and ldo %% 8 == 0");
+  const int terms = e->split_terms;
+  ep.split_terms = terms; ep.out_lo_off = e->out_lo_off; ep.res_kind = e->res_kind; ep.res_lo_off = e->res_lo_off;
+  PST3R_CHECK_ARG(terms == 0 || terms == 2 || terms == 3, "gemm: split_terms must be 0, 2 or 3");
+  PST3R_CHECK_ARG(e->out_kind >= 0 && e->out_kind <= 2 && e->res_kind >= 0 && e->res_kind <= 2, "gemm: bad out_kind / res_kind");
+  if (terms)
+    PST3R_CHECK_ARG(!conv && !e->ln_stats && (e->b_lo_off % 8) == 0 && e->b_lo_off > 0 &&
+                        (terms == 2 || ((e->a_lo_off % 8) == 0 && e->a_lo_off > 0)),
+                    "gemm: split operands need lo offsets that are positive multiples of 8 (no conv / folded LayerNorm)");
+  if (e->out_kind == PST3R_KIND_SPLIT)
+    PST3R_CHECK_ARG(e->out_lo_off > 0 && e->store_mode != PST3R_STORE_D2S && !e->stats_out, "gemm: split output needs out_lo_off");
+  if (e->residual && e->res_kind == PST3R_KIND_SPLIT) PST3R_CHECK_ARG(e->res_lo_off > 0, "gemm: split residual needs res_lo_off");
   const int nb = bat ? bat->batches : 1;
   if (nb > 1) {
     ep.batches = nb; ep.out_bs = bat->out_bs; ep.bias_bs = bat->bias_bs;
@@ -550,20 +666,34 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   // large plain GEMMs with N % 256 == 0 go to the 2-CTA kernel (256 x 256 tiles per SM pair)
   const bool use2 = !conv && nb == 1 && gemm2_enabled() && (N % G2_BN) == 0 &&
                     (long long)((M + 255) / 256) * (N / G2_BN) >= (sms / 2);
+  // split mode: the hi / lo part is dimension 2 of both maps (a plain-bf16 A has a single part)
+  const uint64_t a_parts = terms == 3 ? 2 : 1;
+  const uint64_t a_part_stride = terms == 3 ? (uint64_t)e->a_lo_off * 2 : (uint64_t)lda * 2;
   if (use2) {
     CUtensorMap tA2, tB2;
-    uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[2] = {2, (uint64_t)lda * 2};
-    uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[2] = {2, (uint64_t)ldb * 2};
-    uint32_t bA[2] = {GEMM_BK, GEMM_BM}, bB[2] = {GEMM_BK, G2_BN / 2};
-    int r = encode_tmap(&tA2, A, 2, 2, dA, sA, bA);
+    uint64_t dA[3] = {(uint64_t)K, (uint64_t)M, a_parts}, sA[3] = {2, (uint64_t)lda * 2, a_part_stride};
+    uint64_t dB[3] = {(uint64_t)K, (uint64_t)N, 2}, sB[3] = {2, (uint64_t)ldb * 2, (uint64_t)e->b_lo_off * 2};
+    uint32_t bA[3] = {GEMM_BK, GEMM_BM, 1}, bB[3] = {GEMM_BK, G2_BN / 2, 1};
+    int r = encode_tmap(&tA2, A, 2, terms ? 3 : 2, dA, sA, bA);
     if (r) return r;
-    r = encode_tmap(&tB2, B, 2, 2, dB, sB, bB);
+    r = encode_tmap(&tB2, B, 2, terms ? 3 : 2, dB, sB, bB);
     if (r) return r;
     return launch_gemm2(tA2, tB2, ep, M, N, K, stream);
   }
 
   CUtensorMap tmA, tmB;
-  if (conv) {
+  if (terms) {
+    // (K, rows, part[, batch]); rows / K beyond the logical extents are zero filled, never the next part / problem
+    uint64_t dA[4] = {(uint64_t)K, (uint64_t)M, a_parts, (uint64_t)nb};
+    uint64_t sA[4] = {2, (uint64_t)lda * 2, a_part_stride, (uint64_t)(bat ? bat->a_bs : 0) * 2};
+    uint64_t dB[4] = {(uint64_t)K, (uint64_t)N, 2, (uint64_t)nb};
+    uint64_t sB[4] = {2, (uint64_t)ldb * 2, (uint64_t)e->b_lo_off * 2, (uint64_t)(bat ? bat->b_bs : 0) * 2};
+    uint32_t bA[4] = {GEMM_BK, GEMM_BM, 1, 1}, bB[4] = {GEMM_BK, (uint32_t)BN, 1, 1};
+    int r = encode_tmap(&tmA, A, 2, nb > 1 ? 4 : 3, dA, sA, bA);
+    if (r) return r;
+    r = encode_tmap(&tmB, B, 2, nb > 1 ? 4 : 3, dB, sB, bB);
+    if (r) return r;
+  } else if (conv) {
     // pixel-major map [V, H, W, C] (row pitch lda): box = 64 channels x 128 pixels of one image row; coordinates outside
     // the map (x = -1, W; y = -1, H; channels >= C) are zero-filled by TMA == the convolution's zero padding
     uint64_t dims[4] = {(uint64_t)conv->C, (uint64_t)conv->W, (uint64_t)conv->H, (uint64_t)conv->V};
@@ -585,7 +715,9 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
     int r = encode_tmap(&tmA, A, 2, 2, dims, str, box);
     if (r) return r;
   }
-  if (nb > 1) {
+  if (terms) {
+    // B map encoded above
+  } else if (nb > 1) {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)nb};
     uint64_t str[3] = {2, (uint64_t)ldb * 2, (uint64_t)bat->b_bs * 2};
     uint32_t box[3] = {GEMM_BK, (uint32_t)BN, 1};
@@ -618,7 +750,7 @@ extern "C" int pst3r_gemm_bf16_batched(const void* A, int64_t lda, int64_t a_bat
   PST3R_CHECK_ARG(e->store_mode == PST3R_STORE_PLAIN && e->rows_per_batch == 0 && !e->residual && !e->rope_cs &&
                       !e->col_scale, "gemm_batched: plain store, bias / activation epilogue only");
   PST3R_CHECK_ARG((a_batch_stride % 8) == 0 && (b_batch_stride % 8) == 0 && (bias_batch_stride % 4) == 0 &&
-                      (out_batch_stride % (e->out_f32 ? 4 : 8)) == 0,
+                      (out_batch_stride % (e->out_kind == PST3R_KIND_F32 ? 4 : 8)) == 0,
                   "gemm_batched: batch strides must keep 16-byte alignment");
   BatchCfg bc{batches, a_batch_stride, b_batch_stride, out_batch_stride, bias_batch_stride};
   return gemm_run(A, lda, B, ldb, M, N, K, e, stream, nullptr, batches > 1 ? &bc : nullptr);

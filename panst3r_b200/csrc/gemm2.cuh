@@ -57,6 +57,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m,
       ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void umma_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
@@ -99,6 +105,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int num_n_blocks = N / BN;  // host guarantees N % 256 == 0
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const int terms = ep.split_terms > 1 ? ep.split_terms : 1;  // split-bf16 mode: see GemmEpi::split_terms
+  const int num_k_iters = num_k_blocks * terms;
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   if (warp == 0 && lane == 0) {
@@ -134,13 +142,22 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile % num_m_blocks;
         const int n_blk = tile / num_m_blocks;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int it = 0; it < num_k_iters; ++it) {
+          const int term = it / num_k_blocks;
+          const int kb = it - term * num_k_blocks;
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (leader) mbar_expect_tx(&full_bar[s], 2 * G2_STAGE_BYTES);
           uint8_t* a_dst = smem + s * G2_STAGE_BYTES;
           uint8_t* b_dst = a_dst + G2_A_BYTES;
-          tma_load_2d_2sm(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * 256 + (int)rank * 128);
-          tma_load_2d_2sm(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)rank * (BN / 2));
+          if (terms > 1) {
+            const int pa = (terms == 3 && term == 1) ? 1 : 0;
+            const int pb = (term == terms - 1) ? 1 : 0;
+            tma_load_3d_2sm(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * 256 + (int)rank * 128, pa);
+            tma_load_3d_2sm(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)rank * (BN / 2), pb);
+          } else {
+            tma_load_2d_2sm(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * 256 + (int)rank * 128);
+            tma_load_2d_2sm(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)rank * (BN / 2));
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -158,7 +175,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = 0; kb < num_k_iters; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * G2_STAGE_BYTES);

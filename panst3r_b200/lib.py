@@ -11,7 +11,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libpanst3r_b200.so")
 
 
-ABI_VERSION = 2  # PST3R_ABI_VERSION of include/panst3r_b200.h these ctypes declarations were written against
+ABI_VERSION = 3  # PST3R_ABI_VERSION of include/panst3r_b200.h these ctypes declarations were written against
 
 
 class Pst3rError(RuntimeError):
@@ -22,7 +22,7 @@ class GemmEpilogue(C.Structure):
     _fields_ = [
         ("out", C.c_void_p),
         ("ldo", C.c_int64),
-        ("out_f32", C.c_int32),
+        ("out_kind", C.c_int32),
         ("act", C.c_int32),
         ("bias", C.c_void_p),
         ("col_scale", C.c_void_p),
@@ -47,6 +47,12 @@ class GemmEpilogue(C.Structure):
         ("ln_colsum", C.c_void_p),
         ("ln_eps", C.c_float),
         ("stats_out", C.c_void_p),
+        ("split_terms", C.c_int32),
+        ("a_lo_off", C.c_int64),
+        ("b_lo_off", C.c_int64),
+        ("out_lo_off", C.c_int64),
+        ("res_kind", C.c_int32),
+        ("res_lo_off", C.c_int64),
     ]
 
 
@@ -84,17 +90,20 @@ SIGNATURES = {
     "pst3r_attention_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),
     "pst3r_attention_auto_splits": (_i32, [_i32, _i32, _i32, _i32]),
     "pst3r_attention": (C.c_int, [C.POINTER(AttnArgs), _p]),
-    "pst3r_layernorm": (C.c_int, [_p, _i32, _i64, _p, _i64, _p, _p, _f, _p, _i32, _i64, _p, _i64, _i32, _i32, _i32, _i64, _p]),
+    "pst3r_layernorm": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _p, _p, _f, _p, _i32, _i64, _p, _i32, _i64, _i32, _i32, _i32,
+                                  _i64, _p]),
     "pst3r_rope2d": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f, _f, _p]),
-    "pst3r_add_bcast": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _i64, _i32, _i32, _p]),
+    "pst3r_add_bcast": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _i32, _p, _i32, _i64, _i32, _i32, _p]),
+    "pst3r_convert": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _i32, _i32, _p]),
+    "pst3r_softmax_rows": (C.c_int, [_p, _i64, _i32, _i32, _p, _i64, _i32, _p, _i32, _i64, _p]),
     "pst3r_cast_f32_to_bf16": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p]),
     "pst3r_cast_bf16_to_f32": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p]),
     "pst3r_patchify": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i64, _p]),
     "pst3r_dino_preprocess_patchify": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
-    "pst3r_center_pool8": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
+    "pst3r_center_pool8": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p]),
     "pst3r_attn_mask_bits": (C.c_int, [_p, _i64, _i32, _i32, _p, _p]),
     "pst3r_l2norm_rows": (C.c_int, [_p, _i64, _p, _i32, _i64, _i32, _i32, _f, _p]),
-    "pst3r_nhwc_to_nchw_f32": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
+    "pst3r_nhwc_to_nchw_f32": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "pst3r_class_scores": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p]),
     "pst3r_panoptic_argmax": (C.c_int, [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _i32, _i32, _i32, _f, _p, _p, _i64, _i32,
                                         _p, _p, _p]),

@@ -6,6 +6,7 @@ passes call only panst3r_b200.ops (the C ABI).  Weights are converted once to th
 """
 from __future__ import annotations
 
+import weakref
 from typing import Callable, Dict, Optional, Sequence, Tuple
 
 import torch
@@ -13,7 +14,8 @@ import torch.nn as nn
 
 from .. import ops
 
-_cache: Dict[Tuple, Tuple[Tuple, torch.Tensor]] = {}
+_cache: Dict[Tuple, Tuple[Tuple, Tuple, torch.Tensor]] = {}
+_cache_sweep_at = 4096
 
 
 def _ver(ps: Sequence[torch.Tensor]) -> Tuple:
@@ -21,15 +23,23 @@ def _ver(ps: Sequence[torch.Tensor]) -> Tuple:
 
 
 def prepared(key: str, params: Sequence[torch.Tensor], build: Callable[[], torch.Tensor]) -> torch.Tensor:
-    """Cache `build()` until any of `params` changes (load_state_dict / .to() bump version or data_ptr)."""
+    """Cache `build()` until any of `params` changes (load_state_dict / .to() bump version or data_ptr).
+    For PARAMETERS (long-lived tensors) only — activations are converted per call.  Entries hold weak references to
+    their parameters: a hit requires the very same live objects (CPython recycles id()s, the caching allocator
+    recycles addresses), and entries whose parameters died are dropped."""
+    global _cache_sweep_at
     k = (key, tuple(id(p) for p in params))
     v = _ver(params)
     hit = _cache.get(k)
-    if hit is not None and hit[0] == v:
-        return hit[1]
+    if hit is not None and hit[0] == v and all(r() is p for r, p in zip(hit[1], params)):
+        return hit[2]
     with torch.no_grad():
         t = build()
-    _cache[k] = (v, t)
+    _cache[k] = (v, tuple(weakref.ref(p) for p in params), t)
+    if len(_cache) > _cache_sweep_at:  # drop entries of parameters that no longer exist
+        for kk in [kk for kk, e in _cache.items() if any(r() is None for r in e[1])]:
+            del _cache[kk]
+        _cache_sweep_at = max(4096, 2 * len(_cache))
     return t
 
 
@@ -52,6 +62,35 @@ def f32(p: torch.Tensor) -> torch.Tensor:
 def b16(p: torch.Tensor) -> torch.Tensor:
     _check_cuda(p)
     return prepared("b16", [p], lambda: p.detach().to(torch.bfloat16).contiguous())
+
+
+def _split_cat(w32: torch.Tensor) -> torch.Tensor:
+    """fp32 [N, K] -> bf16 [N, 2K] rows [hi | lo] with hi = bf16(w), lo = bf16(w - hi)."""
+    hi = w32.to(torch.bfloat16)
+    lo = (w32 - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], 1).contiguous()
+
+
+def _as_split(buf: torch.Tensor) -> "ops.Split":
+    k = buf.shape[-1] // 2
+    return ops.Split(buf[..., :k], k)
+
+
+def wsplit(p: torch.Tensor) -> "ops.Split":
+    """Reference-precision weight operand [N, K] (ops.Split: bf16 hi | lo parts of the fp32 parameter)."""
+    _check_cuda(p)
+    return _as_split(prepared("wsplit", [p], lambda: _split_cat(p.detach().reshape(p.shape[0], -1).float())))
+
+
+def cat_wsplit(ps: Sequence[torch.Tensor]) -> "ops.Split":
+    return _as_split(prepared("catwsplit", list(ps),
+                              lambda: _split_cat(torch.cat([p.detach().reshape(p.shape[0], -1).float() for p in ps], 0))))
+
+
+def psplit(p: torch.Tensor) -> "ops.Split":
+    """A parameter used as an ACTIVATION (learned queries, embeddings) in split form."""
+    _check_cuda(p)
+    return _as_split(prepared("psplit", [p], lambda: _split_cat(p.detach().reshape(-1, p.shape[-1]).float())))
 
 
 def cat_w16(ps: Sequence[torch.Tensor]) -> torch.Tensor:

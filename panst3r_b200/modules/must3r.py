@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .common import (ViTBlockParams, b16, bias_of, cat_f32, cat_w16, f32, fold_stats, ln_linear, mlp_residual, pos_grid,
+from .common import (ViTBlockParams, bias_of, cat_f32, cat_w16, f32, fold_stats, ln_linear, mlp_residual, pos_grid,
                      prepared, rope_table, self_attention, vit_block, w16)
 
 
@@ -121,6 +121,14 @@ class MemoryBank:
         self.kv_all = torch.empty((self.depth, self.B, self.cap, 2 * self.dim), device=device, dtype=torch.bfloat16)
         self.tok = [self.tok_all[l] for l in range(self.depth)]
         self.kv = [self.kv_all[l] for l in range(self.depth)]
+
+    def fork(self, n: int) -> "MemoryBank":
+        """Independent bank holding the first n tokens (copy-on-write for non-tail appends)."""
+        nb = MemoryBank(self.B, self.depth, self.dim, self.tok_all.device, self.cap)
+        nb.tok_all[:, :, :n].copy_(self.tok_all[:, :, :n])
+        nb.kv_all[:, :, :n].copy_(self.kv_all[:, :, :n])
+        nb.n = n
+        return nb
 
     def reserve(self, n_total: int):
         if n_total <= self.cap:
@@ -261,6 +269,11 @@ class MUSt3R(nn.Module):
             mem_vals, mem_labels, mem_nimgs = mem[0], mem[1], mem[2]
             bank = getattr(mem_vals, "bank", None)
             n_mem = mem_vals[0].shape[1]
+            if bank is not None and not render and bank.n != n_mem:
+                # `mem` is a VALUE in the reference (torch.cat builds new tensors).  Our bank appends in place, so an
+                # update that does not start from the bank's tail (branching from / re-running an earlier memory)
+                # first moves to a private copy: the other holder's tokens and K|V stay untouched.
+                bank = bank.fork(n_mem)
         else:
             if render:
                 raise ops._l.Pst3rError("render=True needs a memory")
@@ -274,8 +287,9 @@ class MUSt3R(nn.Module):
                 return [bank.kv[l][b:b + 1, :n_mem] for b in range(B)]
             # foreign memory tuple (e.g. the reference's sliced render path): project on the fly
             blk = self.blocks_dec[l]
-            kv = ops.gemm(b16(mem_vals[l]) if mem_vals[l].dtype != torch.bfloat16 else mem_vals[l].contiguous(),
-                          blk.kv_weight(), bias=blk.kv_bias())
+            mv = mem_vals[l]  # an activation: converted per call, never through the parameter cache
+            mv = mv.contiguous() if mv.dtype == torch.bfloat16 else ops.to_bf16(mv.float().contiguous())
+            kv = ops.gemm(mv, blk.kv_weight(), bias=blk.kv_bias())
             return [kv[b:b + 1] for b in range(kv.shape[0])]
 
         if render:

@@ -11,6 +11,13 @@ B200-first restructuring (results are those of the reference ops on the same inp
   * K/V in-projections of the (layer-invariant) memory tokens of all 6 decoder layers are two batched GEMMs;
   * level_embed is folded into the proj_16.fc2 bias; the sine PE is a per-grid constant;
   * the boolean attention mask is a bitmask consumed directly by the attention kernel.
+
+Numerics.  The reference runs this head in fp32 even when the trunk runs under bf16 autocast (panst3r.py:236-245).
+`precise=True` (PanopticDecoder.precision == "fp32", the default) reproduces that policy on the bf16 tensor cores:
+activations and weights are `ops.Split` pairs (hi + lo bf16, 16 mantissa bits), every GEMM accumulates
+A_hi B_hi + A_lo B_hi + A_hi B_lo in fp32, LayerNorm / softmax / GELU are evaluated in fp32, and the 200-query attention
+of the query decoder is evaluated unfused (QK^T GEMM -> masked row softmax -> PV GEMM) so that its probabilities keep
+16 bits too.  `precision == "bf16"` keeps plain bf16 operands and the fused flash-attention kernels (faster, ~1e-2).
 """
 from __future__ import annotations
 
@@ -21,7 +28,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .common import b16, bias_of, cat_f32, cat_w16, f32, prepared, w16
+from .common import _as_split, _split_cat, b16, bias_of, cat_f32, cat_w16, f32, prepared, psplit, w16, wsplit
 from .must3r import _hw, oriented
 
 
@@ -44,41 +51,54 @@ class PixelShuffleUpscaler(nn.Module):
         self.mask_dim = fp_dim[3]
 
     @torch.no_grad()
-    def forward_nhwc(self, feats: torch.Tensor, b: int, hs: int, ws: int, f16_extra_bias: Optional[torch.Tensor] = None):
-        """feats bf16 rows (b*hs*ws, input_dim) -> (f16 bf16 (b*hs*ws, 768) token-major,
-        mask feats bf16 (b, 8hs, 8ws, 256) pixel-major).  f16_extra_bias is added to the f16 output (level_embed)."""
+    def forward_nhwc(self, feats, b: int, hs: int, ws: int, f16_extra_bias: Optional[torch.Tensor] = None,
+                     precise: bool = False):
+        """feats bf16 (or ops.Split) rows (b*hs*ws, input_dim) -> (f16 (b*hs*ws, 768) token-major, mask feats
+        (b, 8hs, 8ws, 256) pixel-major); bf16 tensors, or ops.Split pairs when `precise`.  f16_extra_bias is added to
+        the f16 output (level_embed)."""
         dev = feats.device
+        W = wsplit if precise else w16
+        act = "split" if precise else torch.bfloat16
 
         def mlp_shuffle(x, m: _Mlp, gh, gw):
-            h = ops.gemm(x, w16(m.fc1.weight), bias=bias_of(m.fc1), act=ops.ACT_GELU)
+            h = ops.gemm(x, W(m.fc1.weight), bias=bias_of(m.fc1), act=ops.ACT_GELU, out_dtype=act)
             cout = m.fc2.weight.shape[0] // 4
-            out = torch.empty((b * 2 * gh * 2 * gw, cout), device=dev, dtype=torch.bfloat16)
-            ops.gemm(h, w16(m.fc2.weight), bias=bias_of(m.fc2), out=out, store_mode=ops.STORE_PIXSHUF2, grid=(gh, gw))
+            out = ops._new((b * 2 * gh * 2 * gw, cout), ops._dkind(act), dev)
+            ops.gemm(h, W(m.fc2.weight), bias=bias_of(m.fc2), out=out, store_mode=ops.STORE_PIXSHUF2, grid=(gh, gw))
             return out
 
         f8 = mlp_shuffle(feats, self.proj_8, hs, ws)
         f4 = mlp_shuffle(f8, self.proj_4, 2 * hs, 2 * ws)
         f2 = mlp_shuffle(f4, self.proj_2, 4 * hs, 4 * ws)
-        h = ops.gemm(feats, w16(self.proj_16.fc1.weight), bias=bias_of(self.proj_16.fc1), act=ops.ACT_GELU)
+        h = ops.gemm(feats, W(self.proj_16.fc1.weight), bias=bias_of(self.proj_16.fc1), act=ops.ACT_GELU, out_dtype=act)
         bias16 = f32(self.proj_16.fc2.bias)
         if f16_extra_bias is not None:
             bias16 = prepared("f16bias", [self.proj_16.fc2.bias, f16_extra_bias],
                               lambda: (self.proj_16.fc2.bias.detach().float() + f16_extra_bias.detach().float().view(-1)).contiguous())
-        f16 = ops.gemm(h, w16(self.proj_16.fc2.weight), bias=bias16)
+        f16 = ops.gemm(h, W(self.proj_16.fc2.weight), bias=bias16, out_dtype=act)
         return f16, f2.view(b, 8 * hs, 8 * ws, self.mask_dim)
 
     @torch.no_grad()
-    def forward(self, inputs, img_shape):
+    def forward(self, inputs, img_shape, precise: bool = False):
         """Reference signature: (feats (b, N, C), imgs), (H, W) -> ([f16 (b,768,hs,ws)], mask_feats (b,256,H/2,W/2)) fp32 NCHW."""
         feats = inputs[0]
         H, W = img_shape
         hs, ws = H // self.patch_size, W // self.patch_size
         b = feats.shape[0]
-        x = feats if feats.dtype == torch.bfloat16 else ops.to_bf16(feats.float().contiguous())
-        f16, f2 = self.forward_nhwc(x.reshape(b * hs * ws, -1), b, hs, ws)
+        x = _head_input(feats.reshape(b * hs * ws, -1), precise)
+        f16, f2 = self.forward_nhwc(x, b, hs, ws, precise=precise)
         f16_nchw = ops.nhwc_to_nchw_f32(f16.view(b, hs * ws, -1)).view(b, -1, hs, ws)
         f2_nchw = ops.nhwc_to_nchw_f32(f2.view(b, 64 * hs * ws, -1)).view(b, -1, 8 * hs, 8 * ws)
         return [f16_nchw], f2_nchw
+
+
+def _head_input(x: torch.Tensor, precise: bool):
+    """Head input rows: bf16 stays bf16 (exact; two-term products in precise mode); fp32 becomes an ops.Split when
+    precise, bf16 otherwise."""
+    if x.dtype == torch.bfloat16:
+        return x
+    x = x.float().contiguous()
+    return ops.Split.from_float(x) if precise else ops.to_bf16(x)
 
 
 class TextEncoder(nn.Module):
@@ -97,15 +117,19 @@ class TextEncoder(nn.Module):
         raise NotImplementedError("the HF text tower is outside the CUDA hot path; assign `class_embeddings` directly")
 
     @torch.no_grad()
-    def forward(self, classes: List[str], device=None) -> torch.Tensor:
+    def forward(self, classes: List[str], device=None, precise: bool = False):
         assert all(c in self.class_embeddings for c in classes), "Missing classes in vocabulary"
-        key = tuple(classes)
+        embs = [self.class_embeddings[c] for c in classes]
+        # identity + version of every embedding tensor: re-assigned / updated vectors for the same names must not hit
+        key = (tuple(classes), tuple((id(e), e._version, e.data_ptr()) for e in embs), str(torch.device(device)), precise)
         hit = self._norm_cache.get(key)
-        if hit is None or hit.device != torch.device(device):
-            e = torch.stack([self.class_embeddings[c] for c in classes]).to(device=device, dtype=torch.float32).contiguous()
-            hit = ops.l2norm_rows(e, 0.0, torch.bfloat16)
-            self._norm_cache = {key: hit}
-        return hit
+        if hit is None:
+            e = torch.stack(embs).to(device=device, dtype=torch.float32).contiguous()
+            hit = (ops.l2norm_rows(e, 0.0, "split" if precise else torch.bfloat16), embs)  # embs kept alive: ids stay unique
+            self._norm_cache[key] = hit
+            while len(self._norm_cache) > 4:
+                self._norm_cache.pop(next(iter(self._norm_cache)))
+        return hit[0]
 
 
 class _MHA(nn.Module):
@@ -186,52 +210,60 @@ class MaskTransformer(nn.Module):
         self.mask_embed = _MaskMLP(hidden_dim, hidden_dim, mask_dim, 3)
 
     # ---- prepared -------------------------------------------------------------------------------
-    def _kv_weights(self):
+    def _kv_weights(self, precise: bool = False):
         d = self.hidden_dim
         ws = [l.multihead_attn.in_proj_weight for l in self.cross_attn_layers]
         bs = [l.multihead_attn.in_proj_bias for l in self.cross_attn_layers]
-        wk = prepared("mt_wk", ws, lambda: torch.cat([w.detach()[d:2 * d] for w in ws], 0).to(torch.bfloat16).contiguous())
-        wv = prepared("mt_wv", ws, lambda: torch.cat([w.detach()[2 * d:] for w in ws], 0).to(torch.bfloat16).contiguous())
         bk = prepared("mt_bk", bs, lambda: torch.cat([b.detach()[d:2 * d] for b in bs], 0).float().contiguous())
         bv = prepared("mt_bv", bs, lambda: torch.cat([b.detach()[2 * d:] for b in bs], 0).float().contiguous())
+        if precise:
+            wk = _as_split(prepared("mt_wk_s", ws, lambda: _split_cat(torch.cat([w.detach()[d:2 * d].float() for w in ws], 0))))
+            wv = _as_split(prepared("mt_wv_s", ws, lambda: _split_cat(torch.cat([w.detach()[2 * d:].float() for w in ws], 0))))
+            return wk, bk, wv, bv
+        wk = prepared("mt_wk", ws, lambda: torch.cat([w.detach()[d:2 * d] for w in ws], 0).to(torch.bfloat16).contiguous())
+        wv = prepared("mt_wv", ws, lambda: torch.cat([w.detach()[2 * d:] for w in ws], 0).to(torch.bfloat16).contiguous())
         return wk, bk, wv, bv
 
-    def _pos(self, h, w, device, portrait: bool = False):
-        """Sine PE rows for the (h, w) token grid of one view.  Portrait views (stored transposed): the reference
-        embeds the transposed map and applies its rows, in THAT map's raster order, to the stored tokens as they are
-        (get_pe_with_transpose, mask_transformer.py:106-119) — restated literally."""
-        if portrait:
-            return prepared(f"mt_pe_{h}x{w}_p", [self.level_embed.weight],
-                            lambda: sine_pe(w, h, self.hidden_dim // 2).to(device=device, dtype=torch.bfloat16).contiguous())
-        return prepared(f"mt_pe_{h}x{w}", [self.level_embed.weight],
-                        lambda: sine_pe(h, w, self.hidden_dim // 2).to(device=device, dtype=torch.bfloat16).contiguous())
+    def _pos(self, h, w, device, portrait: bool = False, precise: bool = False):
+        """Sine PE rows for the (h, w) token grid of one view (bf16, or fp32 when precise).  Portrait views (stored
+        transposed): the reference embeds the transposed map and applies its rows, in THAT map's raster order, to the
+        stored tokens as they are (get_pe_with_transpose, mask_transformer.py:106-119) — restated literally."""
+        dt = torch.float32 if precise else torch.bfloat16
+        gh, gw = (w, h) if portrait else (h, w)
+        return prepared(f"mt_pe_{h}x{w}_{'p' if portrait else 'l'}_{'f' if precise else 'b'}", [self.level_embed.weight],
+                        lambda: sine_pe(gh, gw, self.hidden_dim // 2).to(device=device, dtype=dt).contiguous())
 
     @staticmethod
-    def _slice_w(p: torch.Tensor, a: int, b: int, tag: str):
+    def _slice_w(p: torch.Tensor, a: int, b: int, tag: str, precise: bool = False):
+        if p.dim() == 2 and precise:
+            return _as_split(prepared(f"mt_slice_s_{tag}_{a}_{b}", [p], lambda: _split_cat(p.detach()[a:b].float())))
         return prepared(f"mt_slice_{tag}_{a}_{b}", [p], lambda: (p.detach()[a:b].to(torch.bfloat16) if p.dim() == 2 else
                                                                  p.detach()[a:b].float()).contiguous())
 
     # ---- prediction heads (mask_transformer.py:215-288) -----------------------------------------------
     @torch.no_grad()
-    def prediction_heads(self, output: torch.Tensor, mask_feats: torch.Tensor, pooled: Optional[torch.Tensor],
-                         cls_emb: torch.Tensor, want_masks: bool):
-        """output bf16 (Q, C) [batch 1]; mask_feats bf16 (V, Hm, Wm, Cm) pixel-major; pooled bf16 (V*h*w, Cm) or None.
+    def prediction_heads(self, output, mask_feats, pooled, cls_emb, want_masks: bool, precise: bool = False):
+        """output (Q, C) [batch 1]; mask_feats (V, Hm, Wm, Cm) pixel-major; pooled (V*h*w, Cm) or None — bf16 tensors,
+        or ops.Split pairs when `precise`.
         Returns (class logits fp32 (Q, K), mask logits fp32 (V, Q, Hm, Wm) | None, mask bits int32 (1, Q, W) | None)."""
         Q = output.shape[0]
+        W = wsplit if precise else w16
+        act = "split" if precise else torch.bfloat16
+        dev = output.device
         dec = ops.layernorm(output, f32(self.decoder_norm.weight), f32(self.decoder_norm.bias), 1e-5)
-        lang = ops.gemm(dec, w16(self.lang_embed.weight), bias=bias_of(self.lang_embed), out_dtype=torch.float32)
-        lang = ops.l2norm_rows(lang, 1e-7, torch.bfloat16)
+        lang = ops.gemm(dec, W(self.lang_embed.weight), bias=bias_of(self.lang_embed), out_dtype=torch.float32)
+        lang = ops.l2norm_rows(lang, 1e-7, act)
         scale = prepared("mt_scale", [self.cls_logit_scale], lambda: self.cls_logit_scale.detach().float().exp().cpu())
         logits = ops.gemm(lang, cls_emb, alpha=float(scale), out_dtype=torch.float32)
         e = dec
         nl = len(self.mask_embed.layers)
         for i, l in enumerate(self.mask_embed.layers):
-            e = ops.gemm(e, w16(l.weight), bias=bias_of(l), act=ops.ACT_RELU if i < nl - 1 else ops.ACT_NONE)
+            e = ops.gemm(e, W(l.weight), bias=bias_of(l), act=ops.ACT_RELU if i < nl - 1 else ops.ACT_NONE, out_dtype=act)
         masks = None
         if want_masks:
             def plane_major(mf):
                 V, Hm, Wm, Cm = mf.shape
-                mk = torch.empty((V, Q, Hm, Wm), device=output.device, dtype=torch.float32)
+                mk = torch.empty((V, Q, Hm, Wm), device=dev, dtype=torch.float32)
                 ops.gemm(mf.view(V * Hm * Wm, Cm), e, out=mk, store_mode=ops.STORE_TRANSPOSED,
                          rows_per_batch=Hm * Wm, batch_stride=Q * Hm * Wm, ldt=Hm * Wm)
                 return mk
@@ -240,27 +272,41 @@ class MaskTransformer(nn.Module):
         bits = None
         if pooled is not None:
             nk = pooled.shape[0]
-            small = torch.empty((Q, nk), device=output.device, dtype=torch.float32)
+            small = torch.empty((Q, nk), device=dev, dtype=torch.float32)
             ops.gemm(pooled, e, out=small, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=nk, batch_stride=0, ldt=nk)
             bits = ops.attn_mask_bits(small, nk)
         return logits, masks, bits
 
-    def _mha(self, q_in, k, v, m: _MHA, mask_bits, residual):
-        """residual + out_proj(attention(q_in Wq^T + bq, k, v));  k, v already projected: (1, Nk, H, hd)."""
+    def _mha(self, q_in, k, v, m: _MHA, mask_bits, residual, precise: bool = False):
+        """residual + out_proj(attention(q_in Wq^T + bq, k, v)).  k, v already projected:
+        bf16 mode: (1, Nk, H, hd) tensors for the fused flash-attention kernel;
+        precise:   k = ops.Split (H, Nk, hd), v = ops.Split (H, hd, Nk) [V^T] for the unfused reference-precision attention
+                   S = (q k^T) / sqrt(hd)  ->  masked row softmax (fp32)  ->  P v, all on split operands."""
         d, H = self.hidden_dim, self.num_heads
-        wq, bq = self._slice_w(m.in_proj_weight, 0, d, "wq"), self._slice_w(m.in_proj_bias, 0, d, "bq")
-        q = ops.gemm(q_in, wq, bias=bq).view(1, -1, H, d // H)
-        o = ops.attention(q, k, v, mask_bits=mask_bits)
-        return ops.gemm(o.view(-1, d), w16(m.out_proj.weight), bias=bias_of(m.out_proj), residual=residual)
+        hd = d // H
+        wq, bq = self._slice_w(m.in_proj_weight, 0, d, "wq", precise), self._slice_w(m.in_proj_bias, 0, d, "bq")
+        if not precise:
+            q = ops.gemm(q_in, wq, bias=bq).view(1, -1, H, hd)
+            o = ops.attention(q, k, v, mask_bits=mask_bits)
+            return ops.gemm(o.view(-1, d), w16(m.out_proj.weight), bias=bias_of(m.out_proj), residual=residual)
+        q = ops.gemm(q_in, wq, bias=bq, out_dtype="split")
+        Q, Nk = q.shape[0], k.shape[1]
+        S = torch.empty((H, Q, Nk), device=q.device, dtype=torch.float32)
+        ops.gemm_batched(q.view(Q, H, hd).permute(1, 0, 2), k, alpha=hd ** -0.5, out=S)
+        P = ops.softmax_rows(S, Q, mask_bits)
+        o = ops.Split.empty((Q, d), q.device)
+        ops.gemm_batched(P, v, out=o.view(Q, H, hd).permute(1, 0, 2))
+        return ops.gemm(o, wsplit(m.out_proj.weight), bias=bias_of(m.out_proj), residual=residual, out_dtype="split")
 
     @torch.no_grad()
-    def forward_nhwc(self, src, mask_feats, hw, cls_emb: torch.Tensor,
-                     deep_supervision: bool = True, pooled: Optional[torch.Tensor] = None,
-                     mask_override: Optional[List[torch.Tensor]] = None, portrait=False):
-        """src bf16 (V*h*w, C) = stride-16 features + level_embed, views flattened view-major (batch 1);
-        mask_feats bf16 (V', Hm, Wm, Cm) — the views whose full-resolution masks this call produces (all V, or this
-        rank's shard); pooled bf16 (V*h*w, Cm): centre-pooled mask features of ALL views (computed from mask_feats
-        when omitted).  Returns the reference's output dict (batch dim 1).
+    def forward_nhwc(self, src, mask_feats, hw, cls_emb,
+                     deep_supervision: bool = True, pooled=None,
+                     mask_override: Optional[List[torch.Tensor]] = None, portrait=False, precise: bool = False):
+        """src (V*h*w, C) = stride-16 features + level_embed, views flattened view-major (batch 1);
+        mask_feats (V', Hm, Wm, Cm) — the views whose full-resolution masks this call produces (all V, or this
+        rank's shard); pooled (V*h*w, Cm): centre-pooled mask features of ALL views (computed from mask_feats
+        when omitted).  bf16 tensors, or ops.Split pairs when `precise` (see the module docstring).
+        Returns the reference's output dict (batch dim 1).
         Multi aspect ratio (mask_transformer.py:126-146 with multi_ar=True): src / mask_feats / hw / portrait are
         LISTS with one entry per stack of equally shaped views; the memory tokens of all stacks are concatenated in
         stack order (each with the PE of its own grid) and `pred_masks` comes back as a list with one tensor per stack."""
@@ -270,46 +316,67 @@ class MaskTransformer(nn.Module):
         d, H, Q = self.hidden_dim, self.num_heads, self.num_queries
         hd = d // H
         dev = srcs[0].device
+        act = "split" if precise else torch.bfloat16
+        cat0 = _cat_rows
         # key = memory + pos (pos of view 0 of each stack tiled over its views, :139-141)
-        src_pos = [ops.add_bcast(s_, self._pos(h_, w_, dev, p_)) for s_, (h_, w_), p_ in zip(srcs, hws, ports)]
-        src = srcs[0] if len(srcs) == 1 else torch.cat(srcs, 0)
-        src_pos = src_pos[0] if len(src_pos) == 1 else torch.cat(src_pos, 0)
+        src_pos = [ops.add_bcast(s_, self._pos(h_, w_, dev, p_, precise)) for s_, (h_, w_), p_ in zip(srcs, hws, ports)]
+        src = srcs[0] if len(srcs) == 1 else cat0(srcs)
+        src_pos = src_pos[0] if len(src_pos) == 1 else cat0(src_pos)
         Nk = src.shape[0]
-        wk, bk, wv, bv = self._kv_weights()
-        k_all = ops.gemm(src_pos, wk, bias=bk).view(1, Nk, self.num_layers, H, hd)
-        v_all = ops.gemm(src, wv, bias=bv).view(1, Nk, self.num_layers, H, hd)
+        wk, bk, wv, bv = self._kv_weights(precise)
+        L = self.num_layers
+        if precise:
+            k_all = ops.gemm(src_pos, wk, bias=bk, out_dtype="split")  # (Nk, L*d)
+            vT = ops.Split.empty((L * d, Nk), dev)                      # V^T: the PV GEMM wants its B operand K-major
+            ops.gemm(src, wv, bias=bv, out=vT, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=Nk, batch_stride=0, ldt=2 * Nk)
+            k_of = lambda i: k_all[:, i * d:(i + 1) * d].view(Nk, H, hd).permute(1, 0, 2)  # noqa: E731
+            v_of = lambda i: vT[i * d:(i + 1) * d].view(H, hd, Nk)                          # noqa: E731
+        else:
+            k_all = ops.gemm(src_pos, wk, bias=bk).view(1, Nk, L, H, hd)
+            v_all = ops.gemm(src, wv, bias=bv).view(1, Nk, L, H, hd)
+            k_of = lambda i: k_all[:, :, i]  # noqa: E731
+            v_of = lambda i: v_all[:, :, i]  # noqa: E731
         if pooled is None:
             pl = [ops.center_pool8(mf).view(-1, mf.shape[-1]) for mf in mfs]
-            pooled = pl[0] if len(pl) == 1 else torch.cat(pl, 0)
+            pooled = pl[0] if len(pl) == 1 else cat0(pl)
         mask_feats = mfs if multi else mfs[0]
-        qe = b16(self.query_embed.weight)
-        output = b16(self.query_feat.weight)
+        qe = psplit(self.query_embed.weight) if precise else b16(self.query_embed.weight)
+        output = psplit(self.query_feat.weight) if precise else b16(self.query_feat.weight)
         pred_cls, pred_msk = [], []
-        cls, msk, bits = self.prediction_heads(output, mask_feats, pooled, cls_emb, want_masks=deep_supervision)
+        cls, msk, bits = self.prediction_heads(output, mask_feats, pooled, cls_emb, want_masks=deep_supervision, precise=precise)
         if deep_supervision:
             pred_cls.append(cls)
             pred_msk.append(msk)
-        for i in range(self.num_layers):
+        for i in range(L):
             ca, sa, ff = self.cross_attn_layers[i], self.self_attn_layers[i], self.ffn_layers[i]
+            W = wsplit if precise else w16
             # masked cross-attention (post-norm): tgt = LN(tgt + MHA(tgt + query_pos, memory + pos, memory))
             if mask_override is not None:  # test hook: force the block mask of layer i (isolates threshold flips)
                 bits = mask_override[i]
-            t = self._mha(ops.add_bcast(output, qe), k_all[:, :, i], v_all[:, :, i], ca.multihead_attn, bits, output)
+            t = self._mha(ops.add_bcast(output, qe), k_of(i), v_of(i), ca.multihead_attn, bits, output, precise)
             output = ops.layernorm(t, f32(ca.norm.weight), f32(ca.norm.bias), 1e-5)
             # self-attention: q = k = tgt + query_pos, v = tgt
             m = sa.self_attn
             qk_in = ops.add_bcast(output, qe)
-            kk = ops.gemm(qk_in, self._slice_w(m.in_proj_weight, d, 2 * d, "wk"), bias=self._slice_w(m.in_proj_bias, d, 2 * d, "bk"))
-            vv = ops.gemm(output, self._slice_w(m.in_proj_weight, 2 * d, 3 * d, "wv"), bias=self._slice_w(m.in_proj_bias, 2 * d, 3 * d, "bv"))
-            t = self._mha(qk_in, kk.view(1, Q, H, hd), vv.view(1, Q, H, hd), m, None, output)
+            wk_s, bk_s = self._slice_w(m.in_proj_weight, d, 2 * d, "wk", precise), self._slice_w(m.in_proj_bias, d, 2 * d, "bk")
+            wv_s, bv_s = self._slice_w(m.in_proj_weight, 2 * d, 3 * d, "wv", precise), self._slice_w(m.in_proj_bias, 2 * d, 3 * d, "bv")
+            if precise:
+                kk = ops.gemm(qk_in, wk_s, bias=bk_s, out_dtype="split").view(Q, H, hd).permute(1, 0, 2)
+                vvT = ops.Split.empty((d, Q), dev)
+                ops.gemm(output, wv_s, bias=bv_s, out=vvT, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=Q, batch_stride=0, ldt=2 * Q)
+                t = self._mha(qk_in, kk, vvT.view(H, hd, Q), m, None, output, True)
+            else:
+                kk = ops.gemm(qk_in, wk_s, bias=bk_s)
+                vv = ops.gemm(output, wv_s, bias=bv_s)
+                t = self._mha(qk_in, kk.view(1, Q, H, hd), vv.view(1, Q, H, hd), m, None, output)
             output = ops.layernorm(t, f32(sa.norm.weight), f32(sa.norm.bias), 1e-5)
             # FFN
-            hmid = ops.gemm(output, w16(ff.linear1.weight), bias=bias_of(ff.linear1), act=ops.ACT_RELU)
-            t = ops.gemm(hmid, w16(ff.linear2.weight), bias=bias_of(ff.linear2), residual=output)
+            hmid = ops.gemm(output, W(ff.linear1.weight), bias=bias_of(ff.linear1), act=ops.ACT_RELU, out_dtype=act)
+            t = ops.gemm(hmid, W(ff.linear2.weight), bias=bias_of(ff.linear2), residual=output, out_dtype=act)
             output = ops.layernorm(t, f32(ff.norm.weight), f32(ff.norm.bias), 1e-5)
-            last = i == self.num_layers - 1
+            last = i == L - 1
             cls, msk, bits = self.prediction_heads(output, mask_feats, None if last else pooled, cls_emb,
-                                                   want_masks=deep_supervision or last)
+                                                   want_masks=deep_supervision or last, precise=precise)
             if deep_supervision or last:
                 pred_cls.append(cls)
                 pred_msk.append(msk)
@@ -318,14 +385,21 @@ class MaskTransformer(nn.Module):
             "pred_logits": pred_cls[-1][None],
             "pred_masks": b1(pred_msk[-1]),
             "aux_outputs": [{"pred_logits": a[None], "pred_masks": b1(b_)} for a, b_ in zip(pred_cls[:-1], pred_msk[:-1])],
-            "out_queries": output.view(Q, 1, d),
+            "out_queries": (ops.convert(output, torch.empty((Q, d), device=dev, dtype=torch.float32)) if precise else output).view(Q, 1, d),
         }
+
+
+def _cat_rows(parts):
+    """Row-wise concatenation of bf16 tensors or packed ops.Split matrices (pure data movement)."""
+    if isinstance(parts[0], ops.Split):
+        return _as_split(torch.cat([p_.full() for p_ in parts], 0))
+    return torch.cat(parts, 0)
 
 
 class PanopticDecoder(nn.Module):
     def __init__(self, input_mixer=None, upscaler=None, fpn_dim=[768], hidden_dim=768, mask_dim=256, ff_dim=2048,
                  num_queries=200, num_heads=8, dec_layers=6, text_encoder="siglip", fixed_vocab=True,
-                 label_mode="sigmoid", two_stage=False, landscape_only=True, deep_supervision=True):
+                 label_mode="sigmoid", two_stage=False, landscape_only=True, deep_supervision=True, precision="fp32"):
         super().__init__()
         assert upscaler is not None, "Upscaler module must be provided"
         assert label_mode == "sigmoid" and not two_stage
@@ -337,28 +411,53 @@ class PanopticDecoder(nn.Module):
                                                 dec_layers, lang_dim=self.text_encoder.embed_dim,
                                                 num_feature_levels=len(fpn_dim), landscape_only=landscape_only)
         self.deep_supervision = deep_supervision
+        # "fp32": the reference's policy for this head (panst3r.py:236-245) on split-bf16 tensor-core operands;
+        # "bf16": plain bf16 operands + fused flash attention (see the module docstring)
+        assert precision in ("fp32", "bf16")
+        self.precision = precision
+
+    @property
+    def precise(self) -> bool:
+        return self.precision == "fp32"
 
     @torch.no_grad()
     def forward(self, in_feats, in_imgs, pos, true_shape, classes, max_bs=None, outdevice=None, memory_queries=None,
                 multi_ar=False, cat_feats: Optional[torch.Tensor] = None):
         """Reference signature (panoptic_decoder.py:41).  in_feats = (x_enc, y_dec, x_dino), each (B, V, N, C_i);
         `cat_feats`: optional pre-concatenated bf16 (B, V, N, 2816) buffer the producers already wrote into
-        (then in_feats is ignored).  B must be 1 on the CUDA path."""
+        (then in_feats is ignored)."""
         if multi_ar:
             return self._forward_multi_ar(in_feats, in_imgs, pos, true_shape, classes, outdevice, memory_queries, cat_feats)
+        B = cat_feats.shape[0] if cat_feats is not None else in_feats[0].shape[0]
+        if B > 1:  # scenes are independent: one pass per scene, outputs concatenated along the batch dimension
+            from ..panst3r import merge_panouts
+            ts = true_shape.cpu() if torch.is_tensor(true_shape) and true_shape.is_cuda else true_shape
+            outs = []
+            for b in range(B):
+                sl = slice(b, b + 1)
+                mq = None if memory_queries is None else memory_queries[:, sl]
+                outs.append(self.forward(None if in_feats is None else tuple(f[sl] for f in in_feats), in_imgs[sl],
+                                         None if pos is None else pos[sl], ts[sl], classes, max_bs=max_bs, outdevice=outdevice,
+                                         memory_queries=mq, cat_feats=None if cat_feats is None else cat_feats[sl]))
+            return merge_panouts(outs)
+        pr = self.precise
         src, mask_f, grid, portrait, dev = self._stack_features(in_feats, in_imgs, true_shape, cat_feats)
         mt = self.mask_transformer
-        cls_emb = self.text_encoder(classes, device=dev)
+        cls_emb = self.text_encoder(classes, device=dev, precise=pr)
         if memory_queries is None:
-            out = mt.forward_nhwc(src, mask_f, grid, cls_emb, deep_supervision=self.deep_supervision, portrait=portrait)
+            out = mt.forward_nhwc(src, mask_f, grid, cls_emb, deep_supervision=self.deep_supervision, portrait=portrait,
+                                  precise=pr)
         else:
-            logits, masks, _ = mt.prediction_heads(self._queries(memory_queries), mask_f, None, cls_emb, want_masks=True)
+            logits, masks, _ = mt.prediction_heads(self._queries(memory_queries), mask_f, None, cls_emb, want_masks=True,
+                                                   precise=pr)
             out = {"pred_logits": logits[None], "pred_masks": masks[None]}
         return self._to_device(out, outdevice, dev)
 
     def _queries(self, memory_queries):
         mt = self.mask_transformer
         q = memory_queries.reshape(mt.num_queries, mt.hidden_dim)
+        if self.precise:
+            return ops.Split.from_float(q.contiguous() if q.dtype in (torch.float32, torch.bfloat16) else q.float().contiguous())
         return q if q.dtype == torch.bfloat16 else ops.to_bf16(q.float().contiguous())
 
     @staticmethod
@@ -377,30 +476,35 @@ class PanopticDecoder(nn.Module):
     def _stack_features(self, in_feats, in_imgs, true_shape, cat_feats):
         """One stack of equally shaped views -> (stride-16 tokens + level_embed (V*N, 768), mask features
         (V, Hm, Wm, Cm) pixel-major, token grid, portrait flag, device), both in the landscape storage convention."""
+        pr = self.precise
         if cat_feats is None:
-            # producers that did not write into a shared buffer: concatenate (pure data movement)
-            parts = [t if t.dtype == torch.bfloat16 else ops.to_bf16(t.float().contiguous()) for t in in_feats]
-            cat_feats = torch.cat(parts, dim=-1)
+            # producers that did not write into a shared buffer: concatenate (pure data movement).  fp32 features keep
+            # their precision through the reference-precision head (split pairs); bf16 features are exact as they are.
+            if pr and any(t.dtype != torch.bfloat16 for t in in_feats):
+                cat_feats = torch.cat([t.float() for t in in_feats], dim=-1)
+            else:
+                parts = [t if t.dtype == torch.bfloat16 else ops.to_bf16(t.float().contiguous()) for t in in_feats]
+                cat_feats = torch.cat(parts, dim=-1)
         B, V, N, Cc = cat_feats.shape
         if B != 1:
-            raise ops._l.Pst3rError("CUDA PanopticDecoder supports batch size 1 (one scene per call)")
+            raise ops._l.Pst3rError("_stack_features handles one scene (PanopticDecoder.forward loops over the batch)")
         H, W = _hw(true_shape)  # true size; portrait (H > W) views are predicted in their true orientation and
         portrait = H > W        # returned in the landscape storage convention (utils.transpose_to_landscape, dims=(2, 3))
         P = self.upscaler.patch_size
         hs, ws = H // P, W // P
         dev = cat_feats.device
-        x = cat_feats.reshape(V * N, Cc)
-        if self.input_mixer is not None:
-            x = self.input_mixer.forward_rows(x, V, hs, ws)
+        x = _head_input(cat_feats.reshape(V * N, Cc), pr)
         mt = self.mask_transformer
+        if self.input_mixer is not None:
+            x = self.input_mixer.forward_rows(x, V, hs, ws, precise=pr)
         if isinstance(self.upscaler, PixelShuffleUpscaler):
-            src, mask_f = self.upscaler.forward_nhwc(x, V, hs, ws, f16_extra_bias=mt.level_embed.weight)
+            src, mask_f = self.upscaler.forward_nhwc(x, V, hs, ws, f16_extra_bias=mt.level_embed.weight, precise=pr)
         else:
             imgs_t, _, _ = oriented(in_imgs.reshape(V, 3, *in_imgs.shape[-2:]), true_shape)
-            src, mask_f = self.upscaler.forward_nhwc(x, imgs_t, V, hs, ws, f16_extra_bias=mt.level_embed.weight)
+            src, mask_f = self.upscaler.forward_nhwc(x, imgs_t, V, hs, ws, f16_extra_bias=mt.level_embed.weight, precise=pr)
         if portrait:  # swap the spatial dims of both outputs (pure data movement); the head then sees a (ws, hs) grid
-            src = src.view(V, hs, ws, -1).transpose(1, 2).contiguous().view(V * N, -1)
-            mask_f = mask_f.transpose(1, 2).contiguous()
+            src = _swap_grid(src, V, hs, ws)
+            mask_f = _swap_grid(mask_f, V, mask_f.shape[1], mask_f.shape[2], keep4d=True)
             hs, ws = ws, hs
         return src, mask_f, (hs, ws), portrait, dev
 
@@ -410,20 +514,32 @@ class PanopticDecoder(nn.Module):
         per stack.  LoftUp's batch-global MinMaxScaler stays per stack, as in the reference (each stack is one
         `batched_map` call, utils.py:90-160)."""
         n_st = len(true_shape)
+        pr = self.precise
         cats = cat_feats if cat_feats is not None else [None] * n_st
         feats = [tuple(f[i] for f in in_feats) if in_feats is not None else None for i in range(n_st)]
         st = [self._stack_features(feats[i], in_imgs[i], true_shape[i], cats[i]) for i in range(n_st)]
         dev = st[0][4]
         mt = self.mask_transformer
-        cls_emb = self.text_encoder(classes, device=dev)
+        cls_emb = self.text_encoder(classes, device=dev, precise=pr)
         if memory_queries is None:
             out = mt.forward_nhwc([s_[0] for s_ in st], [s_[1] for s_ in st], [s_[2] for s_ in st], cls_emb,
-                                  deep_supervision=self.deep_supervision, portrait=[s_[3] for s_ in st])
+                                  deep_supervision=self.deep_supervision, portrait=[s_[3] for s_ in st], precise=pr)
         else:
             logits, masks, _ = mt.prediction_heads(self._queries(memory_queries), [s_[1] for s_ in st], None, cls_emb,
-                                                   want_masks=True)
+                                                   want_masks=True, precise=pr)
             out = {"pred_logits": logits[None], "pred_masks": [m_[None] for m_ in masks]}
         return self._to_device(out, outdevice, dev)
+
+
+def _swap_grid(t, V: int, gh: int, gw: int, keep4d: bool = False):
+    """(V*gh*gw, C) rows or (V, gh, gw, C) map -> the same tokens on the transposed (gw, gh) grid (pure data movement);
+    bf16 tensors or packed ops.Split matrices."""
+    if isinstance(t, ops.Split):
+        buf = t.full().reshape(V, gh, gw, -1).transpose(1, 2).contiguous()
+        out = _as_split(buf if keep4d else buf.view(V * gh * gw, -1))
+        return out
+    buf = t.reshape(V, gh, gw, -1).transpose(1, 2).contiguous()
+    return buf if keep4d else buf.view(V * gh * gw, -1)
 
 
 # =====================================================================================================
@@ -442,9 +558,11 @@ class InputMixer(nn.Module):
         self.mixer_norm = nn.LayerNorm(hidden_dim)
 
     @torch.no_grad()
-    def forward_rows(self, x: torch.Tensor, V: int, hs: int, ws: int) -> torch.Tensor:
+    def forward_rows(self, x, V: int, hs: int, ws: int, precise: bool = False) -> torch.Tensor:
         """x bf16 rows (V*hs*ws, in_dim) -> bf16 rows (V*hs*ws, hidden_dim)"""
         from .common import pos_grid, rope_table, vit_block
+        if isinstance(x, ops.Split):  # the mixer blocks run on bf16 operands (see PanopticDecoder.precision)
+            x = ops.convert(x, torch.empty(x.shape, device=x.device, dtype=torch.bfloat16))
         N = hs * ws
         _, pos32 = pos_grid(hs, ws, x.device)
         rope = (rope_table(max(hs, ws), self.hidden_dim // self.num_heads, 100.0, x.device), pos32.repeat(V, 1))
@@ -550,7 +668,7 @@ class LoftUpUpscaler(nn.Module):
 
     @torch.no_grad()
     def forward_nhwc(self, feats: torch.Tensor, imgs: torch.Tensor, b: int, hs: int, ws: int,
-                     f16_extra_bias: Optional[torch.Tensor] = None):
+                     f16_extra_bias: Optional[torch.Tensor] = None, precise: bool = False):
         """feats bf16 rows (b*hs*ws, input_dim) (InputMixer output), imgs fp32 (b,3,H,W) ->
         (f16 bf16 (b*hs*ws, input_dim) = patch_embed(feats) [+ level_embed], mask feats bf16 (b, H/2, W/2, dim))."""
         dev = feats.device
@@ -593,6 +711,8 @@ class LoftUpUpscaler(nn.Module):
             h = ops.gemm(h, w16(blk.mlp.fc1.weight), bias=bias_of(blk.mlp.fc1), act=ops.ACT_GELU)
             x = ops.gemm(h, w16(blk.mlp.fc2.weight), bias=bias_of(blk.mlp.fc2), residual=x, out=x)
         x = ops.layernorm(x, f32(self.ca_transformer_norm.weight), f32(self.ca_transformer_norm.bias), 1e-5)
+        if precise:  # hand split pairs to the reference-precision query decoder / mask einsum
+            return ops.Split.from_float(f16), ops.Split.from_float(x).view(b, Hh, Wh, D)
         return f16, x.view(b, Hh, Wh, D)
 
     @torch.no_grad()

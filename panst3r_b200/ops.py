@@ -55,6 +55,115 @@ def _rows2d(t: torch.Tensor, name: str) -> Tuple[int, int, int]:
     return t.shape[0], t.shape[1], t.stride(0)
 
 
+KIND_BF16, KIND_F32, KIND_SPLIT = 0, 1, 2
+
+
+class Split:
+    """Reference-precision matrix for the panoptic head (the reference runs it in fp32, panst3r.py:236-245): every value
+    x is held as two bf16 numbers, hi = bf16(x) and lo = bf16(x - hi) (16 mantissa bits), so that fp32-grade products
+    run on the bf16 tensor cores as A_hi B_hi + A_lo B_hi + A_hi B_lo.  `hi` is a bf16 view [..., cols] (contiguous
+    last dim); the lo parts live `lo_off` elements after their hi parts in the same storage (a fresh matrix is one
+    [rows, 2*cols] buffer, rows = [hi | lo], lo_off = cols).  Row / column slices keep lo_off."""
+    __slots__ = ("hi", "lo_off")
+
+    def __init__(self, hi: torch.Tensor, lo_off: int):
+        self.hi, self.lo_off = hi, int(lo_off)
+
+    @staticmethod
+    def empty(shape, device) -> "Split":
+        *lead, cols = shape
+        buf = torch.empty((*lead, 2 * cols), device=device, dtype=torch.bfloat16)
+        return Split(buf[..., :cols], cols)
+
+    @staticmethod
+    def from_float(x: torch.Tensor) -> "Split":
+        """fp32 / bf16 CUDA tensor -> split copy (one conversion kernel)."""
+        out = Split.empty(x.shape, x.device)
+        convert(x, out)
+        return out
+
+    @property
+    def lo(self) -> torch.Tensor:
+        return self.hi.as_strided(self.hi.shape, self.hi.stride(), self.hi.storage_offset() + self.lo_off)
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    @property
+    def cols(self) -> int:
+        return self.hi.shape[-1]
+
+    def float(self) -> torch.Tensor:
+        return self.hi.float() + self.lo.float()
+
+    def view(self, *shape) -> "Split":
+        """Reshape (the lo parts follow their hi parts at the same offset, so any view that keeps elements in place
+        within their rows is valid; the last dim may be split into (heads, hd))."""
+        return Split(self.hi.view(*shape), self.lo_off)
+
+    def permute(self, *dims) -> "Split":
+        return Split(self.hi.permute(*dims), self.lo_off)
+
+    def __getitem__(self, idx) -> "Split":
+        return Split(self.hi[idx], self.lo_off)
+
+    def full(self) -> torch.Tensor:
+        """The underlying bf16 [..., 2*cols] rows [hi | lo] of a packed matrix (for pure data movement)."""
+        if not self.packed():
+            raise _l.Pst3rError("Split.full: not a packed [hi | lo] matrix")
+        return self.hi.as_strided((*self.hi.shape[:-1], 2 * self.cols), self.hi.stride())
+
+    def packed(self) -> bool:
+        """rows are exactly [hi(cols) | lo(cols)] (what the row kernels expect)"""
+        return self.lo_off == self.cols
+
+
+def _kind(t) -> int:
+    if isinstance(t, Split):
+        return KIND_SPLIT
+    if t.dtype == torch.float32:
+        return KIND_F32
+    if t.dtype == torch.bfloat16:
+        return KIND_BF16
+    raise _l.Pst3rError(f"unsupported dtype {t.dtype}")
+
+
+def _base(t) -> torch.Tensor:
+    return t.hi if isinstance(t, Split) else t
+
+
+def _need_cuda(t, name: str):
+    if not _base(t).is_cuda:
+        raise _l.Pst3rError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+
+
+def _packed(t, name: str):
+    if isinstance(t, Split) and not t.packed():
+        raise _l.Pst3rError(f"{name}: split rows must be [hi | lo] with lo_off == cols")
+
+
+def _dkind(out_dtype) -> int:
+    """KIND_* of an out_dtype argument (torch.bfloat16 / torch.float32 / "split")."""
+    if out_dtype == "split":
+        return KIND_SPLIT
+    if out_dtype is torch.float32:
+        return KIND_F32
+    if out_dtype is torch.bfloat16:
+        return KIND_BF16
+    raise _l.Pst3rError(f"unsupported out_dtype {out_dtype}")
+
+
+def _new(shape, kind: int, device):
+    if kind == KIND_SPLIT:
+        return Split.empty(shape, device)
+    return torch.empty(shape, device=device, dtype=torch.float32 if kind == KIND_F32 else torch.bfloat16)
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          col_scale: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, alpha: float = 1.0,
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
@@ -64,37 +173,50 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          out_ld: int = 0, ln: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None,
          stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epilogue(a @ w.T).  a: bf16 [..., K] (row-strided), w: bf16 [N, K].
+    Reference-precision mode: w is a `Split` weight; a is a `Split` (three product terms) or a plain bf16 tensor (exactly
+    representable inputs, two terms); `out` / `residual` may be `Split`s, out_dtype="split" allocates one.
     PLAIN store with rows_per_batch > 0: `out` is only a base pointer, rows are remapped (pass out_ld).
     ln = (stats fp32 [M, K/32, 2], colsum fp32 [N], eps): LayerNorm(a) folded into the GEMM (w = gamma-scaled weights,
     bias includes W beta); stats_out fp32 [M, N/32, 2]: per-chunk (sum, sum^2) of the stored bf16 rows for the next fold."""
     global launches
     lib = _l.load()
-    _need(a, torch.bfloat16, "gemm.a")
-    _need(w, torch.bfloat16, "gemm.w")
-    M, K, lda = _rows2d(a, "gemm.a")
-    N, K2, ldb = _rows2d(w, "gemm.w")
+    e = _l.GemmEpilogue()
+    if isinstance(w, Split):
+        e.split_terms = 3 if isinstance(a, Split) else 2
+        e.a_lo_off = a.lo_off if isinstance(a, Split) else 0
+        e.b_lo_off = w.lo_off
+    elif isinstance(a, Split):
+        raise _l.Pst3rError("gemm: a split activation needs split weights")
+    ab, wb = _base(a), _base(w)
+    _need(ab, torch.bfloat16, "gemm.a")
+    _need(wb, torch.bfloat16, "gemm.w")
+    M, K, lda = _rows2d(ab, "gemm.a")
+    N, K2, ldb = _rows2d(wb, "gemm.w")
     if K != K2:
         raise _l.Pst3rError(f"gemm: K mismatch {K} vs {K2}")
-    e = _l.GemmEpilogue()
+    if out is None and store_mode == STORE_PLAIN and rows_per_batch == 0:
+        if out_dtype == "split":
+            out = Split.empty((*ab.shape[:-1], N), ab.device)
+        else:
+            out = torch.empty((*ab.shape[:-1], N), device=ab.device, dtype=out_dtype)
+    if out is None:
+        raise _l.Pst3rError("gemm: out must be given for remapped / non-plain store modes")
+    ob = _base(out)
     if store_mode == STORE_PLAIN and rows_per_batch > 0:
-        if out is None or out_ld <= 0:
+        if out_ld <= 0:
             raise _l.Pst3rError("gemm: remapped PLAIN store needs out and out_ld")
         e.ldo = out_ld
     elif store_mode == STORE_PLAIN:
-        if out is None:
-            out = torch.empty((*a.shape[:-1], N), device=a.device, dtype=out_dtype)
-        _, oc, ldo = _rows2d(out, "gemm.out")
+        _, oc, ldo = _rows2d(ob, "gemm.out")
         if oc != N:
             raise _l.Pst3rError("gemm: out has wrong number of columns")
         e.ldo = ldo
     else:
-        if out is None:
-            raise _l.Pst3rError("gemm: out must be given for non-plain store modes")
-        e.ldo = out.stride(-2) if out.dim() >= 2 else 0
-    e.out = out.data_ptr()
-    e.out_f32 = 1 if out.dtype == torch.float32 else 0
-    if out.dtype not in (torch.float32, torch.bfloat16):
-        raise _l.Pst3rError("gemm: out must be bf16 or fp32")
+        e.ldo = ob.stride(-2) if ob.dim() >= 2 else 0
+    e.out = ob.data_ptr()
+    e.out_kind = _kind(out)
+    if isinstance(out, Split):
+        e.out_lo_off = out.lo_off
     e.act = act
     if bias is not None:
         _need(bias, torch.float32, "gemm.bias")
@@ -103,11 +225,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     e.bias = _ptr(bias)
     e.col_scale = _ptr(col_scale)
     if residual is not None:
-        _need(residual, torch.bfloat16, "gemm.residual")
-        _, _, ldr = _rows2d(residual, "gemm.residual")
-        e.residual = residual.data_ptr()
+        rb = _base(residual)
+        _need_cuda(residual, "gemm.residual")
+        _, _, ldr = _rows2d(rb, "gemm.residual")
+        e.residual = rb.data_ptr()
         e.ldr = ldr
         e.res_mod_rows = res_mod_rows
+        e.res_kind = _kind(residual)
+        if isinstance(residual, Split):
+            e.res_lo_off = residual.lo_off
     e.alpha = alpha
     e.store_mode = store_mode
     e.rows_per_batch, e.batch_stride, e.ldt = rows_per_batch, batch_stride, ldt
@@ -130,37 +256,46 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         _need(cs, torch.float32, "gemm.rope_cs")
         _need(pos, torch.int32, "gemm.rope_pos")
         e.rope_cs, e.rope_pos, e.rope_cols, e.rope_maxpos = cs.data_ptr(), pos.data_ptr(), rope_cols, cs.shape[0]
-    _l.check(lib.pst3r_gemm_bf16(a.data_ptr(), lda, w.data_ptr(), ldb, M, N, K, C.byref(e), _stream()), "pst3r_gemm_bf16")
+    _l.check(lib.pst3r_gemm_bf16(ab.data_ptr(), lda, wb.data_ptr(), ldb, M, N, K, C.byref(e), _stream()), "pst3r_gemm_bf16")
     launches += 1
     return out
 
 
-def gemm_batched(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
-                 out: torch.Tensor) -> torch.Tensor:
-    """out[b] = act(a[b] @ w[b].T + bias[b]) for b < L in ONE launch.  a: bf16 [L, M, K], w: bf16 [L, N, K],
-    bias: fp32 [L, N], out: bf16/fp32 [L, M, N]; any batch / row strides, contiguous last dim."""
+def gemm_batched(a, w, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, alpha: float = 1.0, out):
+    """out[b] = act(alpha * a[b] @ w[b].T + bias[b]) for b < L in ONE launch.  a: bf16 [L, M, K], w: bf16 [L, N, K],
+    bias: fp32 [L, N], out: bf16/fp32 [L, M, N]; any batch / row strides, contiguous last dim.  `Split` operands /
+    output select the reference-precision mode (per-head QK^T and PV products of the query decoder's attention)."""
     global launches
     lib = _l.load()
-    _need(a, torch.bfloat16, "gemm_batched.a")
-    _need(w, torch.bfloat16, "gemm_batched.w")
-    if a.dim() != 3 or w.dim() != 3 or out.dim() != 3 or a.stride(-1) != 1 or w.stride(-1) != 1 or out.stride(-1) != 1:
-        raise _l.Pst3rError("gemm_batched: expected 3-D operands with contiguous last dim")
-    L, M, K = a.shape
-    L2, N, K2 = w.shape
-    if L2 != L or K2 != K or tuple(out.shape) != (L, M, N):
-        raise _l.Pst3rError(f"gemm_batched: shape mismatch a{tuple(a.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
-    if out.dtype not in (torch.float32, torch.bfloat16) or not out.is_cuda:
-        raise _l.Pst3rError("gemm_batched: out must be CUDA bf16 or fp32")
     e = _l.GemmEpilogue()
-    e.out, e.ldo, e.out_f32, e.act, e.alpha, e.store_mode = out.data_ptr(), out.stride(1), int(out.dtype == torch.float32), act, 1.0, STORE_PLAIN
+    if isinstance(w, Split):
+        e.split_terms = 3 if isinstance(a, Split) else 2
+        e.a_lo_off = a.lo_off if isinstance(a, Split) else 0
+        e.b_lo_off = w.lo_off
+    elif isinstance(a, Split):
+        raise _l.Pst3rError("gemm_batched: a split activation needs split weights")
+    ab, wb, ob = _base(a), _base(w), _base(out)
+    _need(ab, torch.bfloat16, "gemm_batched.a")
+    _need(wb, torch.bfloat16, "gemm_batched.w")
+    if ab.dim() != 3 or wb.dim() != 3 or ob.dim() != 3 or ab.stride(-1) != 1 or wb.stride(-1) != 1 or ob.stride(-1) != 1:
+        raise _l.Pst3rError("gemm_batched: expected 3-D operands with contiguous last dim")
+    L, M, K = ab.shape
+    L2, N, K2 = wb.shape
+    if L2 != L or K2 != K or tuple(ob.shape) != (L, M, N):
+        raise _l.Pst3rError(f"gemm_batched: shape mismatch a{tuple(ab.shape)} w{tuple(wb.shape)} out{tuple(ob.shape)}")
+    if ob.dtype not in (torch.float32, torch.bfloat16) or not ob.is_cuda:
+        raise _l.Pst3rError("gemm_batched: out must be CUDA bf16 or fp32")
+    e.out, e.ldo, e.out_kind, e.act, e.alpha, e.store_mode = ob.data_ptr(), ob.stride(1), _kind(out), act, alpha, STORE_PLAIN
+    if isinstance(out, Split):
+        e.out_lo_off = out.lo_off
     bias_bs = 0
     if bias is not None:
         _need(bias, torch.float32, "gemm_batched.bias")
         if tuple(bias.shape) != (L, N) or bias.stride(1) != 1:
             raise _l.Pst3rError("gemm_batched: bias must be [L, N]")
         e.bias, bias_bs = bias.data_ptr(), bias.stride(0)
-    _l.check(lib.pst3r_gemm_bf16_batched(a.data_ptr(), a.stride(1), a.stride(0), w.data_ptr(), w.stride(1), w.stride(0), M, N, K,
-                                         L, C.byref(e), out.stride(0), bias_bs, _stream()), "pst3r_gemm_bf16_batched")
+    _l.check(lib.pst3r_gemm_bf16_batched(ab.data_ptr(), ab.stride(1), ab.stride(0), wb.data_ptr(), wb.stride(1), wb.stride(0), M, N, K,
+                                         L, C.byref(e), ob.stride(0), bias_bs, _stream()), "pst3r_gemm_bf16_batched")
     launches += 1
     return out
 
@@ -226,7 +361,12 @@ _ws_cache = {}
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    """Scratch buffer (split-KV partials, GroupNorm statistics) of the CURRENT stream.  One buffer per (device,
+    stream): DINOv2 runs on a side stream next to the encoder / memory build, and two kernels that both split their
+    KV range must never share partial-result storage.  A buffer is allocated while its stream is current and only
+    ever used on it, so the caching allocator's stream-ordered reuse keeps a replaced (grown) buffer alive until the
+    kernels queued on it have run."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
     t = _ws_cache.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
@@ -279,14 +419,18 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optio
     return out
 
 
-def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
-              add: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-              out_dtype: torch.dtype = torch.bfloat16, sum_out: Optional[torch.Tensor] = None,
-              x_rows: Optional[Tuple[int, int, int, int, int]] = None) -> torch.Tensor:
-    """x_rows = (rows, dim, ldx, rows_per_batch, batch_stride): x is only a base pointer with remapped rows."""
+def layernorm(x, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
+              add=None, out=None, out_dtype=torch.bfloat16, sum_out=None,
+              x_rows: Optional[Tuple[int, int, int, int, int]] = None):
+    """y = LN(x [+ add]) * gamma + beta.  x / add / out / sum_out: bf16, fp32 or `Split` (out_dtype="split" allocates one;
+    a Split input defaults to a Split output).
+    x_rows = (rows, dim, ldx, rows_per_batch, batch_stride): x is only a base pointer with remapped rows."""
     global launches
     lib = _l.load()
-    if x.dtype not in (torch.bfloat16, torch.float32) or not x.is_cuda:
+    xb = _base(x)
+    _need_cuda(x, "layernorm.x")
+    _packed(x, "layernorm.x")
+    if xb.dtype not in (torch.bfloat16, torch.float32):
         raise _l.Pst3rError("layernorm.x: expected CUDA bf16/fp32")
     x_rpb, x_bs = 0, 0
     if x_rows is not None:
@@ -294,23 +438,31 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         if out is None:
             raise _l.Pst3rError("layernorm: remapped input needs out")
     else:
-        rows, dim, ldx = _rows2d(x, "layernorm.x")
+        rows, dim, ldx = _rows2d(xb, "layernorm.x")
     _need(gamma, torch.float32, "layernorm.gamma")
     _need(beta, torch.float32, "layernorm.beta")
     if out is None:
-        out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
-    _, _, ldy = _rows2d(out, "layernorm.out")
-    ld_add = 0
+        if isinstance(x, Split) and out_dtype is torch.bfloat16:
+            out_dtype = "split"
+        out = _new(xb.shape, _dkind(out_dtype), xb.device)
+    _packed(out, "layernorm.out")
+    _, _, ldy = _rows2d(_base(out), "layernorm.out")
+    ld_add, add_kind = 0, 0
     if add is not None:
-        _need(add, torch.bfloat16, "layernorm.add")
-        _, _, ld_add = _rows2d(add, "layernorm.add")
-    ld_sum = 0
+        _need_cuda(add, "layernorm.add")
+        _packed(add, "layernorm.add")
+        _, _, ld_add = _rows2d(_base(add), "layernorm.add")
+        add_kind = _kind(add)
+    ld_sum, sum_kind = 0, 0
     if sum_out is not None:
-        _need(sum_out, torch.bfloat16, "layernorm.sum_out")
-        _, _, ld_sum = _rows2d(sum_out, "layernorm.sum_out")
-    _l.check(lib.pst3r_layernorm(x.data_ptr(), int(x.dtype == torch.float32), ldx, _ptr(add), ld_add, gamma.data_ptr(),
-                                 beta.data_ptr(), eps, out.data_ptr(), int(out.dtype == torch.float32), ldy,
-                                 _ptr(sum_out), ld_sum, rows, dim, x_rpb, x_bs, _stream()), "pst3r_layernorm")
+        _need_cuda(sum_out, "layernorm.sum_out")
+        _packed(sum_out, "layernorm.sum_out")
+        _, _, ld_sum = _rows2d(_base(sum_out), "layernorm.sum_out")
+        sum_kind = _kind(sum_out)
+    _l.check(lib.pst3r_layernorm(xb.data_ptr(), _kind(x), ldx, _ptr(None if add is None else _base(add)), add_kind, ld_add,
+                                 gamma.data_ptr(), beta.data_ptr(), eps, _base(out).data_ptr(), _kind(out), ldy,
+                                 _ptr(None if sum_out is None else _base(sum_out)), sum_kind, ld_sum, rows, dim, x_rpb, x_bs,
+                                 _stream()), "pst3r_layernorm")
     launches += 1
     return out
 
@@ -330,21 +482,67 @@ def rope2d_(tokens: torch.Tensor, pos: torch.Tensor, base: float = 100.0, fwd: f
     return tokens
 
 
-def add_bcast(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[r] = a[r] + b[r % b_rows] on bf16 row matrices."""
+def add_bcast(a, b, out=None):
+    """out[r] = a[r] + b[r % b_rows] on row matrices of any kind (bf16 / fp32 / Split); out defaults to a's kind."""
     global launches
     lib = _l.load()
-    _need(a, torch.bfloat16, "add_bcast.a")
-    _need(b, torch.bfloat16, "add_bcast.b")
-    rows, cols, lda = _rows2d(a, "add_bcast.a")
-    brows, bcols, ldb = _rows2d(b, "add_bcast.b")
+    for t, n in ((a, "a"), (b, "b")):
+        _need_cuda(t, f"add_bcast.{n}")
+        _packed(t, f"add_bcast.{n}")
+    rows, cols, lda = _rows2d(_base(a), "add_bcast.a")
+    brows, bcols, ldb = _rows2d(_base(b), "add_bcast.b")
     if bcols != cols:
         raise _l.Pst3rError("add_bcast: column mismatch")
     if out is None:
-        out = torch.empty(a.shape, device=a.device, dtype=torch.bfloat16)
-    _, _, ldo = _rows2d(out, "add_bcast.out")
-    _l.check(lib.pst3r_add_bcast(a.data_ptr(), lda, b.data_ptr(), ldb, brows, out.data_ptr(), ldo, rows, cols, _stream()),
-             "pst3r_add_bcast")
+        out = _new(_base(a).shape, _kind(a), _base(a).device)
+    _packed(out, "add_bcast.out")
+    _, _, ldo = _rows2d(_base(out), "add_bcast.out")
+    _l.check(lib.pst3r_add_bcast(_base(a).data_ptr(), _kind(a), lda, _base(b).data_ptr(), _kind(b), ldb, brows,
+                                 _base(out).data_ptr(), _kind(out), ldo, rows, cols, _stream()), "pst3r_add_bcast")
+    launches += 1
+    return out
+
+
+def convert(x, out):
+    """out = x between bf16 / fp32 / Split row matrices of equal logical shape."""
+    global launches
+    lib = _l.load()
+    _need_cuda(x, "convert.x")
+    _need_cuda(out, "convert.out")
+    _packed(x, "convert.x")
+    _packed(out, "convert.out")
+    xb, ob = _base(x), _base(out)
+    if xb.dim() < 2:
+        xb, ob = xb.reshape(1, -1), ob.reshape(1, -1)
+    if not isinstance(x, Split) and xb.stride(-1) != 1:
+        xb = xb.contiguous()
+    rows, cols, ldx = _rows2d(xb, "convert.x")
+    r2, c2, ldy = _rows2d(ob, "convert.out")
+    if (rows, cols) != (r2, c2):
+        raise _l.Pst3rError("convert: shape mismatch")
+    _l.check(lib.pst3r_convert(xb.data_ptr(), _kind(x), ldx, ob.data_ptr(), _kind(out), ldy, rows, cols, _stream()), "pst3r_convert")
+    launches += 1
+    return out
+
+
+def softmax_rows(S: torch.Tensor, Q: int, mask_bits: Optional[torch.Tensor] = None, out=None):
+    """Row softmax over the last dim of S fp32 [..., Nk] (rows = (head, query), query = row % Q) with an optional block
+    mask int32 [1, Q, W] (bit set = key blocked) -> probabilities as a packed `Split` [..., Nk] (default) or `out`."""
+    global launches
+    lib = _l.load()
+    _need(S, torch.float32, "softmax_rows.S")
+    rows, Nk, lds = _rows2d(S, "softmax_rows.S")
+    if out is None:
+        out = Split.empty(S.shape, S.device)
+    _packed(out, "softmax_rows.out")
+    _, _, ldo = _rows2d(_base(out), "softmax_rows.out")
+    mptr, msq = None, 0
+    if mask_bits is not None:
+        if mask_bits.dtype not in (torch.int32, torch.uint32) or mask_bits.stride(-1) != 1:
+            raise _l.Pst3rError("softmax_rows.mask_bits: expected int32 [1, Q, W]")
+        mptr, msq = mask_bits.data_ptr(), mask_bits.stride(-2)
+    _l.check(lib.pst3r_softmax_rows(S.data_ptr(), lds, rows, Nk, mptr, msq, Q, _base(out).data_ptr(), _kind(out), ldo, _stream()),
+             "pst3r_softmax_rows")
     launches += 1
     return out
 
@@ -402,15 +600,23 @@ def dino_preprocess_patchify(img: torch.Tensor, Ho: int, Wo: int, P: int, ld: in
     return out
 
 
-def center_pool8(feats: torch.Tensor) -> torch.Tensor:
-    """feats bf16 [B, Hm, Wm, C] -> bf16 [B, Hm/8, Wm/8, C] (mean of the centre 2x2 of each 8x8 cell)."""
+def center_pool8(feats):
+    """feats bf16 [B, Hm, Wm, C] (or a packed `Split` of that shape) -> [B, Hm/8, Wm/8, C] of the same kind
+    (mean of the centre 2x2 of each 8x8 cell)."""
     global launches
     lib = _l.load()
-    _need(feats, torch.bfloat16, "center_pool8.feats")
-    feats = feats.contiguous()
-    B, Hm, Wm, Cc = feats.shape
-    out = torch.empty((B, Hm // 8, Wm // 8, Cc), device=feats.device, dtype=torch.bfloat16)
-    _l.check(lib.pst3r_center_pool8(feats.data_ptr(), B, Hm, Wm, Cc, out.data_ptr(), _stream()), "pst3r_center_pool8")
+    fb = _base(feats)
+    _need(fb, torch.bfloat16, "center_pool8.feats")
+    _packed(feats, "center_pool8.feats")
+    B, Hm, Wm, Cc = fb.shape
+    if isinstance(feats, Split):
+        if fb.stride() != (Hm * Wm * 2 * Cc, Wm * 2 * Cc, 2 * Cc, 1):
+            raise _l.Pst3rError("center_pool8: split map must be dense [B, Hm, Wm, 2C]")
+        out = Split.empty((B, Hm // 8, Wm // 8, Cc), fb.device)
+    else:
+        fb = fb.contiguous()
+        out = torch.empty((B, Hm // 8, Wm // 8, Cc), device=fb.device, dtype=torch.bfloat16)
+    _l.check(lib.pst3r_center_pool8(fb.data_ptr(), _kind(feats), B, Hm, Wm, Cc, _base(out).data_ptr(), _stream()), "pst3r_center_pool8")
     launches += 1
     return out
 
@@ -429,28 +635,35 @@ def attn_mask_bits(logits_t: torch.Tensor, Nk: int, out: Optional[torch.Tensor] 
     return out
 
 
-def l2norm_rows(x: torch.Tensor, eps: float, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+def l2norm_rows(x: torch.Tensor, eps: float, out_dtype=torch.bfloat16):
+    """y = x / (||x|| + eps) per row; fp32 in, bf16 / fp32 / "split" out."""
     global launches
     lib = _l.load()
     _need(x, torch.float32, "l2norm_rows.x")
     rows, cols, ldx = _rows2d(x, "l2norm_rows.x")
-    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
-    _, _, ldy = _rows2d(out, "l2norm_rows.out")
-    _l.check(lib.pst3r_l2norm_rows(x.data_ptr(), ldx, out.data_ptr(), int(out_dtype == torch.float32), ldy, rows, cols,
+    out = _new(x.shape, _dkind(out_dtype), x.device)
+    _, _, ldy = _rows2d(_base(out), "l2norm_rows.out")
+    _l.check(lib.pst3r_l2norm_rows(x.data_ptr(), ldx, _base(out).data_ptr(), _kind(out), ldy, rows, cols,
                                    eps, _stream()), "pst3r_l2norm_rows")
     launches += 1
     return out
 
 
-def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
-    """bf16 [B, HW, C] -> fp32 [B, C, HW]"""
+def nhwc_to_nchw_f32(x) -> torch.Tensor:
+    """bf16 (or packed Split) [B, HW, C] -> fp32 [B, C, HW]"""
     global launches
     lib = _l.load()
-    _need(x, torch.bfloat16, "nhwc_to_nchw_f32.x")
-    x = x.contiguous()
-    B, HW, Cc = x.shape
-    out = torch.empty((B, Cc, HW), device=x.device, dtype=torch.float32)
-    _l.check(lib.pst3r_nhwc_to_nchw_f32(x.data_ptr(), B, HW, Cc, out.data_ptr(), _stream()), "pst3r_nhwc_to_nchw_f32")
+    xb = _base(x)
+    _need(xb, torch.bfloat16, "nhwc_to_nchw_f32.x")
+    _packed(x, "nhwc_to_nchw_f32.x")
+    B, HW, Cc = xb.shape
+    if isinstance(x, Split):
+        if xb.stride() != (HW * 2 * Cc, 2 * Cc, 1):
+            raise _l.Pst3rError("nhwc_to_nchw_f32: split map must be dense [B, HW, 2C]")
+    else:
+        xb = xb.contiguous()
+    out = torch.empty((B, Cc, HW), device=xb.device, dtype=torch.float32)
+    _l.check(lib.pst3r_nhwc_to_nchw_f32(xb.data_ptr(), _kind(x), B, HW, Cc, out.data_ptr(), _stream()), "pst3r_nhwc_to_nchw_f32")
     launches += 1
     return out
 
@@ -532,7 +745,7 @@ def conv3x3_nhwc(x: torch.Tensor, w: torch.Tensor, cpad: int, *, bias: Optional[
     if out is None:
         out = torch.empty((V, H, W, O), device=x.device, dtype=torch.bfloat16)
     e = _l.GemmEpilogue()
-    e.out, e.ldo, e.out_f32, e.act, e.alpha = out.data_ptr(), out.stride(2), 0, act, 1.0
+    e.out, e.ldo, e.out_kind, e.act, e.alpha = out.data_ptr(), out.stride(2), KIND_BF16, act, 1.0
     if bias is not None:
         _need(bias, torch.float32, "conv3x3.bias")
         e.bias = bias.data_ptr()
@@ -664,7 +877,7 @@ gemm = _wrap(gemm, _gemm_kind)
 gemm_batched = _wrap(gemm_batched, lambda a, k: "gemm_batched")
 layernorm_batched = _wrap(layernorm_batched, lambda a, k: "layernorm_batched")
 attention = _wrap(attention, _attn_kind)
-for _n in ("layernorm", "rope2d_", "add_bcast", "to_bf16", "to_f32", "patchify", "dino_preprocess_patchify", "center_pool8",
+for _n in ("layernorm", "rope2d_", "add_bcast", "convert", "softmax_rows", "to_bf16", "to_f32", "patchify", "dino_preprocess_patchify", "center_pool8",
            "attn_mask_bits", "l2norm_rows", "nhwc_to_nchw_f32", "conv3x3_nhwc", "loftup_guidance", "loftup_fourier_gn",
            "groupnorm_nhwc_"):
     globals()[_n] = _wrap(globals()[_n], (lambda name: (lambda a, k: name))(_n))

@@ -50,6 +50,20 @@ def stack_views(true_shapes, stored_shapes):
     return list(stacks.values())
 
 
+def merge_panouts(outs):
+    """Concatenate single-scene output dicts along the batch dimension (out_queries is (Q, B, C))."""
+    if len(outs) == 1:
+        return outs[0]
+    m = {"pred_logits": torch.cat([o["pred_logits"] for o in outs], 0),
+         "pred_masks": torch.cat([o["pred_masks"] for o in outs], 0)}
+    if "aux_outputs" in outs[0]:
+        m["aux_outputs"] = [{k: torch.cat([o["aux_outputs"][i][k] for o in outs], 0) for k in outs[0]["aux_outputs"][i]}
+                            for i in range(len(outs[0]["aux_outputs"]))]
+    if "out_queries" in outs[0]:
+        m["out_queries"] = torch.cat([o["out_queries"] for o in outs], 1)
+    return m
+
+
 class PanSt3R(nn.Module):
     def __init__(self, must3r_encoder: nn.Module, must3r_decoder: nn.Module, dino_encoder: nn.Module,
                  panoptic_decoder: nn.Module, retrieval=None, preserve_gpu_mem: bool = False,
@@ -148,6 +162,12 @@ class PanSt3R(nn.Module):
     def forward(self, imgs, true_shape, classes, max_bs=None, outdevice=None):
         """imgs fp32 (1, V, 3, H, W) in [-1, 1] on CUDA; true_shape (1, V, 2) (H, W); returns (panout, pointmaps)."""
         ts = true_shape.cpu() if true_shape.is_cuda else true_shape
+        if imgs.shape[0] > 1:
+            # batch-generic like the reference (panst3r.py:286-296; engine/must3r.py:95-108 keeps one memory per
+            # scene): scenes are independent, so a batch is a loop over single-scene passes
+            outs = [self.forward(imgs[b:b + 1], ts[b:b + 1], classes, max_bs=max_bs, outdevice=outdevice)
+                    for b in range(imgs.shape[0])]
+            return merge_panouts([o[0] for o in outs]), torch.cat([o[1] for o in outs], 0)
         cat, rows, x, pos, join = self._features(imgs, ts)
         mem = self._build_memory_shared(x, pos, ts, join)
         _, pointmaps, _ = self.must3r_decoder(x, pos, ts, mem, render=True, return_feats="last",
@@ -259,24 +279,75 @@ class PanSt3R(nn.Module):
     def set_vocab(self, class_names, device=None):
         self.panoptic_decoder.text_encoder.set_vocab(class_names, device=device)
 
+    # upstream parameter-name variants -> the names this package (and oracle/must3r.py) uses.  The MUSt3R classes live in
+    # the un-vendored `must3r` package (pyproject.toml:14): croco-style names are accepted next to ours.
+    KEY_REMAP = (
+        ("must3r_encoder.enc_blocks.", "must3r_encoder.blocks_enc."),
+        ("must3r_encoder.enc_norm.", "must3r_encoder.norm_enc."),
+        ("must3r_decoder.dec_blocks.", "must3r_decoder.blocks_dec."),
+        ("must3r_decoder.dec_norm.", "must3r_decoder.norm_dec."),
+        ("must3r_decoder.decoder_embed.", "must3r_decoder.feat_embed_enc_to_dec."),
+        ("must3r_decoder.feedback.", "must3r_decoder.feedback_layer."),
+        ("must3r_decoder.head.proj.", "must3r_decoder.head_dec.proj."),
+        ("must3r_decoder.downstream_head.proj.", "must3r_decoder.head_dec.proj."),
+    )
+
     @classmethod
-    def from_checkpoint(cls, checkpoint_path, retrieval_path=None):
+    def remap_state_dict(cls, weights: dict) -> dict:
+        out = {}
+        for k, v in weights.items():
+            for old, new in cls.KEY_REMAP:
+                if k.startswith(old):
+                    k = new + k[len(old):]
+                    break
+            out[k] = v
+        return out
+
+    def load_checkpoint_weights(self, weights: dict, allow_partial: bool = False) -> dict:
+        """load_state_dict(strict=False) as the reference does (panst3r.py:323) — but never silently: returns (and keeps
+        in `self.load_report`) the missing / unexpected keys per sub-module, warns about them, and raises when a whole
+        sub-module received nothing (a name mismatch that would leave it at random init) unless allow_partial."""
+        import warnings
+        res = self.load_state_dict(self.remap_state_dict(weights), strict=False)
+        own = list(self.state_dict().keys())
+        report = {}
+        for sub in ("must3r_encoder", "must3r_decoder", "dino_encoder", "panoptic_decoder"):
+            total = sum(1 for k in own if k.startswith(sub + "."))
+            miss = [k for k in res.missing_keys if k.startswith(sub + ".")]
+            unexp = [k for k in res.unexpected_keys if k.startswith(sub + ".")]
+            report[sub] = {"parameters": total, "missing": miss, "unexpected": unexp}
+        report["other_unexpected"] = [k for k in res.unexpected_keys
+                                      if not k.startswith(("must3r_encoder.", "must3r_decoder.", "dino_encoder.", "panoptic_decoder."))]
+        self.load_report = report
+        bad = [s_ for s_ in report if isinstance(report[s_], dict) and report[s_]["parameters"] and
+               len(report[s_]["missing"]) == report[s_]["parameters"]]
+        for s_, r in report.items():
+            if isinstance(r, dict) and (r["missing"] or r["unexpected"]):
+                warnings.warn(f"PanSt3R checkpoint: {s_}: {len(r['missing'])}/{r['parameters']} parameters missing "
+                              f"(e.g. {r['missing'][:3]}), {len(r['unexpected'])} unexpected (e.g. {r['unexpected'][:3]})")
+        if bad and not allow_partial:
+            raise ops._l.Pst3rError(f"checkpoint loaded NO parameter of {bad}: its key names do not match this package "
+                                    f"(see PanSt3R.KEY_REMAP / model.load_report); pass allow_partial=True to proceed anyway")
+        return report
+
+    @classmethod
+    def from_checkpoint(cls, checkpoint_path, retrieval_path=None, allow_partial: bool = False):
         """Loads the reference's checkpoint format: {'args': Namespace of constructor strings, 'weights': state dict}
         (panst3r.py:301-325).  The constructor strings are evaluated against this package's CUDA classes."""
         ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
         assert "args" in ckpt, "Checkpoint must contain 'args' with model parameters."
         from .modules import panoptic as _p
         ns = {"Dust3rEncoder": Dust3rEncoder, "MUSt3R": MUSt3R, "DinoV2Encoder": DinoV2Encoder,
-              "PanopticDecoder": PanopticDecoder, "PixelShuffleUpscaler": PixelShuffleUpscaler}
-        for extra in ("InputMixer", "LoftUpUpscaler"):
-            if hasattr(_p, extra):
-                ns[extra] = getattr(_p, extra)
+              "PanopticDecoder": PanopticDecoder, "PixelShuffleUpscaler": PixelShuffleUpscaler,
+              "InputMixer": _p.InputMixer, "LoftUpUpscaler": _p.LoftUpUpscaler}
         a = ckpt["args"]
-        get = (lambda k: a[k]) if isinstance(a, dict) else (lambda k: getattr(a, k))
+        get = (lambda k, d=None: a.get(k, d)) if isinstance(a, dict) else (lambda k, d=None: getattr(a, k, d))
         model = cls(must3r_encoder=eval(get("must3r_encoder"), ns), must3r_decoder=eval(get("must3r_decoder"), ns),
                     dino_encoder=eval(get("dino_encoder"), ns), panoptic_decoder=eval(get("panoptic_decoder"), ns),
-                    retrieval=ckpt.get("retrieval"))
-        model.load_state_dict(ckpt["weights"], strict=False)
+                    retrieval=ckpt.get("retrieval"),
+                    postprocess_default=get("postprocess_default", "standard_v2"),
+                    qubo_enabled=get("qubo_enabled", True))
+        model.load_checkpoint_weights(ckpt["weights"], allow_partial=allow_partial)
         return model
 
 

@@ -11,10 +11,10 @@ from oracle.make_golden import CLASSES, GOLDEN, head_inputs  # noqa: F401
 
 def golden_files(pattern="head_*.pt"):
     """Single-stack head fixtures (the multi aspect-ratio fixture has its own tests)."""
-    return sorted(f for f in glob.glob(os.path.join(GOLDEN, pattern)) if "multi_ar" not in f)
+    return sorted(f for f in glob.glob(os.path.join(GOLDEN, pattern)) if "multi_ar" not in f and "conditioned" not in f)
 
 
-def build_oracle_head(variant):
+def build_oracle_head(variant, cls_logit_scale=None):
     if variant == "v1":
         m = op.PanopticDecoder(upscaler=op.PixelShuffleUpscaler(input_dim=2816))
     else:
@@ -23,6 +23,9 @@ def build_oracle_head(variant):
     m.eval()
     m.load_state_dict(W.synth_state_dict(m, seed=1))
     m.text_encoder.class_embeddings = W.synth_class_embeddings(CLASSES)
+    if cls_logit_scale is not None:
+        with torch.no_grad():
+            m.mask_transformer.cls_logit_scale.fill_(cls_logit_scale)
     return m
 
 

@@ -60,9 +60,9 @@ def test_struct_layouts_match_header(built):
 
 def test_version_and_error_string(built):
     lib = built.load()
-    assert lib.pst3r_version() == built.ABI_VERSION == 2
+    assert lib.pst3r_version() == built.ABI_VERSION == 3
     hdr = open(os.path.join(ROOT, "include", "panst3r_b200.h")).read()
-    assert re.search(r"#define\s+PST3R_ABI_VERSION\s+2\b", hdr)
+    assert re.search(r"#define\s+PST3R_ABI_VERSION\s+3\b", hdr)
     assert isinstance(lib.pst3r_last_error(), bytes)
 
 

@@ -15,15 +15,36 @@ def test_oracle_head_matches_golden(path):
     feats, imgs, pos, ts = head_inputs(g["V"], g["H"], g["W"], g["input_seed"], g["portrait"])
     with torch.no_grad():
         out = m(feats, imgs, pos, ts, CLASSES)
-    # fixtures store mask logits in fp16 (size); tolerance = fp16 rounding of the stored value
+    # fixtures are fp32 (the larger one keeps its first aux head in fp16); the oracle is bit-exact against the reference
+    # modules here, 1e-6 leaves room for a different CPU / BLAS build on the GPU box
     assert relmax(out["pred_logits"], g["pred_logits"]) < 1e-5
     assert relmax(out["out_queries"], g["out_queries"]) < 1e-5
-    assert relmax(out["pred_masks"], g["pred_masks"]) < 1e-3
-    assert relmax(out["aux_outputs"][0]["pred_masks"], g["aux0_masks"]) < 1e-3
+    assert relmax(out["pred_masks"], g["pred_masks"]) < 1e-5
+    assert relmax(out["aux_outputs"][0]["pred_masks"], g["aux0_masks"]) < (1e-3 if g["aux0_masks"].dtype == torch.float16 else 1e-5)
     assert g["memq_masks_equal_full"]
     with torch.no_grad():
         mq = m(feats, imgs, pos, ts, CLASSES, memory_queries=out["out_queries"])
     assert torch.equal(mq["pred_masks"], out["pred_masks"])  # config-3 reuse path == final prediction head only
+
+
+def test_oracle_conditioned_golden():
+    """The well-conditioned fixture (class logits O(1)): oracle == reference outputs, argmax ids of the post-processing
+    front half, > 90 % of the pixels decided by a top-2 margin above 1e-4."""
+    import os
+    from helpers import GOLDEN
+    g = torch.load(os.path.join(GOLDEN, "head_v1_conditioned.pt"))
+    m = build_oracle_head(g["variant"], cls_logit_scale=g["cls_logit_scale"])
+    feats, imgs, pos, ts = head_inputs(g["V"], g["H"], g["W"], g["input_seed"])
+    with torch.no_grad():
+        out = m(feats, imgs, pos, ts, CLASSES)
+    assert relmax(out["pred_masks"], g["pred_masks"]) < 1e-5 and relmax(out["pred_logits"], g["pred_logits"]) < 1e-5
+    assert g["pred_logits"].abs().max() > 1.0 and g["pred_masks"].abs().max() > 1.0
+    assert (g["margin"] > 1e-4).float().mean() > 0.9
+    scores = out["pred_logits"].sigmoid().max(-1).values[0]
+    up = torch.nn.functional.interpolate(out["pred_masks"][0].sigmoid(), size=(g["H"], g["W"]), mode="bilinear", align_corners=False)
+    ids = (scores[None, :, None, None] * up).argmax(1)
+    safe = g["margin"] > 1e-6
+    assert torch.equal(ids[safe].to(torch.int16), g["ids"][safe])
 
 
 def test_oracle_multi_ar_head_matches_golden():
@@ -40,7 +61,7 @@ def test_oracle_multi_ar_head_matches_golden():
     assert relmax(out["pred_logits"], g["pred_logits"]) < 1e-5 and relmax(out["out_queries"], g["out_queries"]) < 1e-5
     assert len(out["pred_masks"]) == len(g["pred_masks"]) == 3
     for a, b, c, d in zip(out["pred_masks"], g["pred_masks"], out["aux_outputs"][0]["pred_masks"], g["aux0_masks"]):
-        assert a.shape == b.shape and relmax(a, b) < 1e-3 and relmax(c, d) < 1e-3
+        assert a.shape == b.shape and relmax(a, b) < 1e-5 and relmax(c, d) < 1e-5
     assert g["memq_masks_equal_full"] and all(torch.equal(a, b) for a, b in zip(mq["pred_masks"], out["pred_masks"]))
 
 
