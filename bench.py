@@ -5,7 +5,9 @@
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference path on the host CPU cores
 
 A step = one `PanSt3R.forward()` over one synthetic scene: 16 keyframes at 512x384 (W x H), v1 PixelShuffle head,
-bf16 tensor-core math with fp32 accumulation, random-init weights of the reference architecture (BASELINE config 2).
+random-init weights of the reference architecture (BASELINE config 2), the reference's precision policy: bf16 tensor-core
+math with fp32 accumulation for DINOv2 / encoder / decoder, fp32-grade (split-bf16) arithmetic for the panoptic head
+(`--head-precision bf16` times the all-bf16 variant; the default run reports it next to the headline as `bf16_head`).
 N > 1: the SAME scene, views sharded across ranks (strong scaling; panst3r_b200/dist.py): per-view stages run on
 the owning rank, one NCCL all-gather of encoder tokens precedes the (replicated) sequential memory build.
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the definition of every field.
@@ -157,6 +159,40 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def _timed(torch, dist, world, dev, fn, n):
+    """n calls of fn between barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _capture(torch, fn):
+    """Whole step in one CUDA graph (NCCL all-gathers and the side stream are capturable); None if capture fails."""
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = fn()
+        g.replay()
+        torch.cuda.synchronize()
+        return g, out
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] CUDA graph capture failed ({e!r}); timing eager launches", file=sys.stderr)
+        torch.cuda.synchronize()
+        return None, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -177,15 +213,17 @@ def run_ours(args):
     load()  # fails loudly if the CUDA extension is missing
     V = args.views
     with torch.device("cuda"):
-        model = build_panst3r(args.variant)
+        model = build_panst3r(args.variant, head_precision=args.head_precision)
     init_weights_(model)
     g = torch.Generator().manual_seed(7)
     model.panoptic_decoder.text_encoder.class_embeddings = {c: torch.randn(768, generator=g) for c in CLASSES}
     if world > 1:
-        from panst3r_b200.dist import ShardedPanSt3R
+        from panst3r_b200.dist import ShardedPanSt3R, partition_views
         runner = ShardedPanSt3R(model, rank, world)
+        v0, v1 = partition_views(V, world)[rank]
     else:
         runner = model
+        v0, v1 = 0, V
     host_imgs, ts = make_inputs(V, dev, pinned=True)
     dev_imgs = host_imgs.to(dev)
     keyframes = args.keyframes if 0 < args.keyframes < V else 0
@@ -214,23 +252,13 @@ def run_ours(args):
         out = step_device()
     barrier()
     launches0 = ops.launches
+    ops.flop_count.clear()
     out = step_device()
     launches_per_step = ops.launches - launches0
+    flops_step = dict(ops.flop_count)
     barrier()
 
-    # ---- optional CUDA graph over the whole forward ----
-    graph = None
-    if args.graph:  # NCCL all-gathers are graph-capturable; falls back to eager launches if capture fails
-        try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                gout = step_device()
-            graph.replay()
-            torch.cuda.synchronize()
-        except Exception as e:  # noqa: BLE001
-            print(f"[bench] CUDA graph capture failed ({e!r}); timing eager launches", file=sys.stderr)
-            graph = None
-            torch.cuda.synchronize()
+    graph, gout = _capture(torch, step_device) if args.graph else (None, None)
 
     def run_step():
         if graph is not None:
@@ -246,36 +274,25 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = run_step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms_total = _timed(torch, dist, world, dev, run_step, args.steps)
+    out = gout if graph is not None else out
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     units = keyframes or V  # the metric counts keyframe views
     value = units * args.steps / (ms_total / 1e3)
 
     # ---- e2e: host buffers in, host buffers out, through the public forward() ----
+    # Every rank moves only ITS views: the image slice it owns goes host -> device, its pointmaps / mask logits (and the
+    # replicated class logits) come back.  Serving-loop pipelining: step i's H2D (copy-in stream) and step i-1's D2H
+    # (copy-out stream) overlap the forward of step i; every step still lands its own results in pinned host memory
+    # inside the timed region.
     res_dev = flat(out)
-    res_host = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res_dev]
-    h2d = host_imgs.numel() * host_imgs.element_size()
+    h2d = host_imgs[:, v0:v1].numel() * host_imgs.element_size()
     d2h = sum(r.numel() * r.element_size() for r in res_dev)
-
-    # Serving-loop pipelining: step i's H2D (copy-in stream) and step i-1's D2H (copy-out stream) overlap the
-    # forward of step i.  Every step still moves its own inputs from pinned host memory and lands its own
-    # pred_logits / pred_masks / pointmaps in pinned host memory inside the timed region.
     main = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    in_stage = [torch.empty_like(dev_imgs) for _ in range(2)]
+    in_stage = [torch.empty_like(dev_imgs[:, v0:v1]) for _ in range(2)]
     out_stage = [[torch.empty_like(r) for r in res_dev] for _ in range(2)]
-    res_host2 = [res_host, [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res_dev]]
+    res_host2 = [[torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res_dev] for _ in range(2)]
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_staged = [torch.cuda.Event() for _ in range(2)]
     ev_out = [torch.cuda.Event() for _ in range(2)]
@@ -283,11 +300,11 @@ def run_ours(args):
     def e2e_loop(n):
         for i in range(n):
             b_ = i & 1
-            with torch.cuda.stream(s_in):           # host -> device of this step's images
-                in_stage[b_].copy_(host_imgs, non_blocking=True)
+            with torch.cuda.stream(s_in):           # host -> device of this step's (local) images
+                in_stage[b_].copy_(host_imgs[:, v0:v1], non_blocking=True)
                 ev_in[b_].record(s_in)
             main.wait_event(ev_in[b_])
-            dev_imgs.copy_(in_stage[b_], non_blocking=True)
+            dev_imgs[:, v0:v1].copy_(in_stage[b_], non_blocking=True)
             o = run_step()
             main.wait_event(ev_out[b_])             # staging buffer b_ must have been drained (step i-2)
             for st, r in zip(out_stage[b_], flat(o)):
@@ -303,44 +320,54 @@ def run_ours(args):
     e2e_loop(2)
     barrier()
     w0 = time.perf_counter()
-    e0.record()
-    e2e_loop(args.steps)
-    e1.record()
-    barrier()
+    ms_e2e = _timed(torch, dist, world, dev, lambda: e2e_loop(args.steps), 1)
     wall = time.perf_counter() - w0
-    t = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = units * args.steps / (float(t.item()) / 1e3)
+    e2e_value = units * args.steps / (ms_e2e / 1e3)
+    if world > 1:  # whole-job byte counts
+        tb = torch.tensor([float(h2d), float(d2h)], device=dev)
+        dist.all_reduce(tb)
+        h2d_total, d2h_total = int(tb[0].item()), int(tb[1].item())
+    else:
+        h2d_total, d2h_total = h2d, d2h
 
-    # ---- per-kernel-kind profile of one eager step + roofline of the dominant kernel ----
-    roofline, breakdown = None, None
-    with ops.profiler() as prof:  # every rank runs the step (it contains collectives); rank 0 reports
-        step_device()
-    barrier()
-    att_roof = None
+    # ---- per-kernel breakdown of ONE timed-configuration step (CUPTI device durations via torch.profiler) ----
+    breakdown = kernel_breakdown(torch, run_step, barrier)
+    roofline = att_roof = gemm_class = None
     if rank == 0:
         peaks, peak_src = _peaks()
-        breakdown = prof.summary()
         roofline = dominant_roofline(ops, torch, V, peaks, peak_src, breakdown)
         att_roof = attention_roofline(ops, torch, V, peaks, peak_src)
+        gemm_class = class_fractions(breakdown, flops_step, peaks)
     barrier()
 
-    # ---- N > 1 only: the same GPUs running one independent scene each (no collective), for comparison ----
-    scene_parallel = None
+    # ---- N = 1: the all-bf16 head variant, and the reference's own GPU path as denominator ----
+    bf16_head = gpu_ref = None
+    if world == 1 and not keyframes and args.head_precision == "fp32" and args.bf16_head:
+        model.panoptic_decoder.precision = "bf16"
+        for _ in range(3):
+            step_device()
+        g2, _ = _capture(torch, step_device) if args.graph else (None, None)
+        fn2 = (lambda: g2.replay()) if g2 is not None else step_device
+        for _ in range(2):
+            fn2()
+        ms2 = _timed(torch, dist, world, dev, fn2, args.steps)
+        bf16_head = {"value": V * args.steps / (ms2 / 1e3), "unit": UNIT, "ms_per_step": ms2 / args.steps,
+                     "note": "same step with PanopticDecoder.precision='bf16' (plain bf16 operands in the head, ~1e-2 parity)"}
+        model.panoptic_decoder.precision = "fp32"
+        del g2
+    if world == 1 and not keyframes and args.gpu_reference:
+        gpu_ref = gpu_reference_leg(args, model, dev_imgs, ts, value)
+
+    # ---- N > 1: BASELINE config 5 shape (8 keyframes per GPU, weak scaling) and scene-parallel replicas ----
+    weak = scene_parallel = None
+    if world > 1 and args.weak:
+        weak = weak_scaling_leg(args, torch, dist, world, rank, local, dev, runner)
     if world > 1 and args.scene_parallel:
         try:
             for _ in range(2):
                 model(dev_imgs, ts, CLASSES)
-            barrier()
-            e0.record()
-            for _ in range(args.steps):
-                model(dev_imgs, ts, CLASSES)
-            e1.record()
-            barrier()
-            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            scene_parallel = {"value": world * V * args.steps / (float(t.item()) / 1e3), "unit": UNIT, "scaling": "weak",
+            ms3 = _timed(torch, dist, world, dev, lambda: model(dev_imgs, ts, CLASSES), args.steps)
+            scene_parallel = {"value": world * V * args.steps / (ms3 / 1e3), "unit": UNIT, "scaling": "weak",
                               "note": "one independent 16-keyframe scene per GPU, eager launches, no data-path collective"}
         except Exception as e:  # noqa: BLE001
             scene_parallel = {"error": repr(e)}
@@ -349,25 +376,32 @@ def run_ours(args):
         cpu_base = None
         if world == 1 and args.cpu_baseline:
             cpu_base = cpu_baseline_leg(args)
+        head_desc = "fp32-grade (split bf16) head" if args.head_precision == "fp32" else "bf16 head"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": (f"{V}-keyframe 512x384 batch" if not keyframes else
                                     f"{keyframes} keyframes + {V - keyframes} render-only frames at 512x384 (memory-query path)") +
-                                   f", {'v1 PixelShuffle' if args.variant == 'v1' else 'v2 InputMixer + LoftUp'} head, bf16, " +
+                                   f", {'v1 PixelShuffle' if args.variant == 'v1' else 'v2 InputMixer + LoftUp'} head, bf16 trunk + " +
+                                   head_desc + ", " +
                                    ("PanSt3R.forward()" if not keyframes else "PanSt3R.forward_inference_multi_ar()"),
                        "views": V, "keyframes": keyframes or V, "variant": args.variant, "classes": len(CLASSES),
+                       "head_precision": args.head_precision,
                        "parallelism": f"views sharded x{world}",
                        "cuda_graph": graph is not None,
                        "l2": "per-step working set (1.7 GB bf16 weights + >2 GB activations) exceeds the 126 MB L2; no flush needed"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "wall_ms_per_step": 1e3 * wall / args.steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
+                    "h2d_bytes_per_step_rank0": h2d, "wall_ms_per_step": 1e3 * wall / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,
             "attention_roofline": att_roof,
+            "class_fractions": gemm_class,
             "total_views_per_s": V * args.steps / (ms_total / 1e3),
+            "bf16_head": bf16_head,
+            "gpu_reference": gpu_ref,
+            "baseline_config5": weak,
             "scene_parallel": scene_parallel,
             "kernel_breakdown_ms": breakdown,
             "cpu_baseline": cpu_base,
@@ -384,11 +418,68 @@ def run_ours(args):
         os._exit(0)
 
 
+def kernel_breakdown(torch, run_step, barrier):
+    """Device time per kernel of ONE step of the timed configuration (same graph replay / launches as the timed loop),
+    from CUPTI kernel records (torch.profiler): every kernel's own duration, whichever stream it ran on.  The sum exceeds
+    `ms_per_step` only by what DINOv2 overlaps with the memory build on the side stream.  Never inside a timed region."""
+    import re
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        run_step()
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run_step()
+            torch.cuda.synchronize()
+        barrier()
+        agg = {}
+        for ev in prof.key_averages():
+            t_us = float(getattr(ev, "device_time_total", 0.0) or getattr(ev, "cuda_time_total", 0.0))
+            if t_us <= 0:
+                continue
+            name = ev.key
+            m = re.search(r"pst3r::(\w+)(<[^(]*>)?", name)
+            if m:
+                name = m.group(1) + (m.group(2) or "")
+            elif "nccl" in name.lower():
+                name = "nccl:" + name.split("(")[0][:48]
+            elif name.lower().startswith(("memcpy", "memset")):
+                name = name.split(" ")[0]
+            else:
+                name = "other:" + name.split("(")[0][:48]
+            d = agg.setdefault(name, {"ms": 0.0, "calls": 0})
+            d["ms"] += t_us / 1e3
+            d["calls"] += int(ev.count)
+        total = sum(d["ms"] for d in agg.values()) or 1.0
+        for d in agg.values():
+            d["share"] = round(d["ms"] / total, 4)
+            d["ms"] = round(d["ms"], 4)
+        out = dict(sorted(agg.items(), key=lambda kv: -kv[1]["ms"]))
+        out["_total_ms"] = round(total, 3)
+        out["_source"] = "CUPTI kernel durations (torch.profiler) of one step as timed"
+        return out
+    except Exception as e:  # noqa: BLE001
+        barrier()
+        return {"_error": repr(e)}
+
+
+def _load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the profiled kernels, parsed from the committed
+    `ncu --set full` captures (tools/ncu_traffic.py writes profiles/r02_ncu_traffic.json from the raw CSV)."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def dominant_roofline(ops, torch, V, peaks, peak_src, breakdown):
-    """Time the dominant kernel (by share of the step) alone with CUDA events at its in-step shape."""
-    dom = max(breakdown, key=lambda k: breakdown[k]["ms"]) if breakdown else "attention"
+    """The kernel with the largest share of the step (CUPTI breakdown), timed alone with CUDA events at its in-step shape
+    AND with its in-step epilogue (bias + erf-GELU for the ViT-L fc1)."""
+    names = [k for k in (breakdown or {}) if not k.startswith("_")]
+    dom = names[0] if names else "attention3_fwd_kernel"
     dev = "cuda"
-    reps = 10
+    reps = 20
+    traffic_tab = _load_traffic()
     if dom.startswith("attention"):
         B, Hh, Nq, Nk, hd = V, 12, 768, V * 768, 64  # render cross-attention over the keyframe memory
         q = torch.randn(B, Nq, Hh, hd, device=dev).bfloat16()
@@ -396,15 +487,18 @@ def dominant_roofline(ops, torch, V, peaks, peak_src, breakdown):
         v = torch.randn(1, Nk, Hh, hd, device=dev).bfloat16()
         fn = lambda: ops.attention(q, k, v)  # noqa: E731
         flops = 4.0 * B * Hh * Nq * Nk * hd
-        name = f"attention_fwd_kernel<64> B{B} H{Hh} Nq{Nq} Nk{Nk} (decoder render cross-attention)"
+        name = f"attention3_fwd_kernel B{B} H{Hh} Nq{Nq} Nk{Nk} hd64 (decoder render cross-attention)"
+        tkey = "attention3_render"
     else:
-        M, N, K = V * 768, 4096, 1024  # encoder / DINOv2 fc1
+        M, N, K = V * 768, 4096, 1024  # encoder / DINOv2 fc1 with its in-step epilogue
         a = torch.randn(M, K, device=dev).bfloat16()
-        w = torch.randn(N, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) * K ** -0.5).bfloat16()
+        bias = torch.randn(N, device=dev)
         o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        fn = lambda: ops.gemm(a, w, out=o)  # noqa: E731
+        fn = lambda: ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, out=o)  # noqa: E731
         flops = 2.0 * M * N * K
-        name = f"gemm_bf16_tn_kernel M{M} N{N} K{K} (ViT-L fc1)"
+        name = f"gemm2_bf16_tn_kernel M{M} N{N} K{K} + bias + erf-GELU epilogue (ViT-L fc1, as in the step)"
+        tkey = "gemm2_fc1_gelu"
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -417,14 +511,29 @@ def dominant_roofline(ops, torch, V, peaks, peak_src, breakdown):
     ms = e0.elapsed_time(e1) / reps
     ach = flops / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops", 1590.0))
-    # DRAM bytes per launch of this kernel at this shape from the committed `ncu --set full` capture
-    # (profiles/r01_ncu_full_key_kernels_v2.md): dram__bytes_read.sum + dram__bytes_write.sum
-    traffic = {"gemm": 34.19e6 + 48.33e6, "attention": 57.09e6 + 7.11e6}.get("attention" if dom.startswith("attention") else "gemm")
-    if V != 16:
-        traffic = None
+    traffic = traffic_tab.get(tkey, {}).get("dram_bytes") if V == 16 else None
     return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "traffic": traffic, "peak_source": peak_src + ", burst figure (kernel timed alone)", "kernel_ms": ms,
-            "share_of_step": breakdown[dom]["share"] if breakdown and dom in breakdown else None}
+            "traffic": traffic, "traffic_source": traffic_tab.get(tkey, {}).get("source"),
+            "peak_source": peak_src + ", burst figure (kernel timed alone)", "kernel_ms": ms,
+            "share_of_step": breakdown[dom]["share"] if breakdown and dom in breakdown else None,
+            "dominant_by": "CUPTI share of the timed step"}
+
+
+def class_fractions(breakdown, flops_step, peaks):
+    """In-step fraction of the SUSTAINED bf16 peak per kernel class: algorithmic FLOPs the wrappers issued in one step
+    (2MNK per GEMM incl. the split-precision terms, 4 Nq Nk hd per attention head) / CUPTI time of the class."""
+    if not breakdown or "_error" in breakdown:
+        return None
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    cls = {"gemm": ("gemm", "gemm2"), "attention": ("attention",)}
+    out = {}
+    for c, prefixes in cls.items():
+        ms = sum(v["ms"] for k, v in breakdown.items() if not k.startswith("_") and k.startswith(prefixes) and "combine" not in k)
+        fl = float(flops_step.get(c, 0.0))
+        if ms > 0 and fl > 0:
+            out[c] = {"tflop_per_step": fl / 1e12, "ms": round(ms, 3), "tflops": fl / (ms * 1e-3) / 1e12,
+                      "frac_of_sustained_peak": fl / (ms * 1e-3) / 1e12 / peak}
+    return out
 
 
 def attention_roofline(ops, torch, V, peaks, peak_src):
@@ -448,8 +557,78 @@ def attention_roofline(ops, torch, V, peaks, peak_src):
     peak = float(peaks.get("bf16_tflops", 1590.0))
     return {"kernel": f"attention3_fwd_kernel B{B} H{Hh} Nq{Nq} Nk{Nk} hd{hd} (render cross-attention over keyframe memory)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "kernel_ms": ms,
-            "bound": "MUFU ex2 (16/clk/SM) at head_dim 64: ceiling ~1150 TFLOP/s; ncu: XU pipe 59 %, tensor pipe 29 %",
+            "bound": "MUFU ex2 (16/clk/SM) at head_dim 64: ceiling ~1150 TFLOP/s",
             "peak_source": peak_src}
+
+
+def gpu_reference_leg(args, model, dev_imgs, ts, our_value):
+    """The reference's OWN single-GPU path on this box, as the denominator of the north star's '>= 8x the reference's
+    single-GPU forward': the oracle modules (the reference's panoptic-head code restated + restated MUSt3R, same weights
+    as the CUDA model) on `cuda`, torch's fused SDPA standing in for xformers (not installable here;
+    gradio_panst3r.py:25), TF32 matmuls as the demo enables them (gradio_panst3r.py:19), bf16 autocast on DINOv2 /
+    encoder / decoder and an fp32 head (panst3r.py:174, 204, 236-245).  CUDA events, 2 warm-up + 3 timed runs."""
+    import torch
+    from oracle import blocks as OB
+    from oracle.panst3r import build_panst3r as build_oracle
+    try:
+        V = dev_imgs.shape[1]
+        with torch.device("cuda"):
+            ref = build_oracle(args.variant)
+        ref.load_state_dict(model.state_dict(), strict=True)  # identical state-dict surface
+        ref.panoptic_decoder.text_encoder.class_embeddings = {k: v.cuda() for k, v in
+                                                              model.panoptic_decoder.text_encoder.class_embeddings.items()}
+        OB.toggle_memory_efficient_attention(True)
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            with torch.no_grad():
+                for _ in range(2):
+                    ref(dev_imgs, ts, CLASSES, amp=True)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = 3
+                e0.record()
+                for _ in range(n):
+                    ref(dev_imgs, ts, CLASSES, amp=True)
+                e1.record()
+                torch.cuda.synchronize()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            OB.toggle_memory_efficient_attention(False)
+        ms = e0.elapsed_time(e1) / n
+        val = V / (ms / 1e3)
+        del ref
+        torch.cuda.empty_cache()
+        return {"value": val, "unit": UNIT, "ms_per_step": ms, "ours_over_reference": our_value / val,
+                "what": "oracle modules on cuda: torch SDPA (xformers stand-in), TF32 matmul, bf16 autocast trunk + fp32 head, "
+                        "eager PyTorch, same weights and inputs as our arm; 3 timed runs after 2 warm-ups",
+                "kind": "port (upstream must3r/croco are not installable: oracle restatement)"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def weak_scaling_leg(args, torch, dist, world, rank, local, dev, runner):
+    """BASELINE config 5's shape at this N: 8 keyframes per GPU (64 keyframes on 8 GPUs), views sharded, NCCL token
+    all-gather; the sequential memory build over all 8N keyframes is replicated."""
+    Vw = 8 * world
+    try:
+        host, tsw = make_inputs(Vw, dev)
+        imgs = host.to(dev)
+        for _ in range(2):
+            runner(imgs, tsw, CLASSES)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        n = max(2, min(args.steps, 5))
+        ms = _timed(torch, dist, world, dev, lambda: runner(imgs, tsw, CLASSES), n)
+        clocks = sampler.stop() if rank == 0 else None
+        del imgs
+        return {"value": Vw * n / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / n, "steps": n, "scaling": "weak",
+                "config": {"workload": f"{Vw}-keyframe 512x384 batch, 8 views per GPU, views sharded x{world}, eager launches",
+                           "views": Vw, "views_per_gpu": 8},
+                "clocks": clocks}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
 
 
 def cpu_baseline_leg(args):
@@ -487,6 +666,12 @@ def main():
     ap.add_argument("--ref-views", type=int, default=2)
     ap.add_argument("--keyframes", type=int, default=0,
                     help="BASELINE config 3: this many keyframes, the remaining --views frames are render-only (e.g. --views 64 --keyframes 8)")
+    ap.add_argument("--head-precision", default="fp32", choices=["fp32", "bf16"],
+                    help="panoptic head arithmetic: fp32 = the reference's policy (split-bf16 operands), bf16 = plain bf16")
+    ap.add_argument("--no-bf16-head", dest="bf16_head", action="store_false", help="skip the secondary all-bf16-head timing")
+    ap.add_argument("--no-gpu-reference", dest="gpu_reference", action="store_false",
+                    help="skip timing the reference's own PyTorch path on the GPU (N = 1)")
+    ap.add_argument("--no-weak", dest="weak", action="store_false", help="N > 1: skip the 8-views-per-GPU (config 5) leg")
     ap.add_argument("--no-scene-parallel", dest="scene_parallel", action="store_false")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")

@@ -15,6 +15,28 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+# The reference toggles xformers' memory-efficient attention globally (gradio_panst3r.py:25,
+# `toggle_memory_efficient_attention(enabled=has_xformers)`); xformers is not installable here, torch's fused SDPA
+# stands in for it (SURVEY §8d "GPU reference baseline").  Off by default: the CPU oracle uses the plain softmax form.
+_FUSED_ATTENTION = False
+
+
+def toggle_memory_efficient_attention(enabled: bool = True):
+    global _FUSED_ATTENTION
+    _FUSED_ATTENTION = bool(enabled)
+
+
+def _attend(q, k, v, scale, mask=None):
+    """softmax(q k^T scale [masked]) v on (B, H, N, hd) tensors; mask: bool, True = blocked."""
+    if _FUSED_ATTENTION:
+        am = None if mask is None else ~mask
+        return F.scaled_dot_product_attention(q, k, v, attn_mask=am, scale=scale)
+    attn = (q @ k.transpose(-2, -1)) * scale
+    if mask is not None:
+        attn = attn.masked_fill(mask, float("-inf"))
+    return attn.softmax(dim=-1) @ v
+
+
 class RoPE2D(nn.Module):
     """2-D rotary embedding, base frequency `freq` (Appendix A.2; curope kernels.cu semantics, fp32 angles).
 
@@ -84,9 +106,7 @@ class Attention(nn.Module):
         q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
         if self.rope is not None:
             q, k = self.rope(q, xpos), self.rope(k, xpos)
-        attn = (q @ k.transpose(-2, -1)) * self.scale
-        attn = attn.softmax(dim=-1)
-        x = (attn @ v).transpose(1, 2).reshape(B, N, C)
+        x = _attend(q, k, v, self.scale).transpose(1, 2).reshape(B, N, C)
         return self.proj(x)
 
 
@@ -125,11 +145,7 @@ class CrossAttention(nn.Module):
         v = self.projv(value).reshape(B, Nk, H, C // H).permute(0, 2, 1, 3)
         if self.rope is not None:
             q, k = self.rope(q, qpos), self.rope(k, kpos)
-        attn = (q @ k.transpose(-2, -1)) * self.scale
-        if mask is not None:  # True = blocked
-            attn = attn.masked_fill(mask, float("-inf"))
-        attn = attn.softmax(dim=-1)
-        x = (attn @ v).transpose(1, 2).reshape(B, Nq, C)
+        x = _attend(q, k, v, self.scale, mask).transpose(1, 2).reshape(B, Nq, C)  # mask: True = blocked
         return self.proj(x)
 
 

@@ -60,9 +60,19 @@ class MemoryDecoderBlock(nn.Module):
         self.mlp = Mlp(dim, int(dim * mlp_ratio))
         self.norm_y = norm(dim)
 
-    def forward(self, x, xpos, mem, mask):
+    def forward(self, x, xpos, mem, mask, n=1):
+        """x (B*n, N, D): the n views of each scene; mem (B, Nmem, D): that scene's memory; mask (B*n, 1, N, Nmem) or None."""
         x = x + self.attn(self.norm1(x), xpos)
-        x = x + self.cross_attn(self.norm2(x), mem, mem, None, None, mask)
+        Bn, N, D = x.shape
+        if mask is None:
+            # render: the views only READ the memory, so they fold into the query axis — one K/V projection per scene
+            # instead of one per view (row-wise identical to expanding the memory over the views)
+            q = self.norm2(x).reshape(Bn // n, n * N, D)
+            x = x + self.cross_attn(q, mem, mem, None, None).reshape(Bn, N, D)
+        else:
+            Nm = mem.shape[1]
+            mem_b = mem[:, None].expand(Bn // n, n, Nm, D).reshape(Bn, Nm, D)
+            x = x + self.cross_attn(self.norm2(x), mem_b, mem_b, None, None, mask)
         x = x + self.mlp(self.norm3(x))
         return x
 
@@ -138,9 +148,7 @@ class MUSt3R(nn.Module):
                 labels = torch.cat([mem_labels, new_labels.reshape(B, n * N)], dim=1)  # (B, Nmem + nN)
                 mask = labels[:, None, None, :] == new_labels.reshape(B, n, N)[..., None]  # (B, n, N, Ncand)
                 mask = mask.reshape(B * n, 1, N, -1)
-            Nm = mem_l.shape[1]
-            mem_b = mem_l[:, None].expand(B, n, Nm, self.embed_dim).reshape(B * n, Nm, self.embed_dim)
-            hv = blk(hv, posv, mem_b, mask)
+            hv = blk(hv, posv, mem_l, mask, n)
             feats.append(hv.view(B, n, N, -1))
 
         pointmaps = self.head_dec(self.norm_dec(hv), (H, W)).view(B, n, H, W, -1)

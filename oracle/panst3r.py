@@ -51,13 +51,16 @@ class PanSt3R(nn.Module):
         return pointmaps, feats[-1]
 
     @torch.no_grad()
-    def forward(self, imgs, true_shape, classes, max_bs=None, outdevice=None):
-        x_dino = self.forward_dino(imgs, true_shape)
-        x, pos = self.forward_must3r_encoder(imgs, true_shape)
-        mem = self.build_memory(x, pos, true_shape)
-        pointmaps, y = self.render(x, pos, true_shape, mem)
-        panout = self.panoptic_decoder((x, y, x_dino), imgs, pos, true_shape, classes)
-        return panout, pointmaps
+    def forward(self, imgs, true_shape, classes, max_bs=None, outdevice=None, amp=False):
+        """amp=True: the reference's inference precision policy (panst3r.py:174, 204, 236-245): DINOv2, encoder and
+        decoder under torch.autocast(bf16), the panoptic head in fp32.  amp=False: fp32 everywhere."""
+        with torch.autocast(imgs.device.type, dtype=torch.bfloat16, enabled=bool(amp)):
+            x_dino = self.forward_dino(imgs, true_shape)
+            x, pos = self.forward_must3r_encoder(imgs, true_shape)
+            mem = self.build_memory(x, pos, true_shape)
+            pointmaps, y = self.render(x, pos, true_shape, mem)
+        panout = self.panoptic_decoder((x.float(), y.float(), x_dino.float()), imgs, pos, true_shape, classes)
+        return panout, pointmaps.float()
 
     @torch.no_grad()
     def forward_inference_multi_ar(self, imgs, true_shape, classes, num_keyframes=None, max_bs=None, outdevice=None):

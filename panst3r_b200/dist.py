@@ -48,11 +48,34 @@ def gather_rows(local: torch.Tensor, counts: Sequence[int], group=None) -> torch
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
 
 
+def _gather_any(local, counts, group=None):
+    """gather_rows for bf16 tensors or packed ops.Split matrices (their [hi | lo] rows travel as they are)."""
+    from . import ops
+    from .modules.common import _as_split
+    if isinstance(local, ops.Split):
+        return _as_split(gather_rows(local.full(), counts, group))
+    return gather_rows(local, counts, group)
+
+
+def allreduce_minmax(minmax: Optional[torch.Tensor], device, group=None) -> torch.Tensor:
+    """Batch-global per-channel (min, max) of LoftUp's MinMaxScaler (model/upscalers/loftup.py:14-19) across ranks:
+    the reference reduces over the WHOLE batch of views, so view-sharded ranks exchange their 3 x 2 extrema
+    (one MAX all-reduce of [-min, max]).  A rank without views contributes the neutral element."""
+    t = torch.full((3, 2), float("-inf"), device=device, dtype=torch.float32)
+    if minmax is not None:
+        t = torch.stack([-minmax[:, 0], minmax[:, 1]], dim=1).contiguous()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return torch.stack([-t[:, 0], t[:, 1]], dim=1).contiguous()
+
+
 class ShardedPanSt3R:
     """forward(imgs, true_shape, classes) -> (panout, pointmaps) for THIS rank's views.
 
-    `imgs` is the full (1, V, 3, H, W) batch on every rank (each rank touches only its slice); returned
-    `pred_masks` / `pointmaps` cover views [start, end) = partition_views(V, world)[rank]."""
+    `imgs` is the (1, V, 3, Hs, Ws) batch on every rank — only the slice of the local views is read, so a caller may
+    leave the rest unfilled (bench.py uploads just that slice).  Returned `pred_masks` / `pointmaps` cover views
+    [start, end) = partition_views(V, world)[rank].  Handles the v1 and v2 heads, landscape and portrait scenes
+    (views stored transposed, true_shape (H > W)), ragged partitions (V % world != 0, ranks without views); all views
+    of a scene share one shape (mixed-shape scenes go through the single-GPU forward_inference_multi_ar)."""
 
     def __init__(self, model, rank: int, world: int, group=None):
         self.model, self.rank, self.world, self.group = model, rank, world, group
@@ -60,9 +83,12 @@ class ShardedPanSt3R:
     @torch.no_grad()
     def __call__(self, imgs: torch.Tensor, true_shape: torch.Tensor, classes, outdevice=None):
         from . import ops
+        from .modules.common import pos_grid
+        from .modules.must3r import _hw
+        from .modules.panoptic import PixelShuffleUpscaler
         from .panst3r import DEC_DIM, DINO_DIM, ENC_DIM
         m = self.model
-        B, V, _, H, W = imgs.shape
+        B, V = imgs.shape[:2]
         if B != 1:
             raise ops._l.Pst3rError("one scene per call (B == 1)")
         parts = partition_views(V, self.world)
@@ -70,12 +96,14 @@ class ShardedPanSt3R:
         s, e = parts[self.rank]
         nv = e - s
         ts = true_shape.cpu() if true_shape.is_cuda else true_shape
-        if int(ts.reshape(-1, 2)[0, 0]) != H or int(ts.reshape(-1, 2)[0, 1]) != W:
-            raise ops._l.Pst3rError("the sharded runner handles landscape scenes (true_shape == tensor shape) only")
+        H, W = _hw(ts)  # true size; portrait views (H > W) are stored transposed and processed in their true orientation
         P = m.must3r_encoder.patch_size
         hs, ws = H // P, W // P
         N = hs * ws
         dev = imgs.device
+        pd = m.panoptic_decoder
+        mt = pd.mask_transformer
+        pr = pd.precise
         # ---- per-view producers on the owning rank, written into one concatenated feature buffer
         cat = torch.empty((1, max(nv, 1), N, ENC_DIM + DEC_DIM + DINO_DIM), device=dev, dtype=torch.bfloat16)
         rows = cat.view(-1, cat.shape[-1])
@@ -95,30 +123,41 @@ class ShardedPanSt3R:
             x_loc = torch.empty((0, N, ENC_DIM), device=dev, dtype=torch.bfloat16)
         # ---- exchange 1: encoder tokens of every view, then the replicated sequential memory build
         x_all = gather_rows(x_loc, counts, self.group).view(1, V, N, ENC_DIM)
-        from .modules.common import pos_grid
         pos_all = pos_grid(hs, ws, dev)[0][None, None].expand(1, V, N, 2)
         with ops.sm_budget(max(ops.num_sms() - dino_sms, 8) if dino_sms else 0):
             mem = m.build_memory(x_all, pos_all, ts)
         if nv > 0:
             cur.wait_stream(side)
         pointmaps = None
-        mt = m.panoptic_decoder.mask_transformer
-        if nv > 0:
-            _, pointmaps, _ = m.must3r_decoder(x_all[:, s:e], pos_all[:, s:e], my_ts, mem, render=True, return_feats="last",
-                                               feats_out=rows[:, ENC_DIM:ENC_DIM + DEC_DIM])
-            src_loc, mask_f = m.panoptic_decoder.upscaler.forward_nhwc(rows, nv, hs, ws, f16_extra_bias=mt.level_embed.weight)
-            Cm = mask_f.shape[-1]
-            pooled_loc = ops.center_pool8(mask_f).view(nv * N, Cm)
-        else:
-            Cm = mt.mask_dim
-            src_loc = torch.empty((0, mt.hidden_dim), device=dev, dtype=torch.bfloat16)
-            pooled_loc = torch.empty((0, Cm), device=dev, dtype=torch.bfloat16)
-            mask_f = torch.empty((0, 8 * hs, 8 * ws, Cm), device=dev, dtype=torch.bfloat16)
+        portrait = H > W
+        grid = (ws, hs) if portrait else (hs, ws)  # the head works in the landscape storage convention
+        loftup = not isinstance(pd.upscaler, PixelShuffleUpscaler)
+        if loftup:  # v2: LoftUp's MinMaxScaler is batch-global -> 3-channel min/max all-reduce across the view shards
+            pd.upscaler.minmax_reduce = lambda mm: allreduce_minmax(mm, dev, self.group)
+        try:
+            if nv > 0:
+                _, pointmaps, _ = m.must3r_decoder(x_all[:, s:e], pos_all[:, s:e], my_ts, mem, render=True, return_feats="last",
+                                                   feats_out=rows[:, ENC_DIM:ENC_DIM + DEC_DIM])
+                src_loc, mask_f, grid, portrait, _ = pd._stack_features(None, my_imgs, my_ts, cat)
+                Cm = mask_f.shape[-1]
+                pooled_loc = ops.center_pool8(mask_f).view(nv * N, Cm)
+            else:
+                if loftup:
+                    allreduce_minmax(None, dev, self.group)
+                Cm = mt.mask_dim
+                mk = (lambda *sh: ops.Split.empty(sh, dev)) if pr else (lambda *sh: torch.empty(sh, device=dev, dtype=torch.bfloat16))
+                src_loc, pooled_loc, mask_f = mk(0, mt.hidden_dim), mk(0, Cm), mk(0, 8 * grid[0], 8 * grid[1], Cm)
+        finally:
+            if loftup:
+                pd.upscaler.minmax_reduce = None
         # ---- exchange 2: stride-16 features + centre-pooled mask features for the replicated query decoder
         tok_counts = [c * N for c in counts]
-        src_all = gather_rows(src_loc, tok_counts, self.group)
-        pooled_all = gather_rows(pooled_loc, tok_counts, self.group)
-        cls_emb = m.panoptic_decoder.text_encoder(classes, device=dev)
-        panout = mt.forward_nhwc(src_all, mask_f, (hs, ws), cls_emb, deep_supervision=m.panoptic_decoder.deep_supervision,
-                                 pooled=pooled_all)
+        src_all = _gather_any(src_loc, tok_counts, self.group)
+        pooled_all = _gather_any(pooled_loc, tok_counts, self.group)
+        cls_emb = pd.text_encoder(classes, device=dev, precise=pr)
+        panout = mt.forward_nhwc(src_all, mask_f, grid, cls_emb, deep_supervision=pd.deep_supervision,
+                                 pooled=pooled_all, portrait=portrait, precise=pr)
+        if outdevice is not None:
+            panout = pd._to_device(panout, outdevice, dev)
+            pointmaps = None if pointmaps is None else pointmaps.to(outdevice)
         return panout, pointmaps

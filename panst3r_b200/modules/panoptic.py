@@ -682,6 +682,8 @@ class LoftUpUpscaler(nn.Module):
         f16 = ops.gemm(feats, w16(self.patch_embed.weight), bias=pb)
         # guidance branch: x0.5 image -> MinMaxScaler (batch global) -> Fourier features -> GN(1) -> 2 x (conv3x3, GN(8), ReLU)
         half, minmax = ops.loftup_guidance(imgs.float())
+        if getattr(self, "minmax_reduce", None) is not None:  # view-sharded runs: batch-global extrema across ranks
+            minmax = self.minmax_reduce(minmax)
         gy, gx, fr = self._tables(Hh, Wh, dev)
         gn0, c1, gn1, c2, gn2 = (self.first_conv[i] for i in (0, 1, 2, 4, 5))
         ld0 = ((self.start_dim + 7) // 8) * 8

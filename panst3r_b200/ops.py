@@ -15,8 +15,9 @@ from . import lib as _l
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 STORE_PLAIN, STORE_TRANSPOSED, STORE_PIXSHUF2, STORE_D2S = 0, 1, 2, 3
 
-# launch counter (bench.py reports gpu_launches from this)
+# launch counter (bench.py reports gpu_launches from this) and algorithmic FLOPs issued per kernel class
 launches = 0
+flop_count = {}
 
 
 def _stream() -> int:
@@ -258,6 +259,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         e.rope_cs, e.rope_pos, e.rope_cols, e.rope_maxpos = cs.data_ptr(), pos.data_ptr(), rope_cols, cs.shape[0]
     _l.check(lib.pst3r_gemm_bf16(ab.data_ptr(), lda, wb.data_ptr(), ldb, M, N, K, C.byref(e), _stream()), "pst3r_gemm_bf16")
     launches += 1
+    flop_count["gemm"] = flop_count.get("gemm", 0.0) + 2.0 * M * N * K * max(1, e.split_terms)
     return out
 
 
@@ -297,6 +299,7 @@ def gemm_batched(a, w, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NO
     _l.check(lib.pst3r_gemm_bf16_batched(ab.data_ptr(), ab.stride(1), ab.stride(0), wb.data_ptr(), wb.stride(1), wb.stride(0), M, N, K,
                                          L, C.byref(e), ob.stride(0), bias_bs, _stream()), "pst3r_gemm_bf16_batched")
     launches += 1
+    flop_count["gemm"] = flop_count.get("gemm", 0.0) + 2.0 * L * M * N * K * max(1, e.split_terms)
     return out
 
 
@@ -416,6 +419,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optio
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     _l.check(lib.pst3r_attention(C.byref(a), _stream()), "pst3r_attention")
     launches += 1 if splits <= 1 else 2
+    flop_count["attention"] = flop_count.get("attention", 0.0) + 4.0 * B * H * Nq * Nk * hd
     return out
 
 

@@ -351,17 +351,19 @@ class PanSt3R(nn.Module):
         return model
 
 
-def build_panst3r(variant: str = "v1", enc_depth=24, dec_depth=12, dino_depth=24, mixer_layers=3) -> PanSt3R:
-    """Reference configuration (configs/base.yaml, base_v2.yaml) with reducible depths for tests."""
+def build_panst3r(variant: str = "v1", enc_depth=24, dec_depth=12, dino_depth=24, mixer_layers=3,
+                  head_precision: str = "fp32") -> PanSt3R:
+    """Reference configuration (configs/base.yaml, base_v2.yaml) with reducible depths for tests.  head_precision:
+    "fp32" = the reference's policy for the panoptic head (panst3r.py:236-245), "bf16" = plain bf16 operands."""
     enc = Dust3rEncoder(depth=enc_depth)
     dec = MUSt3R(depth=dec_depth)
     dino = DinoV2Encoder(depth=dino_depth)
     if variant == "v1":
-        pd = PanopticDecoder(upscaler=PixelShuffleUpscaler(input_dim=ENC_DIM + DEC_DIM + DINO_DIM))
+        pd = PanopticDecoder(upscaler=PixelShuffleUpscaler(input_dim=ENC_DIM + DEC_DIM + DINO_DIM), precision=head_precision)
     elif variant == "v2":
         from .modules.panoptic import InputMixer, LoftUpUpscaler
         pd = PanopticDecoder(input_mixer=InputMixer([512, 512], 16, 2816, 768, num_layers=mixer_layers),
-                             upscaler=LoftUpUpscaler(input_dim=768, dim=384), mask_dim=384)
+                             upscaler=LoftUpUpscaler(input_dim=768, dim=384), mask_dim=384, precision=head_precision)
     else:
         raise ValueError(variant)
     return PanSt3R(enc, dec, dino, pd).eval()

@@ -38,6 +38,14 @@ def _worker(rank, world, port, q):
             s, e = parts[rank]
             got = gather_rows(full[s:e].clone(), [b - a for a, b in parts])
             assert torch.equal(got, full), (V, rank)
+        # (1b) LoftUp's batch-global MinMaxScaler across view shards: one MAX all-reduce of [-min, max]; a rank without
+        #      views contributes the neutral element (model/upscalers/loftup.py:14-19)
+        from panst3r_b200.dist import allreduce_minmax
+        mine = torch.tensor([[-0.5 - rank, 0.25 + rank], [0.1 * rank, 0.9 - 0.1 * rank], [-1.0, 1.0]])
+        got = allreduce_minmax(mine, "cpu")
+        assert torch.equal(got, torch.tensor([[-1.5, 1.25], [0.0, 0.9], [-1.0, 1.0]])), got
+        got = allreduce_minmax(mine if rank == 0 else None, "cpu")
+        assert torch.equal(got, torch.tensor([[-0.5, 0.25], [0.0, 0.9], [-1.0, 1.0]])), got
         # (2) shard/replicate scheme of the head: per-view upscaler on the owning rank, gather of stride-16 features
         #     and mask features, replicated query decoder -> local slice equals the single-process result
         from helpers import CLASSES, build_oracle_head, head_inputs

@@ -1,0 +1,38 @@
+#!/bin/bash
+# One gpurun session: probe, GPU tests, smoke, bench, error table, sanitizer.  Every step has its own timeout and log
+# under gpurun_out/ so that one failure does not lose the others.  Usage: tools/gpu_session.sh [steps...]
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+STEPS="${@:-probe tests smoke bench errtab}"
+for s in $STEPS; do
+  echo "=== $s $(date +%T)"
+  case $s in
+    probe)
+      { nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv; nproc;
+        python - <<'PY'
+import importlib
+for m in ("must3r", "croco", "dust3r", "curope", "xformers", "asmk"):
+    try:
+        importlib.import_module(m); print(m, "IMPORTABLE")
+    except Exception as e:
+        print(m, "absent:", type(e).__name__, e)
+PY
+        pip download must3r --no-deps -d /tmp/x 2>&1 | tail -1; find / -iname '*must3r*' -not -path '*/proc/*' 2>/dev/null | grep -v "$PWD" | head; } > gpurun_out/probe.log 2>&1 ;;
+    tests)   timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" ;;
+    testsall) timeout 1800 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" ;;
+    precise) timeout 900 python -m pytest tests/test_gpu_precise.py -m gpu -q -s --timeout 600 > gpurun_out/pytest_precise.log 2>&1; echo "rc=$?" ;;
+    smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
+    bench)   timeout 900 python bench.py > gpurun_out/bench_v1.json 2> gpurun_out/bench_v1.err; echo "bench rc=$?" ;;
+    bench16) timeout 900 python bench.py --head-precision bf16 --no-gpu-reference --no-cpu-baseline > gpurun_out/bench_v1_bf16head.json 2> gpurun_out/bench_v1_bf16head.err ;;
+    benchv2) timeout 900 python bench.py --variant v2 --no-gpu-reference --no-cpu-baseline > gpurun_out/bench_v2.json 2> gpurun_out/bench_v2.err ;;
+    benchc3) timeout 900 python bench.py --views 64 --keyframes 8 --no-gpu-reference --no-cpu-baseline --steps 5 > gpurun_out/bench_cfg3.json 2> gpurun_out/bench_cfg3.err ;;
+    benchref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ;;
+    errtab)  timeout 1200 python tools/error_table.py > gpurun_out/errtab.log 2>&1; echo "errtab rc=$?" ;;
+    memcheck) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_precise.py tests/test_gpu_kernels.py -m gpu -q -x -k "not full_size and not 12288 and not 4864" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" ;;
+    racecheck) timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "layernorm or mask_helpers or patchify or rope" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" ;;
+    launches) timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r02.csv python tools/profile_step.py step > gpurun_out/launches_r02.log 2>&1 ;;
+    *) echo "unknown step $s" ;;
+  esac
+done
+echo "=== done $(date +%T)"
+tail -5 gpurun_out/pytest.log 2>/dev/null
