@@ -212,9 +212,10 @@ int pst3r_convert(const void* x, int32_t x_kind, int64_t ldx, void* y, int32_t y
 /* Masked row softmax of the reference-precision attention (the query decoder's nn.MultiheadAttention,
  * mask_transformer.py:314,372,395-398, evaluated as S = QK^T GEMM -> this -> PV GEMM on split operands):
  * out[r][k] = softmax over the unblocked keys of S[r][0..Nk) (fp32, scale already applied); mask_bits as in
- * pst3r_attention, row q = r % Q (shared by all heads), NULL = no mask.  out of kind out_kind, row stride ldo. */
+ * pst3r_attention, row q = r % Q (shared by all heads), NULL = no mask.  out of kind out_kind, row stride ldo; a split
+ * output keeps its lo parts out_lo_off (>= Nk, a multiple of 8 when it feeds the P V GEMM) elements after the hi parts. */
 int pst3r_softmax_rows(const float* S, int64_t lds, int32_t rows, int32_t Nk, const uint32_t* mask_bits, int64_t mask_sq,
-                       int32_t Q, void* out, int32_t out_kind, int64_t ldo, pst3r_stream_t stream);
+                       int32_t Q, void* out, int32_t out_kind, int64_t ldo, int64_t out_lo_off, pst3r_stream_t stream);
 
 /* Patchify (im2col) for the ViT patch embeddings: img fp32 [B,3,H,W] -> bf16 [B*(H/P)*(W/P), ldo] with
  * column = c*P*P + i*P + j (Conv2d weight flattening).  Columns [3*P*P, ldo) are zero-filled. */

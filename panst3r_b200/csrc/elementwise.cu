@@ -224,7 +224,8 @@ __global__ void convert_kernel(const void* __restrict__ x, int x_kind, long long
 // bit mask leaves open (bit k&31 of word [q][k>>5] set => blocked; q = r % Q: the mask is shared by all heads,
 // mask_transformer.py:272).  S fp32 [rows][>=Nk] already carries the 1/sqrt(hd) scale.  One block per row; S stays in L2.
 __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, int Nk, const uint32_t* __restrict__ bits,
-                                    long long mask_sq, int Q, void* __restrict__ out, int out_kind, long long ldo) {
+                                    long long mask_sq, int Q, void* __restrict__ out, int out_kind, long long ldo,
+                                    long long out_lo_off) {
   const int r = blockIdx.x;
   const float* srow = S + (long long)r * lds;
   const uint32_t* mrow = bits ? bits + (long long)(r % Q) * mask_sq : nullptr;
@@ -260,7 +261,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, 
   const float inv = red[32] > 0.0f ? 1.0f / red[32] : 0.0f;
   for (int k = threadIdx.x; k < Nk; k += blockDim.x) {
     const float pv = blocked(k) ? 0.0f : expf(srow[k] - mx) * inv;
-    kstore(out, out_kind, (long long)r * ldo + k, Nk, pv);
+    kstore(out, out_kind, (long long)r * ldo + k, out_lo_off, pv);
   }
 }
 
@@ -580,13 +581,14 @@ extern "C" int pst3r_convert(const void* x, int32_t x_kind, int64_t ldx, void* y
 }
 
 extern "C" int pst3r_softmax_rows(const float* S, int64_t lds, int32_t rows, int32_t Nk, const uint32_t* mask_bits,
-                                  int64_t mask_sq, int32_t Q, void* out, int32_t out_kind, int64_t ldo, pst3r_stream_t s_) {
+                                  int64_t mask_sq, int32_t Q, void* out, int32_t out_kind, int64_t ldo, int64_t out_lo_off,
+                                  pst3r_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
   PST3R_CHECK_ARG(S && out && rows > 0 && Nk > 0 && lds >= Nk && out_kind >= 0 && out_kind <= 2 && Q > 0 &&
-                      ldo >= (out_kind == PST3R_KIND_SPLIT ? 2 : 1) * (int64_t)Nk,
+                      (out_kind == PST3R_KIND_SPLIT ? (out_lo_off >= Nk && ldo >= out_lo_off + Nk) : ldo >= Nk),
                   "softmax_rows: bad args");
   if (mask_bits) PST3R_CHECK_ARG(mask_sq * 32 >= Nk, "softmax_rows: mask rows shorter than Nk");
-  softmax_rows_kernel<<<rows, 256, 0, s>>>(S, lds, Nk, mask_bits, mask_sq, Q, out, out_kind, ldo);
+  softmax_rows_kernel<<<rows, 256, 0, s>>>(S, lds, Nk, mask_bits, mask_sq, Q, out, out_kind, ldo, out_lo_off);
   PST3R_CHECK_CUDA(cudaGetLastError());
   return PST3R_OK;
 }

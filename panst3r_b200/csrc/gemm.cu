@@ -65,7 +65,40 @@ struct GemmEpi {
   long long out_lo_off;
   int res_kind;
   long long res_lo_off;
+  // plane-major fp32 store (PST3R_STORE_TRANSPOSED) through shared memory + TMA tile stores: every epilogue warp stages
+  // its 32 rows x 32 columns transposed ([column][row], conflict free) and one lane issues a 32 x 32 box store — 32 full
+  // 128-byte lines per instruction instead of 32 per-thread scalar stores with 64-bit address arithmetic each (the
+  // mask-logit einsum was issue bound in exactly that loop: 21 instructions per element, profiles/r02_mask_logit_store.md)
+  int tma_store;
+  // Accumulator promotion (PROMOTE kernels, split mode with long reductions).  The tensor core ADDS into its fp32
+  // accumulator with truncation, a bias of ~2^-24 per tcgen05.mma that grows linearly with the reduction length
+  // (measured: 1.2e-4 after 3 x 11264 / 16 = 2112 accumulations, profiles/r02_error_table.md).  The K loop is therefore cut
+  // into chunks of `promote` k-iterations that alternate between the two TMEM accumulators; the epilogue warps, idle
+  // during the main loop otherwise, fold every finished chunk into fp32 REGISTER accumulators (round-to-nearest adds).
+  int promote;
 };
+
+constexpr uint32_t GEMM_OUT_STAGE_BYTES = 8 * 32 * 32 * 4;  // 8 epilogue warps x (32 x 32 fp32)
+
+// TMA-store epilogue of one 32-column chunk of one warp (all 32 lanes take part).  row0: first of the warp's 32 rows.
+__device__ __forceinline__ void epilogue_chunk_tma(const GemmEpi& ep, const CUtensorMap* tmOut, float* stage, float (&v)[32],
+                                                   int row0, int col0, int lane) {
+  if (ep.alpha != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= ep.alpha;
+  }
+  if (lane == 0) bulk_wait_read_all();  // the previous box of this warp has left the staging tile
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) stage[i * 32 + lane] = v[i];
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    const int b = row0 / (int)ep.rows_per_batch;
+    tma_store_3d(tmOut, stage, row0 - b * (int)ep.rows_per_batch, col0, b);
+    bulk_commit_group();
+  }
+}
 
 __device__ __forceinline__ void split_pack8(const float* v, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
@@ -103,8 +136,10 @@ struct GemmSmem {
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr uint32_t OUT_OFFSET = STAGES * STAGE_BYTES;  // epilogue staging tiles for TMA stores
+  static constexpr uint32_t BAR_OFFSET = OUT_OFFSET + GEMM_OUT_STAGE_BYTES;
   static constexpr uint32_t TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static_assert(TOTAL + 1024 <= 232448, "shared memory budget");
   static constexpr uint32_t DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
 };
 
@@ -376,10 +411,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PROMOTE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmEpi ep, const int M, const int N, const int K) {
+                    const __grid_constant__ CUtensorMap tmOut, const GemmEpi ep, const int M, const int N, const int K) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -399,6 +434,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
   const int terms = ep.split_terms > 1 ? ep.split_terms : 1;
   const int num_k_iters = num_k_blocks * terms;  // split mode: one pass over the k-blocks per product term
+  // PROMOTE: the reduction is cut into chunks that alternate between the two accumulators (see GemmEpi::promote)
+  const int chunk_iters = PROMOTE ? ep.promote : num_k_iters;
+  const int num_chunks = (num_k_iters + chunk_iters - 1) / chunk_iters;
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   if (warp == 0 && lane == 0) {
@@ -480,47 +518,50 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      int local = 0;  // accumulator hand-overs so far: one per (tile, chunk)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_blk = (tile % tiles_per_batch) / num_m_blocks;
         const int n_rem = N - n_blk * BN;
         const int n_mma = n_rem >= BN ? BN : ((n_rem + 15) & ~15);
         const uint32_t idesc = make_idesc_bf16(GEMM_BM, n_mma, 0, 0);
-        const int acc = local & 1;
-        const uint32_t acc_ph = (local >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k_iters; ++kb) {
-          mbar_wait(&full_bar[s], ph);
+        for (int ch = 0; ch < num_chunks; ++ch, ++local) {
+          const int acc = local & 1;
+          const uint32_t acc_ph = (local >> 1) & 1;
+          mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + L::A_BYTES;
-          const uint64_t a_desc = make_smem_desc_sw128(a_addr, 0, 1024);
-          const uint64_t b_desc = make_smem_desc_sw128(b_addr, 0, 1024);
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          const int k0 = ch * chunk_iters;
+          const int k1 = min(k0 + chunk_iters, num_k_iters);
+          for (int kb = k0; kb < k1; ++kb) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+            const uint32_t b_addr = a_addr + L::A_BYTES;
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr, 0, 1024);
+            const uint64_t b_desc = make_smem_desc_sw128(b_addr, 0, 1024);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // +32 B per UMMA_K step inside the 128 B swizzle span (address field is in 16 B units)
-            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // +32 B per UMMA_K step inside the 128 B swizzle span (address field is in 16 B units)
+              umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - k0) | k) != 0);
+            }
+            umma_commit(&empty_bar[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
-          umma_commit(&empty_bar[s]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          umma_commit(&tfull_bar[acc]);
         }
-        umma_commit(&tfull_bar[acc]);
       }
     }
   } else {
     // ------------------------------- epilogue -----------------------------------
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int cgrp = (warp - 2) >> 2;  // which half of the 32-column chunks
+    float* out_stage = reinterpret_cast<float*>(smem + L::OUT_OFFSET) + (warp - 2) * 1024;
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int bidx = tile / tiles_per_batch;
       const int trem = tile - bidx * tiles_per_batch;
       const int m_blk = trem % num_m_blocks;
       const int n_blk = trem / num_m_blocks;
-      const int acc = local & 1;
-      const uint32_t acc_ph = (local >> 1) & 1;
       int row = m_blk * GEMM_BM + quad * 32 + lane;
       int m_lim = M;
       const float2 ln = ln_row_stats(ep, row, M);  // before the accumulator wait: overlaps the main loop
@@ -529,25 +570,67 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         row = (m_blk / ep.conv_tpr) * ep.conv_w + xcol;
         m_lim = xcol < ep.conv_w ? 0x7fffffff : 0;  // segment tail beyond the image row: nothing to store
       }
-      mbar_wait(&tfull_bar[acc], acc_ph);
-      tc_fence_after();
-      const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       const int n_rem = N - n_blk * BN;
-#pragma unroll 1
-      for (int c = cgrp; c < BN / 32; c += 2) {
-        if (c * 32 >= n_rem) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(t_base + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
+      if constexpr (PROMOTE) {
+        // fold every finished K chunk into register accumulators; this warp owns the 32-column chunks cgrp, cgrp + 2, ...
+        constexpr int NCH = (BN / 32 + 1) / 2;
+        float accv[NCH][32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_chunk(ep, v, row, n_blk * BN + c * 32, m_lim, N, bidx, ln);
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) accv[j][i] = 0.0f;
+        for (int ch = 0; ch < num_chunks; ++ch, ++local) {
+          const int acc = local & 1;
+          mbar_wait(&tfull_bar[acc], (local >> 1) & 1);
+          tc_fence_after();
+          const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) {
+            const int c = cgrp + 2 * j;
+            if (c < BN / 32 && c * 32 < n_rem) {  // warp-uniform
+              uint32_t r[32];
+              tmem_ld32(t_base + c * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) accv[j][i] += __uint_as_float(r[i]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          const int c = cgrp + 2 * j;
+          if (c < BN / 32 && c * 32 < n_rem) epilogue_chunk(ep, accv[j], row, n_blk * BN + c * 32, m_lim, N, bidx, ln);
+        }
+      } else {
+        const int acc = local & 1;
+        const uint32_t acc_ph = (local >> 1) & 1;
+        mbar_wait(&tfull_bar[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c = cgrp; c < BN / 32; c += 2) {
+          if (c * 32 >= n_rem) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld32(t_base + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (ep.tma_store)
+            epilogue_chunk_tma(ep, &tmOut, out_stage, v, m_blk * GEMM_BM + quad * 32, n_blk * BN + c * 32, lane);
+          else
+            epilogue_chunk(ep, v, row, n_blk * BN + c * 32, m_lim, N, bidx, ln);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        ++local;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (ep.tma_store && lane == 0) bulk_wait_all();  // our box stores are performed before the grid counts as complete
   }
 
   tc_fence_before();
@@ -558,11 +641,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& ep, int M, int N, int K,
-                       cudaStream_t stream) {
+template <int BN, int STAGES, bool PROMOTE = false>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const GemmEpi& ep, int M,
+                       int N, int K, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
-  auto kern = gemm_bf16_tn_kernel<BN, STAGES>;
+  auto kern = gemm_bf16_tn_kernel<BN, STAGES, PROMOTE>;
   static bool configured = false;
   if (!configured) {
     PST3R_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
@@ -570,7 +653,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN) * ep.batches;
   const int grid = tiles < sm_budget() ? tiles : sm_budget();
-  PST3R_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::DYN_BYTES, stream, tmA, tmB, ep, M, N, K));
+  PST3R_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::DYN_BYTES, stream, tmA, tmB, tmOut, ep, M, N, K));
   return PST3R_OK;
 }
 
@@ -579,6 +662,24 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 #include "gemm2.cuh"
 
 using namespace pst3r;
+
+static bool tma_store_enabled() {  // PST3R_TMA_STORE=0: per-thread stores (A/B measurements)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PST3R_TMA_STORE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static bool promote_enabled() {  // PST3R_PROMOTE=0: plain accumulation in split mode (A/B measurements)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PST3R_PROMOTE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 struct ConvCfg { int V, H, W, C, cpad; };
 struct BatchCfg { int batches; long long a_bs, b_bs, out_bs, bias_bs; };
@@ -647,6 +748,31 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
     ep.conv_cblocks = conv->cpad / 64; ep.conv_w = conv->W; ep.conv_h = conv->H; ep.conv_tpr = (conv->W + GEMM_BM - 1) / GEMM_BM;
   }
 
+  // Split mode with a long reduction: promote the accumulator every PROMOTE_ITERS k-iterations (GemmEpi::promote);
+  // short reductions (<= 16 iterations: 64 truncating accumulations, 4e-6) keep the plain kernels and tile shapes
+  constexpr int PROMOTE_ITERS = 8;
+  const int k_iters_total = ((K + GEMM_BK - 1) / GEMM_BK) * (terms ? terms : 1);
+  ep.promote = (terms && k_iters_total > 16 && promote_enabled()) ? PROMOTE_ITERS : 0;
+
+  // Plane-major fp32 planes (the mask-logit einsum): TMA tile stores when the layout allows it
+  CUtensorMap tmOut;
+  memset(&tmOut, 0, sizeof(tmOut));
+  ep.tma_store = 0;
+  if (e->store_mode == PST3R_STORE_TRANSPOSED && e->out_kind == PST3R_KIND_F32 && tma_store_enabled() && !conv && nb == 1 &&
+      !ep.promote &&
+      !e->bias && !e->residual && !e->col_scale && !e->rope_cs && !e->ln_stats && e->act == PST3R_ACT_NONE &&
+      (e->rows_per_batch % 32) == 0 && (M % e->rows_per_batch) == 0 && (e->ldt % 4) == 0 && e->ldt >= e->rows_per_batch &&
+      (reinterpret_cast<uintptr_t>(e->out) & 15) == 0 &&
+      (M == e->rows_per_batch || ((e->batch_stride % 4) == 0 && e->batch_stride >= (int64_t)N * e->ldt))) {
+    const uint64_t nbat = (uint64_t)(M / e->rows_per_batch);
+    uint64_t dO[3] = {(uint64_t)e->rows_per_batch, (uint64_t)N, nbat};
+    uint64_t sO[3] = {4, (uint64_t)e->ldt * 4, (uint64_t)(nbat > 1 ? e->batch_stride : (int64_t)N * e->ldt) * 4};
+    uint32_t bO[3] = {32, 32, 1};
+    int r = encode_tmap(&tmOut, e->out, 4, 3, dO, sO, bO, /*swizzle128=*/false);
+    if (r) return r;
+    ep.tma_store = 1;
+  }
+
   // Tile-width heuristic: the widest BN whose tile count still fills the machine.
   const int sms = sm_budget();
   const int mb = (M + GEMM_BM - 1) / GEMM_BM;
@@ -655,7 +781,7 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   // waves x bytes-per-k-block, i.e. the per-SM load time of the slowest SM.
   int BN = 64;
   long long best = -1;
-  for (int cand = 64; cand <= 256; cand *= 2) {
+  for (int cand = 64; cand <= (ep.promote ? 128 : 256); cand *= 2) {  // promotion keeps BN/2 accumulators per thread
     const long long tiles = (long long)mb * ((N + cand - 1) / cand) * nb;
     const long long waves = (tiles + sms - 1) / sms;
     const long long cost = waves * (128 + cand);
@@ -664,7 +790,7 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   }
 
   // large plain GEMMs with N % 256 == 0 go to the 2-CTA kernel (256 x 256 tiles per SM pair)
-  const bool use2 = !conv && nb == 1 && gemm2_enabled() && (N % G2_BN) == 0 &&
+  const bool use2 = !conv && nb == 1 && !ep.promote && gemm2_enabled() && (N % G2_BN) == 0 &&
                     (long long)((M + 255) / 256) * (N / G2_BN) >= (sms / 2);
   // split mode: the hi / lo part is dimension 2 of both maps (a plain-bf16 A has a single part)
   const uint64_t a_parts = terms == 3 ? 2 : 1;
@@ -678,7 +804,7 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
     if (r) return r;
     r = encode_tmap(&tB2, B, 2, terms ? 3 : 2, dB, sB, bB);
     if (r) return r;
-    return launch_gemm2(tA2, tB2, ep, M, N, K, stream);
+    return launch_gemm2(tA2, tB2, tmOut, ep, M, N, K, stream);
   }
 
   CUtensorMap tmA, tmB;
@@ -730,10 +856,13 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
     int r = encode_tmap(&tmB, B, 2, 2, dims, str, box);
     if (r) return r;
   }
+  if (ep.promote)
+    return BN == 128 ? launch_gemm<128, 6, true>(tmA, tmB, tmOut, ep, M, N, K, stream)
+                     : launch_gemm<64, 8, true>(tmA, tmB, tmOut, ep, M, N, K, stream);
   switch (BN) {
-    case 256: return launch_gemm<256, 4>(tmA, tmB, ep, M, N, K, stream);
-    case 128: return launch_gemm<128, 6>(tmA, tmB, ep, M, N, K, stream);
-    default: return launch_gemm<64, 8>(tmA, tmB, ep, M, N, K, stream);
+    case 256: return launch_gemm<256, 4>(tmA, tmB, tmOut, ep, M, N, K, stream);
+    case 128: return launch_gemm<128, 6>(tmA, tmB, tmOut, ep, M, N, K, stream);
+    default: return launch_gemm<64, 8>(tmA, tmB, tmOut, ep, M, N, K, stream);
   }
 }
 

@@ -16,7 +16,8 @@ constexpr int G2_STAGES = 6;
 constexpr uint32_t G2_A_BYTES = GEMM_BM * GEMM_BK * 2;          // 16 KB
 constexpr uint32_t G2_B_BYTES = (G2_BN / 2) * GEMM_BK * 2;      // 16 KB (half of the B tile)
 constexpr uint32_t G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr uint32_t G2_BAR_OFFSET = G2_STAGES * G2_STAGE_BYTES;
+constexpr uint32_t G2_OUT_OFFSET = G2_STAGES * G2_STAGE_BYTES;  // epilogue staging tiles for TMA stores
+constexpr uint32_t G2_BAR_OFFSET = G2_OUT_OFFSET + GEMM_OUT_STAGE_BYTES;
 constexpr uint32_t G2_DYN_BYTES = G2_BAR_OFFSET + (2 * G2_STAGES + 4) * 8 + 16 + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -83,7 +84,7 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const GemmEpi ep, const int M, const int N, const int K) {
+                     const __grid_constant__ CUtensorMap tmOut, const GemmEpi ep, const int M, const int N, const int K) {
   constexpr int BN = G2_BN;
   constexpr int STAGES = G2_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -194,6 +195,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ------------------------------- epilogue (both CTAs) -----------------------
     const int quad = warp & 3;
     const int cgrp = (warp - 2) >> 2;
+    float* out_stage = reinterpret_cast<float*>(smem + G2_OUT_OFFSET) + (warp - 2) * 1024;
     int local = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
       const int m_blk = tile % num_m_blocks;
@@ -213,12 +215,16 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_chunk(ep, v, row, n_blk * BN + c * 32, M, N, 0, ln);
+        if (ep.tma_store)
+          epilogue_chunk_tma(ep, &tmOut, out_stage, v, m_blk * 256 + (int)rank * 128 + quad * 32, n_blk * BN + c * 32, lane);
+        else
+          epilogue_chunk(ep, v, row, n_blk * BN + c * 32, M, N, 0, ln);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
     }
+    if (ep.tma_store && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -238,8 +244,8 @@ static bool gemm2_enabled() {
   return v == 1;
 }
 
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& ep, int M, int N, int K,
-                        cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const GemmEpi& ep, int M,
+                        int N, int K, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
@@ -258,7 +264,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  PST3R_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel, tmA, tmB, ep, M, N, K));
+  PST3R_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel, tmA, tmB, tmOut, ep, M, N, K));
   return PST3R_OK;
 }
 

@@ -95,7 +95,7 @@ SIGNATURES = {
     "pst3r_rope2d": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f, _f, _p]),
     "pst3r_add_bcast": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _i32, _p, _i32, _i64, _i32, _i32, _p]),
     "pst3r_convert": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _i32, _i32, _p]),
-    "pst3r_softmax_rows": (C.c_int, [_p, _i64, _i32, _i32, _p, _i64, _i32, _p, _i32, _i64, _p]),
+    "pst3r_softmax_rows": (C.c_int, [_p, _i64, _i32, _i32, _p, _i64, _i32, _p, _i32, _i64, _i64, _p]),
     "pst3r_cast_f32_to_bf16": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p]),
     "pst3r_cast_bf16_to_f32": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p]),
     "pst3r_patchify": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i64, _p]),

@@ -327,8 +327,9 @@ class MaskTransformer(nn.Module):
         L = self.num_layers
         if precise:
             k_all = ops.gemm(src_pos, wk, bias=bk, out_dtype="split")  # (Nk, L*d)
-            vT = ops.Split.empty((L * d, Nk), dev)                      # V^T: the PV GEMM wants its B operand K-major
-            ops.gemm(src, wv, bias=bv, out=vT, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=Nk, batch_stride=0, ldt=2 * Nk)
+            vT = ops.Split.empty((L * d, Nk), dev, align=8)             # V^T: the PV GEMM wants its B operand K-major
+            ops.gemm(src, wv, bias=bv, out=vT, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=Nk, batch_stride=0,
+                     ldt=vT.hi.stride(0))
             k_of = lambda i: k_all[:, i * d:(i + 1) * d].view(Nk, H, hd).permute(1, 0, 2)  # noqa: E731
             v_of = lambda i: vT[i * d:(i + 1) * d].view(H, hd, Nk)                          # noqa: E731
         else:
@@ -362,8 +363,9 @@ class MaskTransformer(nn.Module):
             wv_s, bv_s = self._slice_w(m.in_proj_weight, 2 * d, 3 * d, "wv", precise), self._slice_w(m.in_proj_bias, 2 * d, 3 * d, "bv")
             if precise:
                 kk = ops.gemm(qk_in, wk_s, bias=bk_s, out_dtype="split").view(Q, H, hd).permute(1, 0, 2)
-                vvT = ops.Split.empty((d, Q), dev)
-                ops.gemm(output, wv_s, bias=bv_s, out=vvT, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=Q, batch_stride=0, ldt=2 * Q)
+                vvT = ops.Split.empty((d, Q), dev, align=8)
+                ops.gemm(output, wv_s, bias=bv_s, out=vvT, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=Q, batch_stride=0,
+                         ldt=vvT.hi.stride(0))
                 t = self._mha(qk_in, kk, vvT.view(H, hd, Q), m, None, output, True)
             else:
                 kk = ops.gemm(qk_in, wk_s, bias=bk_s)

@@ -71,10 +71,13 @@ class Split:
         self.hi, self.lo_off = hi, int(lo_off)
 
     @staticmethod
-    def empty(shape, device) -> "Split":
+    def empty(shape, device, align: int = 1) -> "Split":
+        """align > 1: the lo parts start at the next multiple of `align` columns (a GEMM operand needs lo_off % 8 == 0;
+        such a matrix is not `packed()`: only the GEMM and the kernels taking an explicit lo offset accept it)."""
         *lead, cols = shape
-        buf = torch.empty((*lead, 2 * cols), device=device, dtype=torch.bfloat16)
-        return Split(buf[..., :cols], cols)
+        pitch = -(-cols // align) * align
+        buf = torch.empty((*lead, 2 * pitch), device=device, dtype=torch.bfloat16)
+        return Split(buf[..., :cols], pitch)
 
     @staticmethod
     def from_float(x: torch.Tensor) -> "Split":
@@ -537,16 +540,15 @@ def softmax_rows(S: torch.Tensor, Q: int, mask_bits: Optional[torch.Tensor] = No
     _need(S, torch.float32, "softmax_rows.S")
     rows, Nk, lds = _rows2d(S, "softmax_rows.S")
     if out is None:
-        out = Split.empty(S.shape, S.device)
-    _packed(out, "softmax_rows.out")
+        out = Split.empty(S.shape, S.device, align=8)  # feeds the P V GEMM: lo offset a multiple of 8
     _, _, ldo = _rows2d(_base(out), "softmax_rows.out")
     mptr, msq = None, 0
     if mask_bits is not None:
         if mask_bits.dtype not in (torch.int32, torch.uint32) or mask_bits.stride(-1) != 1:
             raise _l.Pst3rError("softmax_rows.mask_bits: expected int32 [1, Q, W]")
         mptr, msq = mask_bits.data_ptr(), mask_bits.stride(-2)
-    _l.check(lib.pst3r_softmax_rows(S.data_ptr(), lds, rows, Nk, mptr, msq, Q, _base(out).data_ptr(), _kind(out), ldo, _stream()),
-             "pst3r_softmax_rows")
+    _l.check(lib.pst3r_softmax_rows(S.data_ptr(), lds, rows, Nk, mptr, msq, Q, _base(out).data_ptr(), _kind(out), ldo,
+                                    out.lo_off if isinstance(out, Split) else 0, _stream()), "pst3r_softmax_rows")
     launches += 1
     return out
 

@@ -132,11 +132,13 @@ def test_row_kernels_on_split_operands(ops):
     assert relmax(ops.nhwc_to_nchw_f32(t), val(t).transpose(1, 2)) < 1e-6
 
 
-def test_precise_attention_pieces(ops):
+@pytest.mark.parametrize("Nk", [1400, 12, 201])
+def test_precise_attention_pieces(ops, Nk):
     """The unfused reference-precision attention of the query decoder: per-head QK^T (batched split GEMM over head
-    slices, K = 96 = 1.5 k-blocks), masked row softmax, per-head PV against V^T (K = Nk not a multiple of 64)."""
+    slices, K = 96 = 1.5 k-blocks), masked row softmax, per-head PV against V^T (K = Nk not a multiple of 64, nor of 8
+    for tiny scenes: the lo parts then sit at the next multiple of 8)."""
     from test_gpu_kernels import pack_bits
-    H, Q, Nk, hd = 8, 200, 1400, 96
+    H, Q, hd = 8, 200, 96
     d = H * hd
     q, k, v = r64(Q, d), r64(Nk, 6 * d), r64(Nk, d)
     sq, sk = split_of(ops, q), split_of(ops, k)
@@ -152,12 +154,13 @@ def test_precise_attention_pieces(ops):
     assert relmax(S, ref_s) < TOL_SPLIT
     P = ops.softmax_rows(S, Q, bits)
     ref_p = S.double().masked_fill(mask, float("-inf")).softmax(-1)
-    assert relmax(val(P), ref_p) < TOL_SPLIT and val(P)[:, mask[0]].abs().max().item() == 0
+    assert P.lo_off % 8 == 0 and relmax(val(P), ref_p) < TOL_SPLIT and val(P)[:, mask[0]].abs().max().item() == 0
     # V^T through the transposed split store, then O_h = P_h V_h
     w = r64(d, 64, scale=0.125)
     src = r64(Nk, 64)
-    vT = ops.Split.empty((d, Nk), "cuda")
-    ops.gemm(split_of(ops, src), split_of(ops, w), out=vT, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=Nk, batch_stride=0, ldt=2 * Nk)
+    vT = ops.Split.empty((d, Nk), "cuda", align=8)
+    ops.gemm(split_of(ops, src), split_of(ops, w), out=vT, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=Nk, batch_stride=0,
+             ldt=vT.hi.stride(0))
     o = ops.Split.empty((Q, d), "cuda")
     ops.gemm_batched(P, vT.view(H, hd, Nk), out=o.view(Q, H, hd).permute(1, 0, 2))
     ref_o = torch.einsum("hqk,hdk->qhd", val(P), val(vT).view(H, hd, Nk)).reshape(Q, d)
