@@ -53,6 +53,46 @@ def _build_ref_head(ref, variant):
     return m
 
 
+def record_pooled_logits(m):
+    """Context manager: records, for every prediction-head call of the REFERENCE mask transformer, the bilinearly
+    downsampled mask logits its attention mask is thresholded from (mask_transformer.py:264-272, 279-288) as (Q, Nk)
+    fp32 tensors in view-major token order.  The query decoder is a discontinuous function of these values (sign
+    decisions), so parity tests need them: see tests/test_gpu_precise.py."""
+    import contextlib
+
+    @contextlib.contextmanager
+    def ctx():
+        rec = []
+        mt = m.mask_transformer
+        orig = mt._compute_masks
+
+        def hook(mask_feats, mask_embed, attn_mask_target_size):
+            om, am = orig(mask_feats, mask_embed, attn_mask_target_size)
+            if am is not None:  # (b, 1, Q, hs, ws) per view chunk -> collected per call below
+                rec[-1].append(am.detach().clone())
+            return om, am
+        orig_fph = mt.forward_prediction_heads
+
+        def fph(*a, **k):
+            rec.append([])
+            return orig_fph(*a, **k)
+        mt._compute_masks, mt.forward_prediction_heads = hook, fph
+        try:
+            yield rec
+        finally:
+            mt._compute_masks, mt.forward_prediction_heads = orig, orig_fph
+    return ctx()
+
+
+def _pooled(rec):
+    """list over head calls of (Q, Nk): chunks are (b_chunk, 1, Q, hs, ws) over the flattened (B, V) views, B = 1"""
+    out = []
+    for chunks in rec[:6]:
+        am = torch.cat(chunks, 0)[:, 0]                    # (V, Q, hs, ws)
+        out.append(am.permute(1, 0, 2, 3).flatten(1).contiguous())  # (Q, V*hs*ws)
+    return out
+
+
 def main():
     ref = ref_import.load_reference()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -61,7 +101,8 @@ def main():
         m = build_ref_head(ref, variant)
         feats, imgs, pos, ts = head_inputs(V, H, Wd, seed=5, portrait=portrait)
         with torch.no_grad():
-            out = m(feats, imgs, pos, ts, CLASSES)
+            with record_pooled_logits(m) as rec:
+                out = m(feats, imgs, pos, ts, CLASSES)
             mq = m(feats, imgs, pos, ts, CLASSES, memory_queries=out["out_queries"])
             x = torch.cat(feats, -1).flatten(0, 1)
             if m.input_mixer is not None and not callable(getattr(m.input_mixer, "__name__", None)):
@@ -80,6 +121,7 @@ def main():
             "aux_masks_absmax": [float(a["pred_masks"].abs().max()) for a in out["aux_outputs"]],
             "memq_masks_equal_full": bool(torch.equal(mq["pred_masks"], out["pred_masks"])),
             "fpn0": fpn[0], "mask_feats": mask_f,
+            "pooled_logits": _pooled(rec),  # what the six attention masks are thresholded from
         }
         if V > 2:  # keep the larger fixture small: upscaler outputs are pinned by the V = 2 cases
             blob["fpn0"], blob["mask_feats"], blob["aux0_masks"] = fpn[0].half(), mask_f.half(), blob["aux0_masks"].half()
@@ -113,7 +155,8 @@ def make_conditioned_golden(ref=None):
     m = build_ref_head(ref, c["variant"], cls_logit_scale=c["cls_logit_scale"])
     feats, imgs, pos, ts = head_inputs(c["V"], c["H"], c["W"], seed=c["input_seed"])
     with torch.no_grad():
-        out = m(feats, imgs, pos, ts, CLASSES)
+        with record_pooled_logits(m) as rec:
+            out = m(feats, imgs, pos, ts, CLASSES)
         scores = out["pred_logits"].sigmoid().max(-1).values[0]
         up = torch.nn.functional.interpolate(out["pred_masks"][0].sigmoid(), size=(c["H"], c["W"]), mode="bilinear", align_corners=False)
         weighted = scores[None, :, None, None] * up
@@ -122,6 +165,7 @@ def make_conditioned_golden(ref=None):
     blob.update({"classes": CLASSES, "weight_seed": 1, "pred_logits": out["pred_logits"], "pred_masks": out["pred_masks"],
                  "out_queries": out["out_queries"],
                  "aux_logits": [a["pred_logits"] for a in out["aux_outputs"]],
+                 "pooled_logits": _pooled(rec),
                  "ids": weighted.argmax(1).to(torch.int16), "margin": top2[:, 0] - top2[:, 1]})
     torch.save(blob, os.path.join(GOLDEN, "head_v1_conditioned.pt"))
     mg = blob["margin"]

@@ -790,7 +790,7 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   }
 
   // large plain GEMMs with N % 256 == 0 go to the 2-CTA kernel (256 x 256 tiles per SM pair)
-  const bool use2 = !conv && nb == 1 && !ep.promote && gemm2_enabled() && (N % G2_BN) == 0 &&
+  const bool use2 = !conv && nb == 1 && gemm2_enabled() && (N % G2_BN) == 0 &&
                     (long long)((M + 255) / 256) * (N / G2_BN) >= (sms / 2);
   // split mode: the hi / lo part is dimension 2 of both maps (a plain-bf16 A has a single part)
   const uint64_t a_parts = terms == 3 ? 2 : 1;

@@ -82,7 +82,10 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+// PROMOTE: accumulator promotion for split-mode reductions (GemmEpi::promote): every epilogue thread then keeps 128 fp32
+// partial sums in registers, so that variant is compiled for 200 registers per thread (320 threads x 200 = 64000 <= 65536).
+template <bool PROMOTE>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(PROMOTE ? 200 : 168)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmOut, const GemmEpi ep, const int M, const int N, const int K) {
   constexpr int BN = G2_BN;
@@ -108,6 +111,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
   const int terms = ep.split_terms > 1 ? ep.split_terms : 1;  // split-bf16 mode: see GemmEpi::split_terms
   const int num_k_iters = num_k_blocks * terms;
+  const int chunk_iters = PROMOTE ? ep.promote : num_k_iters;
+  const int num_chunks = (num_k_iters + chunk_iters - 1) / chunk_iters;
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   if (warp == 0 && lane == 0) {
@@ -169,26 +174,31 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
       int s = 0;
       uint32_t ph = 0;
-      int local = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
-        const int acc = local & 1;
-        const uint32_t acc_ph = (local >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k_iters; ++kb) {
-          mbar_wait(&full_bar[s], ph);
+      int local = 0;  // accumulator hand-overs so far: one per (tile, chunk)
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        for (int ch = 0; ch < num_chunks; ++ch, ++local) {
+          const int acc = local & 1;
+          const uint32_t acc_ph = (local >> 1) & 1;
+          mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * G2_STAGE_BYTES);
-          const uint32_t b_addr = a_addr + G2_A_BYTES;
-          const uint64_t a_desc = make_smem_desc_sw128(a_addr, 0, 1024);
-          const uint64_t b_desc = make_smem_desc_sw128(b_addr, 0, 1024);
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          const int k0 = ch * chunk_iters;
+          const int k1 = min(k0 + chunk_iters, num_k_iters);
+          for (int kb = k0; kb < k1; ++kb) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + s * G2_STAGE_BYTES);
+            const uint32_t b_addr = a_addr + G2_A_BYTES;
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr, 0, 1024);
+            const uint64_t b_desc = make_smem_desc_sw128(b_addr, 0, 1024);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) umma_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_2sm(&empty_bar[s]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              umma_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - k0) | k) != 0);
+            umma_commit_2sm(&empty_bar[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+          umma_commit_2sm(&tfull_bar[acc]);
         }
-        umma_commit_2sm(&tfull_bar[acc]);
       }
     }
   } else {
@@ -197,32 +207,62 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int cgrp = (warp - 2) >> 2;
     float* out_stage = reinterpret_cast<float*>(smem + G2_OUT_OFFSET) + (warp - 2) * 1024;
     int local = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_blk = tile % num_m_blocks;
       const int n_blk = tile / num_m_blocks;
-      const int acc = local & 1;
-      const uint32_t acc_ph = (local >> 1) & 1;
       const int row = m_blk * 256 + (int)rank * 128 + quad * 32 + lane;
       const float2 ln = ln_row_stats(ep, row, M);
-      mbar_wait(&tfull_bar[acc], acc_ph);
-      tc_fence_after();
-      const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = cgrp; c < BN / 32; c += 2) {
-        uint32_t r[32];
-        tmem_ld32(t_base + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
+      if constexpr (PROMOTE) {
+        // this warp owns the 32-column chunks cgrp, cgrp + 2, ...: BN / 64 register accumulators of 32 columns each
+        constexpr int NCH = BN / 64;
+        float accv[NCH][32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (ep.tma_store)
-          epilogue_chunk_tma(ep, &tmOut, out_stage, v, m_blk * 256 + (int)rank * 128 + quad * 32, n_blk * BN + c * 32, lane);
-        else
-          epilogue_chunk(ep, v, row, n_blk * BN + c * 32, M, N, 0, ln);
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) accv[j][i] = 0.0f;
+        for (int ch = 0; ch < num_chunks; ++ch, ++local) {
+          const int acc = local & 1;
+          mbar_wait(&tfull_bar[acc], (local >> 1) & 1);
+          tc_fence_after();
+          const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) {
+            uint32_t r[32];
+            tmem_ld32(t_base + (cgrp + 2 * j) * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) accv[j][i] += __uint_as_float(r[i]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
+        }
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) epilogue_chunk(ep, accv[j], row, n_blk * BN + (cgrp + 2 * j) * 32, M, N, 0, ln);
+      } else {
+        const int acc = local & 1;
+        const uint32_t acc_ph = (local >> 1) & 1;
+        mbar_wait(&tfull_bar[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c = cgrp; c < BN / 32; c += 2) {
+          uint32_t r[32];
+          tmem_ld32(t_base + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (ep.tma_store)
+            epilogue_chunk_tma(ep, &tmOut, out_stage, v, m_blk * 256 + (int)rank * 128 + quad * 32, n_blk * BN + c * 32, lane);
+          else
+            epilogue_chunk(ep, v, row, n_blk * BN + c * 32, M, N, 0, ln);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
+        ++local;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
     }
     if (ep.tma_store && lane == 0) bulk_wait_all();
   }
@@ -248,7 +288,8 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
                         int N, int K, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
+    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
+    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
     configured = true;
   }
   const int tiles = ((M + 255) / 256) * (N / G2_BN);
@@ -264,7 +305,10 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  PST3R_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel, tmA, tmB, tmOut, ep, M, N, K));
+  if (ep.promote)
+    PST3R_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<true>, tmA, tmB, tmOut, ep, M, N, K));
+  else
+    PST3R_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<false>, tmA, tmB, tmOut, ep, M, N, K));
   return PST3R_OK;
 }
 

@@ -208,6 +208,11 @@ class MaskTransformer(nn.Module):
         self.lang_embed = nn.Linear(hidden_dim, lang_dim)
         self.cls_logit_scale = nn.Parameter(torch.ones([]))
         self.mask_embed = _MaskMLP(hidden_dim, hidden_dim, mask_dim, 3)
+        # test instrumentation (the query decoder is a discontinuous function of sign(mask logit) decisions):
+        # `mask_override`: list of 6 block-mask bit tensors forced into the layers; `bits_record`: list that receives the
+        # block mask each layer actually used.  Both None in normal operation.
+        self.mask_override: Optional[List[torch.Tensor]] = None
+        self.bits_record: Optional[list] = None
 
     # ---- prepared -------------------------------------------------------------------------------
     def _kv_weights(self, precise: bool = False):
@@ -310,6 +315,8 @@ class MaskTransformer(nn.Module):
         Multi aspect ratio (mask_transformer.py:126-146 with multi_ar=True): src / mask_feats / hw / portrait are
         LISTS with one entry per stack of equally shaped views; the memory tokens of all stacks are concatenated in
         stack order (each with the PE of its own grid) and `pred_masks` comes back as a list with one tensor per stack."""
+        if mask_override is None:
+            mask_override = self.mask_override
         multi = isinstance(src, (list, tuple))
         srcs, mfs, hws = (list(src), list(mask_feats), list(hw)) if multi else ([src], [mask_feats], [hw])
         ports = list(portrait) if isinstance(portrait, (list, tuple)) else [portrait] * len(srcs)
@@ -352,6 +359,8 @@ class MaskTransformer(nn.Module):
             ca, sa, ff = self.cross_attn_layers[i], self.self_attn_layers[i], self.ffn_layers[i]
             W = wsplit if precise else w16
             # masked cross-attention (post-norm): tgt = LN(tgt + MHA(tgt + query_pos, memory + pos, memory))
+            if self.bits_record is not None:
+                self.bits_record.append(bits.clone())
             if mask_override is not None:  # test hook: force the block mask of layer i (isolates threshold flips)
                 bits = mask_override[i]
             t = self._mha(ops.add_bcast(output, qe), k_of(i), v_of(i), ca.multihead_attn, bits, output, precise)
