@@ -331,7 +331,14 @@ def run_ours(args):
         h2d_total, d2h_total = h2d, d2h
 
     # ---- per-kernel breakdown of ONE timed-configuration step (CUPTI device durations via torch.profiler) ----
-    breakdown = kernel_breakdown(torch, run_step, barrier)
+    # taken on ONE stream (DINOv2 not overlapped with the memory build): a kernel that shares the SMs with another stream's
+    # kernels reports an inflated duration, and the sum would no longer compare with the step time
+    ov = model.overlap_dino
+    model.overlap_dino = False
+    try:
+        breakdown = kernel_breakdown(torch, step_device, barrier)
+    finally:
+        model.overlap_dino = ov
     roofline = att_roof = gemm_class = None
     if rank == 0:
         peaks, peak_src = _peaks()
@@ -419,9 +426,9 @@ def run_ours(args):
 
 
 def kernel_breakdown(torch, run_step, barrier):
-    """Device time per kernel of ONE step of the timed configuration (same graph replay / launches as the timed loop),
-    from CUPTI kernel records (torch.profiler): every kernel's own duration, whichever stream it ran on.  The sum exceeds
-    `ms_per_step` only by what DINOv2 overlaps with the memory build on the side stream.  Never inside a timed region."""
+    """Device time per kernel of ONE step (the timed step's launches, issued on a single stream) from CUPTI kernel
+    records (torch.profiler): every kernel's own duration.  `_total_ms` compares with `ms_per_step` (the timed loop
+    additionally overlaps DINOv2 with the memory build and replays a CUDA graph).  Never inside a timed region."""
     import re
     try:
         from torch.profiler import ProfilerActivity, profile
@@ -455,7 +462,7 @@ def kernel_breakdown(torch, run_step, barrier):
             d["ms"] = round(d["ms"], 4)
         out = dict(sorted(agg.items(), key=lambda kv: -kv[1]["ms"]))
         out["_total_ms"] = round(total, 3)
-        out["_source"] = "CUPTI kernel durations (torch.profiler) of one step as timed"
+        out["_source"] = "CUPTI kernel durations (torch.profiler) of one step, single stream, eager launches"
         return out
     except Exception as e:  # noqa: BLE001
         barrier()

@@ -274,14 +274,15 @@ int pst3r_loftup_guidance(const float* img, int32_t V, int32_t H, int32_t W, flo
                           void* workspace, pst3r_stream_t stream);
 /* MinMaxScaler -> ImplicitFeaturizer (n_freqs sin/cos features of [gy, gx, r, g, b] + scaled rgb; channel order
  * [sin(f*5+m) | cos(f*5+m) | rgb]) -> GroupNorm(1, C) with (gamma, beta) -> bf16 pixel-major out [V, Hh, Wh, ldo]
- * (channels [C, ldo) zeroed).  gy/gx = torch.linspace(-1,1,.) tables, freqs = exp(linspace(-2,10,n_freqs)),
+ * (channels [C, ldo) zeroed; out_kind PST3R_KIND_SPLIT: pixel rows [hi(ldo) | lo(ldo)]).  gy/gx = torch.linspace(-1,1,.) tables, freqs = exp(linspace(-2,10,n_freqs)),
  * biases = the flat (2, 5, n_freqs) parameter. */
 int pst3r_loftup_fourier_gn(const float* half, const float* minmax, const float* gy, const float* gx,
                             const float* freqs, const float* biases, int32_t V, int32_t Hh, int32_t Wh,
-                            int32_t n_freqs, const float* gamma, const float* beta, float eps, void* out, int64_t ldo,
-                            void* workspace, pst3r_stream_t stream);
-/* In-place GroupNorm (+ optional ReLU) on a pixel-major bf16 map x [V, npix, C] (nn.GroupNorm(groups, C)). */
-int pst3r_groupnorm_nhwc(void* x, int32_t V, int32_t npix, int32_t C, int32_t groups, const float* gamma,
+                            int32_t n_freqs, const float* gamma, const float* beta, float eps, void* out, int32_t out_kind,
+                            int64_t ldo, void* workspace, pst3r_stream_t stream);
+/* In-place GroupNorm (+ optional ReLU) on a pixel-major map x [V, npix, C] (nn.GroupNorm(groups, C)); kind:
+ * PST3R_KIND_BF16, or PST3R_KIND_SPLIT with [hi(C) | lo(C)] pixel rows. */
+int pst3r_groupnorm_nhwc(void* x, int32_t kind, int32_t V, int32_t npix, int32_t C, int32_t groups, const float* gamma,
                          const float* beta, float eps, int32_t relu, void* workspace, pst3r_stream_t stream);
 
 #ifdef __cplusplus

@@ -480,35 +480,39 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
           uint8_t* a_dst = smem + s * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + L::A_BYTES;
-          if (terms > 1) {
-            // hi / lo part of each operand for this product term: (hi,hi), (lo,hi), (hi,lo) | (A,hi), (A,lo)
-            const int pa = (terms == 3 && term == 1) ? 1 : 0;
-            const int pb = (term == terms - 1) ? 1 : 0;
-            if (ep.batches > 1) {
-              tma_load_4d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM, pa, bidx);
-              tma_load_4d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN, pb, bidx);
-            } else {
-              tma_load_3d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM, pa);
-              tma_load_3d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN, pb);
-            }
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-            continue;
-          }
+          // hi / lo part of each operand for this product term: (hi,hi), (lo,hi), (hi,lo) | (A,hi), (A,lo)
+          const int pa = (terms == 3 && term == 1) ? 1 : 0;
+          const int pb = (terms > 1 && term == terms - 1) ? 1 : 0;
           if (ep.conv_cblocks > 0) {
             // k-block -> (tap, channel block); m-tile -> (view, y, 128-pixel segment of the row)
             const int tap = kb / ep.conv_cblocks, cb = kb - tap * ep.conv_cblocks;
             const int xb = m_blk % ep.conv_tpr, rowidx = m_blk / ep.conv_tpr;
-            tma_load_4d(a_dst, &tmA, &full_bar[s], cb * 64, xb * GEMM_BM + tap % 3 - 1, rowidx % ep.conv_h + tap / 3 - 1,
-                        rowidx / ep.conv_h);
+            if (terms > 1)
+              tma_load_5d(a_dst, &tmA, &full_bar[s], cb * 64, xb * GEMM_BM + tap % 3 - 1, rowidx % ep.conv_h + tap / 3 - 1,
+                          rowidx / ep.conv_h, pa);
+            else
+              tma_load_4d(a_dst, &tmA, &full_bar[s], cb * 64, xb * GEMM_BM + tap % 3 - 1, rowidx % ep.conv_h + tap / 3 - 1,
+                          rowidx / ep.conv_h);
+          } else if (terms > 1) {
+            if (ep.batches > 1)
+              tma_load_4d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM, pa, bidx);
+            else
+              tma_load_3d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM, pa);
           } else if (ep.batches > 1) {
             tma_load_3d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM, bidx);
           } else {
             tma_load_2d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
           }
-          if (ep.batches > 1)
+          if (terms > 1) {
+            if (ep.batches > 1)
+              tma_load_4d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN, pb, bidx);
+            else
+              tma_load_3d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN, pb);
+          } else if (ep.batches > 1) {
             tma_load_3d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN, bidx);
-          else
+          } else {
             tma_load_2d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -734,7 +738,7 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   PST3R_CHECK_ARG(terms == 0 || terms == 2 || terms == 3, "gemm: split_terms must be 0, 2 or 3");
   PST3R_CHECK_ARG(e->out_kind >= 0 && e->out_kind <= 2 && e->res_kind >= 0 && e->res_kind <= 2, "gemm: bad out_kind / res_kind");
   if (terms)
-    PST3R_CHECK_ARG(!conv && !e->ln_stats && (e->b_lo_off % 8) == 0 && e->b_lo_off > 0 &&
+    PST3R_CHECK_ARG((!conv || terms == 3) && !e->ln_stats && (e->b_lo_off % 8) == 0 && e->b_lo_off > 0 &&
                         (terms == 2 || ((e->a_lo_off % 8) == 0 && e->a_lo_off > 0)),
                     "gemm: split operands need lo offsets that are positive multiples of 8 (no conv / folded LayerNorm)");
   if (e->out_kind == PST3R_KIND_SPLIT)
@@ -808,7 +812,18 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   }
 
   CUtensorMap tmA, tmB;
-  if (terms) {
+  if (terms && conv) {
+    // split pixel-major map: pixel rows [hi(ld) | lo(ld)], the part is dimension 4 of the activation map
+    uint64_t dA[5] = {(uint64_t)conv->C, (uint64_t)conv->W, (uint64_t)conv->H, (uint64_t)conv->V, 2};
+    uint64_t sA[5] = {2, (uint64_t)lda * 2, (uint64_t)lda * conv->W * 2, (uint64_t)lda * conv->W * conv->H * 2, (uint64_t)e->a_lo_off * 2};
+    uint32_t bA[5] = {GEMM_BK, GEMM_BM, 1, 1, 1};
+    uint64_t dB[3] = {(uint64_t)K, (uint64_t)N, 2}, sB[3] = {2, (uint64_t)ldb * 2, (uint64_t)e->b_lo_off * 2};
+    uint32_t bB[3] = {GEMM_BK, (uint32_t)BN, 1};
+    int r = encode_tmap(&tmA, A, 2, 5, dA, sA, bA);
+    if (r) return r;
+    r = encode_tmap(&tmB, B, 2, 3, dB, sB, bB);
+    if (r) return r;
+  } else if (terms) {
     // (K, rows, part[, batch]); rows / K beyond the logical extents are zero filled, never the next part / problem
     uint64_t dA[4] = {(uint64_t)K, (uint64_t)M, a_parts, (uint64_t)nb};
     uint64_t sA[4] = {2, (uint64_t)lda * 2, a_part_stride, (uint64_t)(bat ? bat->a_bs : 0) * 2};
@@ -894,5 +909,6 @@ extern "C" int pst3r_conv3x3_nhwc(const void* x, int64_t ldx, int32_t V, int32_t
   const int tpr = (W + GEMM_BM - 1) / GEMM_BM;
   const long long mv = (long long)V * H * tpr * GEMM_BM;  // virtual rows: 128-pixel row segments
   PST3R_CHECK_ARG(mv < 0x7fffffffLL, "conv3x3: map too large");
-  return gemm_run(x, ldx, w, 9LL * cpad, (int32_t)mv, O, 9 * cpad, e, stream, &c);
+  // split mode: weight rows are [hi(9 cpad) | lo(9 cpad)], pixel rows [hi | lo] with the lo part a_lo_off elements later
+  return gemm_run(x, ldx, w, (e->split_terms ? 18LL : 9LL) * cpad, (int32_t)mv, O, 9 * cpad, e, stream, &c);
 }

@@ -83,9 +83,9 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 }
 
 // PROMOTE: accumulator promotion for split-mode reductions (GemmEpi::promote): every epilogue thread then keeps 128 fp32
-// partial sums in registers, so that variant is compiled for 200 registers per thread (320 threads x 200 = 64000 <= 65536).
+// partial sums in registers, so that variant is compiled for 192 registers per thread (200 would fit 65536 / 320 but not the per-warp allocation granularity: the launch fails).
 template <bool PROMOTE>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(PROMOTE ? 200 : 168)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(PROMOTE ? 192 : 168)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmOut, const GemmEpi ep, const int M, const int N, const int K) {
   constexpr int BN = G2_BN;

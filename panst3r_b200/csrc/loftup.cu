@@ -150,9 +150,16 @@ __global__ void group_stats_final_kernel(const double* __restrict__ partial, int
 }
 
 // features -> GroupNorm(1, C) -> bf16 NHWC [V, Hh, Wh, ldo] (channels [C, ldo) zero)
+// split != 0: pixel rows are [hi(ldo) | lo(ldo)] (reference-precision head, PST3R_KIND_SPLIT)
+__device__ __forceinline__ void put_bf16(bf16* o, int c, int lo_off, int split, float v) {
+  const bf16 h = __float2bfloat16(v);
+  o[c] = h;
+  if (split) o[c + lo_off] = __float2bfloat16(v - __bfloat162float(h));
+}
+
 __global__ void loftup_fourier_write_kernel(FourierArgs a, const float* __restrict__ stats /* [V][2] */,
                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            bf16* __restrict__ out, int ldo) {
+                                            bf16* __restrict__ out, int ldo, int split) {
   const int v = blockIdx.y;
   const int npix = a.Hh * a.Wh;
   const int nf = a.n_freqs;
@@ -161,7 +168,7 @@ __global__ void loftup_fourier_write_kernel(FourierArgs a, const float* __restri
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
     float base[5];
     fourier_base(a, v, pix / a.Wh, pix % a.Wh, base);
-    bf16* o = out + ((long long)v * npix + pix) * ldo;
+    bf16* o = out + ((long long)v * npix + pix) * (split ? 2 * ldo : ldo);
     for (int f = 0; f < nf; ++f) {
       const float fr = a.freqs[f];
 #pragma unroll
@@ -170,16 +177,16 @@ __global__ void loftup_fourier_write_kernel(FourierArgs a, const float* __restri
         const int cs = f * 5 + m, cc = nf * 5 + f * 5 + m;
         const float sv = sinf(t + a.biases[cs]);
         const float cv = cosf(t + a.biases[cc]);
-        o[cs] = __float2bfloat16((sv - mean) * rstd * gamma[cs] + beta[cs]);
-        o[cc] = __float2bfloat16((cv - mean) * rstd * gamma[cc] + beta[cc]);
+        put_bf16(o, cs, ldo, split, (sv - mean) * rstd * gamma[cs] + beta[cs]);
+        put_bf16(o, cc, ldo, split, (cv - mean) * rstd * gamma[cc] + beta[cc]);
       }
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const int ch = 10 * nf + c;
-      o[ch] = __float2bfloat16((base[2 + c] - mean) * rstd * gamma[ch] + beta[ch]);
+      put_bf16(o, ch, ldo, split, (base[2 + c] - mean) * rstd * gamma[ch] + beta[ch]);
     }
-    for (int ch = C; ch < ldo; ++ch) o[ch] = __float2bfloat16(0.0f);
+    for (int ch = C; ch < ldo; ++ch) put_bf16(o, ch, ldo, split, 0.0f);
   }
 }
 
@@ -187,7 +194,7 @@ __global__ void loftup_fourier_write_kernel(FourierArgs a, const float* __restri
 // GroupNorm on pixel-major bf16 maps [V, npix, C]: per-(view, group) stats, then normalise + affine (+ReLU) in place
 // ---------------------------------------------------------------------------------------------------
 __global__ void groupnorm_stats_kernel(const bf16* __restrict__ x, int npix, int C, int groups,
-                                       double* __restrict__ partial /* [V*groups][gridDim.x][2] */) {
+                                       double* __restrict__ partial /* [V*groups][gridDim.x][2] */, int split) {
   const int v = blockIdx.y;
   const int cpg = C / groups;
   // thread -> fixed channel pair; rows strided: coalesced 4-byte loads along channels
@@ -198,8 +205,14 @@ __global__ void groupnorm_stats_kernel(const bf16* __restrict__ x, int npix, int
   const int chunk = (npix + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * chunk, p1 = min(npix, p0 + chunk);
   float s = 0.0f, ss = 0.0f;
+  const int ld = split ? 2 * C : C;
   for (int p = p0 + r0; p < p1; p += rows_per_iter) {
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + ((long long)v * npix + p) * C + 2 * tc));
+    const bf16* px = x + ((long long)v * npix + p) * ld + 2 * tc;
+    float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(px));
+    if (split) {
+      const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(px + C));
+      f.x += l.x; f.y += l.y;
+    }
     s += f.x + f.y;
     ss += f.x * f.x + f.y * f.y;
   }
@@ -221,7 +234,8 @@ __global__ void groupnorm_stats_kernel(const bf16* __restrict__ x, int npix, int
 }
 
 __global__ void groupnorm_apply_kernel(bf16* __restrict__ x, int npix, int C, int groups, const float* __restrict__ stats,
-                                       const float* __restrict__ gamma, const float* __restrict__ beta, int relu, long long total2) {
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, int relu, long long total2,
+                                       int split) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total2) return;
   const int cv = C >> 1;
@@ -230,12 +244,21 @@ __global__ void groupnorm_apply_kernel(bf16* __restrict__ x, int npix, int C, in
   const int v = row / npix;
   const int g = c / (C / groups);
   const float mean = stats[2 * (v * groups + g)], rstd = stats[2 * (v * groups + g) + 1];
-  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(x + row * C + c);
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(x + row * (split ? 2 * C : C) + c);
   float2 f = __bfloat1622float2(*p);
+  if (split) {
+    const float2 l = __bfloat1622float2(p[C / 2]);
+    f.x += l.x; f.y += l.y;
+  }
   f.x = (f.x - mean) * rstd * gamma[c] + beta[c];
   f.y = (f.y - mean) * rstd * gamma[c + 1] + beta[c + 1];
   if (relu) { f.x = fmaxf(f.x, 0.0f); f.y = fmaxf(f.y, 0.0f); }
-  *p = __floats2bfloat162_rn(f.x, f.y);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(f.x, f.y);
+  *p = h;
+  if (split) {
+    const float2 hf = __bfloat1622float2(h);
+    p[C / 2] = __floats2bfloat162_rn(f.x - hf.x, f.y - hf.y);
+  }
 }
 
 }  // namespace pst3r
@@ -264,10 +287,11 @@ extern "C" int pst3r_loftup_guidance(const float* img, int32_t V, int32_t H, int
 extern "C" int pst3r_loftup_fourier_gn(const float* half, const float* minmax, const float* gy, const float* gx,
                                        const float* freqs, const float* biases, int32_t V, int32_t Hh, int32_t Wh,
                                        int32_t n_freqs, const float* gamma, const float* beta, float eps, void* out,
-                                       int64_t ldo, void* workspace, pst3r_stream_t s_) {
+                                       int32_t out_kind, int64_t ldo, void* workspace, pst3r_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
   PST3R_CHECK_ARG(half && minmax && gy && gx && freqs && biases && gamma && beta && out && workspace && V > 0 &&
-                      ldo >= 10 * n_freqs + 3, "loftup_fourier_gn: bad args");
+                      ldo >= 10 * n_freqs + 3 && (out_kind == PST3R_KIND_BF16 || out_kind == PST3R_KIND_SPLIT),
+                  "loftup_fourier_gn: bad args");
   FourierArgs a{half, minmax, gy, gx, freqs, biases, V, Hh, Wh, n_freqs};
   const int C = 10 * n_freqs + 3;
   const int nb = 64;
@@ -277,27 +301,30 @@ extern "C" int pst3r_loftup_fourier_gn(const float* half, const float* minmax, c
   PST3R_CHECK_CUDA(cudaGetLastError());
   group_stats_final_kernel<<<(V + 63) / 64, 64, 0, s>>>(partial, nb, (double)C * Hh * Wh, eps, stats, V);
   PST3R_CHECK_CUDA(cudaGetLastError());
-  loftup_fourier_write_kernel<<<dim3(nb * 4, V), 256, 0, s>>>(a, stats, gamma, beta, reinterpret_cast<bf16*>(out), (int)ldo);
+  loftup_fourier_write_kernel<<<dim3(nb * 4, V), 256, 0, s>>>(a, stats, gamma, beta, reinterpret_cast<bf16*>(out), (int)ldo,
+                                                                   out_kind == PST3R_KIND_SPLIT);
   PST3R_CHECK_CUDA(cudaGetLastError());
   return PST3R_OK;
 }
 
-extern "C" int pst3r_groupnorm_nhwc(void* x, int32_t V, int32_t npix, int32_t C, int32_t groups, const float* gamma,
+extern "C" int pst3r_groupnorm_nhwc(void* x, int32_t kind, int32_t V, int32_t npix, int32_t C, int32_t groups, const float* gamma,
                                     const float* beta, float eps, int32_t relu, void* workspace, pst3r_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
   PST3R_CHECK_ARG(x && gamma && beta && workspace && V > 0 && npix > 0 && C > 0 && groups > 0 && (C % (2 * groups)) == 0 &&
-                      C / 2 <= 512 && groups <= 32, "groupnorm_nhwc: bad args");
+                      C / 2 <= 512 && groups <= 32 && (kind == PST3R_KIND_BF16 || kind == PST3R_KIND_SPLIT),
+                  "groupnorm_nhwc: bad args");
+  const int split = kind == PST3R_KIND_SPLIT;
   const int nb = 64;
   const int cv = C / 2;
   const int threads = (512 / cv) * cv;  // multiple of C/2, <= 512
   double* partial = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(workspace) + 256 * 6 * 4 + 32);
   float* stats = reinterpret_cast<float*>(partial + (long long)V * groups * nb * 2);
-  groupnorm_stats_kernel<<<dim3(nb, V), threads, threads * 2 * sizeof(float), s>>>(reinterpret_cast<const bf16*>(x), npix, C, groups, partial);
+  groupnorm_stats_kernel<<<dim3(nb, V), threads, threads * 2 * sizeof(float), s>>>(reinterpret_cast<const bf16*>(x), npix, C, groups, partial, split);
   PST3R_CHECK_CUDA(cudaGetLastError());
   group_stats_final_kernel<<<(V * groups + 63) / 64, 64, 0, s>>>(partial, nb, (double)(C / groups) * npix, eps, stats, V * groups);
   PST3R_CHECK_CUDA(cudaGetLastError());
   const long long total2 = (long long)V * npix * cv;
-  groupnorm_apply_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, s>>>(reinterpret_cast<bf16*>(x), npix, C, groups, stats, gamma, beta, relu, total2);
+  groupnorm_apply_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, s>>>(reinterpret_cast<bf16*>(x), npix, C, groups, stats, gamma, beta, relu, total2, split);
   PST3R_CHECK_CUDA(cudaGetLastError());
   return PST3R_OK;
 }

@@ -115,9 +115,12 @@ class ShardedPanSt3R:
         if nv > 0:
             x_loc, _ = m.forward_must3r_encoder(my_imgs, my_ts, out=rows[:, :ENC_DIM])
             x_loc = x_loc[0]
-            # DINOv2 of the local views shares the GPU with the (replicated, latency-bound) memory build below
-            side.wait_stream(cur)
-            with torch.cuda.stream(side), ops.sm_budget(dino_sms):
+            if m.overlap_dino:
+                # DINOv2 of the local views shares the GPU with the (replicated, latency-bound) memory build below
+                side.wait_stream(cur)
+                with torch.cuda.stream(side), ops.sm_budget(dino_sms):
+                    m.forward_dino(my_imgs, my_ts, out=rows[:, ENC_DIM + DEC_DIM:])
+            else:
                 m.forward_dino(my_imgs, my_ts, out=rows[:, ENC_DIM + DEC_DIM:])
         else:
             x_loc = torch.empty((0, N, ENC_DIM), device=dev, dtype=torch.bfloat16)
@@ -126,7 +129,7 @@ class ShardedPanSt3R:
         pos_all = pos_grid(hs, ws, dev)[0][None, None].expand(1, V, N, 2)
         with ops.sm_budget(max(ops.num_sms() - dino_sms, 8) if dino_sms else 0):
             mem = m.build_memory(x_all, pos_all, ts)
-        if nv > 0:
+        if nv > 0 and m.overlap_dino:
             cur.wait_stream(side)
         pointmaps = None
         portrait = H > W

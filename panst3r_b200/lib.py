@@ -85,8 +85,8 @@ SIGNATURES = {
     "pst3r_conv3x3_nhwc": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, C.POINTER(GemmEpilogue), _p]),
     "pst3r_loftup_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "pst3r_loftup_guidance": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p]),
-    "pst3r_loftup_fourier_gn": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _f, _p, _i64, _p, _p]),
-    "pst3r_groupnorm_nhwc": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _f, _i32, _p, _p]),
+    "pst3r_loftup_fourier_gn": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _f, _p, _i32, _i64, _p, _p]),
+    "pst3r_groupnorm_nhwc": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _f, _i32, _p, _p]),
     "pst3r_attention_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),
     "pst3r_attention_auto_splits": (_i32, [_i32, _i32, _i32, _i32]),
     "pst3r_attention": (C.c_int, [C.POINTER(AttnArgs), _p]),

@@ -295,12 +295,7 @@ class MaskTransformer(nn.Module):
             o = ops.attention(q, k, v, mask_bits=mask_bits)
             return ops.gemm(o.view(-1, d), w16(m.out_proj.weight), bias=bias_of(m.out_proj), residual=residual)
         q = ops.gemm(q_in, wq, bias=bq, out_dtype="split")
-        Q, Nk = q.shape[0], k.shape[1]
-        S = torch.empty((H, Q, Nk), device=q.device, dtype=torch.float32)
-        ops.gemm_batched(q.view(Q, H, hd).permute(1, 0, 2), k, alpha=hd ** -0.5, out=S)
-        P = ops.softmax_rows(S, Q, mask_bits)
-        o = ops.Split.empty((Q, d), q.device)
-        ops.gemm_batched(P, v, out=o.view(Q, H, hd).permute(1, 0, 2))
+        o = attention_precise(q, k, v, hd ** -0.5, mask_bits)
         return ops.gemm(o, wsplit(m.out_proj.weight), bias=bias_of(m.out_proj), residual=residual, out_dtype="split")
 
     @torch.no_grad()
@@ -398,6 +393,22 @@ class MaskTransformer(nn.Module):
             "aux_outputs": [{"pred_logits": a[None], "pred_masks": b1(b_)} for a, b_ in zip(pred_cls[:-1], pred_msk[:-1])],
             "out_queries": (ops.convert(output, torch.empty((Q, d), device=dev, dtype=torch.float32)) if precise else output).view(Q, 1, d),
         }
+
+
+def attention_precise(q, k_heads, vT_heads, scale: float, mask_bits=None, out=None):
+    """Reference-precision attention on split operands, unfused: S = scale * q k^T (batched GEMM over heads) -> row softmax
+    in fp32 (optionally block-masked) -> O = P v (batched GEMM against V^T).
+    q: ops.Split (Nq, H*hd) rows; k_heads: ops.Split (H, Nk, hd); vT_heads: ops.Split (H, hd, Nk).  -> ops.Split (Nq, H*hd).
+    This is what croco's `CrossAttention` / `Attention` and nn.MultiheadAttention compute in the reference's fp32 head
+    (model/blocks.py:29-35, mask_transformer.py:314,372); the probabilities never drop to bf16."""
+    H, Nk, hd = k_heads.shape
+    Nq = q.shape[0]
+    S = torch.empty((H, Nq, Nk), device=q.device, dtype=torch.float32)
+    ops.gemm_batched(q.view(Nq, H, hd).permute(1, 0, 2), k_heads, alpha=scale, out=S)
+    P = ops.softmax_rows(S, Nq, mask_bits)
+    o = out if out is not None else ops.Split.empty((Nq, H * hd), q.device)
+    ops.gemm_batched(P, vT_heads, out=o.view(Nq, H, hd).permute(1, 0, 2))
+    return o
 
 
 def _cat_rows(parts):
@@ -569,17 +580,44 @@ class InputMixer(nn.Module):
         self.mixer_norm = nn.LayerNorm(hidden_dim)
 
     @torch.no_grad()
-    def forward_rows(self, x, V: int, hs: int, ws: int, precise: bool = False) -> torch.Tensor:
-        """x bf16 rows (V*hs*ws, in_dim) -> bf16 rows (V*hs*ws, hidden_dim)"""
+    def forward_rows(self, x, V: int, hs: int, ws: int, precise: bool = False):
+        """x rows (V*hs*ws, in_dim), bf16 or ops.Split -> rows (V*hs*ws, hidden_dim): bf16, or ops.Split when `precise`
+        (split operands, LayerNorm in fp32, unfused reference-precision attention per view)."""
         from .common import pos_grid, rope_table, vit_block
-        if isinstance(x, ops.Split):  # the mixer blocks run on bf16 operands (see PanopticDecoder.precision)
-            x = ops.convert(x, torch.empty(x.shape, device=x.device, dtype=torch.bfloat16))
         N = hs * ws
+        D, H = self.hidden_dim, self.num_heads
+        hd = D // H
         _, pos32 = pos_grid(hs, ws, x.device)
-        rope = (rope_table(max(hs, ws), self.hidden_dim // self.num_heads, 100.0, x.device), pos32.repeat(V, 1))
-        h = ops.gemm(x, w16(self.in_proj.weight), bias=bias_of(self.in_proj))
+        rope = (rope_table(max(hs, ws), hd, 100.0, x.device), pos32.repeat(V, 1))
+        if not precise:
+            if isinstance(x, ops.Split):
+                x = ops.convert(x, torch.empty(x.shape, device=x.device, dtype=torch.bfloat16))
+            h = ops.gemm(x, w16(self.in_proj.weight), bias=bias_of(self.in_proj))
+            for blk in self.mixer_blk:
+                h, _ = vit_block(h, blk, V, N, rope)
+            return ops.layernorm(h, f32(self.mixer_norm.weight), f32(self.mixer_norm.bias), 1e-5)
+        dev = x.device
+        h = ops.gemm(x, wsplit(self.in_proj.weight), bias=bias_of(self.in_proj), out_dtype="split")
         for blk in self.mixer_blk:
-            h, _ = vit_block(h, blk, V, N, rope)
+            qkv_w, qkv_b = blk.attn.qkv.weight, blk.attn.qkv.bias
+            w_qk = MaskTransformer._slice_w(qkv_w, 0, 2 * D, "mix_qk", True)
+            w_v = MaskTransformer._slice_w(qkv_w, 2 * D, 3 * D, "mix_v", True)
+            b_qk = None if qkv_b is None else MaskTransformer._slice_w(qkv_b, 0, 2 * D, "mix_bqk")
+            b_v = None if qkv_b is None else MaskTransformer._slice_w(qkv_b, 2 * D, 3 * D, "mix_bv")
+            hn = ops.layernorm(h, f32(blk.norm1.weight), f32(blk.norm1.bias), blk.eps)
+            qk = ops.gemm(hn, w_qk, bias=b_qk, rope=(rope[0], rope[1], 2 * D), out_dtype="split")  # (V*N, 2D), RoPE on q and k
+            vT = ops.Split.empty((V, D, N), dev, align=8)  # V^T per view: the PV GEMM wants its B operand K-major
+            ops.gemm(hn, w_v, bias=b_v, out=vT, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=N,
+                     batch_stride=vT.hi.stride(0), ldt=vT.hi.stride(1))
+            o = ops.Split.empty((V * N, D), dev)
+            for v in range(V):
+                r = slice(v * N, (v + 1) * N)
+                attention_precise(qk[r, :D], qk[r, D:2 * D].view(N, H, hd).permute(1, 0, 2), vT[v].view(H, hd, N), hd ** -0.5,
+                                  out=o[r])
+            h = ops.gemm(o, wsplit(blk.attn.proj.weight), bias=bias_of(blk.attn.proj), residual=h, out=h)
+            hn = ops.layernorm(h, f32(blk.norm2.weight), f32(blk.norm2.bias), blk.eps)
+            mid = ops.gemm(hn, wsplit(blk.mlp.fc1.weight), bias=bias_of(blk.mlp.fc1), act=ops.ACT_GELU, out_dtype="split")
+            h = ops.gemm(mid, wsplit(blk.mlp.fc2.weight), bias=bias_of(blk.mlp.fc2), residual=h, out=h)
         return ops.layernorm(h, f32(self.mixer_norm.weight), f32(self.mixer_norm.bias), 1e-5)
 
     def forward(self, x, pos):
@@ -634,15 +672,17 @@ class LoftUpUpscaler(nn.Module):
 
     # ---- prepared constants ----------------------------------------------------------------------
     @staticmethod
-    def _conv_w(conv: nn.Conv2d, cpad: int):
+    def _conv_w(conv: nn.Conv2d, cpad: int, precise: bool = False):
         wt = conv.weight
 
         def build():
             O, Cc = wt.shape[:2]
             t = torch.zeros((O, 3, 3, cpad), device=wt.device, dtype=torch.float32)
             t[..., :Cc] = wt.detach().float().permute(0, 2, 3, 1)  # [O, C, ky, kx] -> [O, ky, kx, C]
-            return t.reshape(O, 9 * cpad).to(torch.bfloat16).contiguous()
-        return prepared(f"conv_w_{cpad}", [wt], build)
+            t = t.reshape(O, 9 * cpad)
+            return _split_cat(t) if precise else t.to(torch.bfloat16).contiguous()
+        buf = prepared(f"conv_w_{cpad}_{'s' if precise else 'b'}", [wt], build)
+        return _as_split(buf) if precise else buf
 
     def _tables(self, Hh, Wh, device):
         def build():
@@ -653,7 +693,7 @@ class LoftUpUpscaler(nn.Module):
         t = prepared(f"loftup_tab_{Hh}x{Wh}", [self.ca_transformer_norm.weight], build)
         return t[:Hh], t[Hh:Hh + Wh], t[Hh + Wh:]
 
-    def _lr_pe_term(self, hs, ws, device):
+    def _lr_pe_term(self, hs, ws, device, precise: bool = False):
         """Constant of (grid, weights): lr_input_proj.0 applied to the 20 sine-PE channels of the low-res grid, plus its
         bias -> bf16 (hs*ws, dim).  (ImplicitFeaturizer(color_feats=False, n_freqs=5, learn_bias=True), loftup.py:99.)"""
         lin = self.lr_input_proj[0]
@@ -670,11 +710,13 @@ class LoftUpUpscaler(nn.Module):
             c = torch.cos(arg + bb[1].reshape(5, 2, 1, 1)).flatten(0, 1)
             pe = torch.cat([s, c], 0).flatten(1).t()  # (hs*ws, 20)
             wpe = lin.weight.detach().float()[:, self.input_dim:]
-            return (pe @ wpe.t() + lin.bias.detach().float()).to(torch.bfloat16).contiguous()
-        return prepared(f"loftup_lrpe_{hs}x{ws}", [lin.weight, lin.bias, b], build)
+            return (pe @ wpe.t() + lin.bias.detach().float()).to(torch.float32 if precise else torch.bfloat16).contiguous()
+        return prepared(f"loftup_lrpe_{hs}x{ws}_{'f' if precise else 'b'}", [lin.weight, lin.bias, b], build)
 
-    def _lr_feat_w(self):
+    def _lr_feat_w(self, precise: bool = False):
         lin = self.lr_input_proj[0]
+        if precise:
+            return _as_split(prepared("loftup_lrw_s", [lin.weight], lambda: _split_cat(lin.weight.detach()[:, :self.input_dim].float())))
         return prepared("loftup_lrw", [lin.weight], lambda: lin.weight.detach()[:, :self.input_dim].to(torch.bfloat16).contiguous())
 
     @torch.no_grad()
@@ -685,12 +727,16 @@ class LoftUpUpscaler(nn.Module):
         dev = feats.device
         N = hs * ws
         D, Hh, Wh = self.dim, hs * self.patch_size // 2, ws * self.patch_size // 2
+        W = wsplit if precise else w16
+        act = "split" if precise else torch.bfloat16
+        if isinstance(feats, ops.Split) and not precise:
+            feats = ops.convert(feats, torch.empty(feats.shape, device=dev, dtype=torch.bfloat16))
         # stride-16 features for the query decoder: 1x1 conv == GEMM
         pb = f32(self.patch_embed.bias)
         if f16_extra_bias is not None:
             pb = prepared("loftup_f16bias", [self.patch_embed.bias, f16_extra_bias],
                           lambda: (self.patch_embed.bias.detach().float() + f16_extra_bias.detach().float().view(-1)).contiguous())
-        f16 = ops.gemm(feats, w16(self.patch_embed.weight), bias=pb)
+        f16 = ops.gemm(feats, W(self.patch_embed.weight), bias=pb, out_dtype=act)
         # guidance branch: x0.5 image -> MinMaxScaler (batch global) -> Fourier features -> GN(1) -> 2 x (conv3x3, GN(8), ReLU)
         half, minmax = ops.loftup_guidance(imgs.float())
         if getattr(self, "minmax_reduce", None) is not None:  # view-sharded runs: batch-global extrema across ranks
@@ -699,44 +745,58 @@ class LoftUpUpscaler(nn.Module):
         gn0, c1, gn1, c2, gn2 = (self.first_conv[i] for i in (0, 1, 2, 4, 5))
         ld0 = ((self.start_dim + 7) // 8) * 8
         x0 = ops.loftup_fourier_gn(half, minmax, gy, gx, fr, f32(self.fourier_feat[1].biases).view(-1), f32(gn0.weight),
-                                   f32(gn0.bias), gn0.eps, ld0)
+                                   f32(gn0.bias), gn0.eps, ld0, split=precise)
         x0 = x0[..., :self.start_dim] if ld0 != self.start_dim else x0
         cpad1 = ((self.start_dim + 63) // 64) * 64
-        x1 = ops.conv3x3_nhwc(x0, self._conv_w(c1, cpad1), cpad1, bias=f32(c1.bias))
+        x1 = ops.conv3x3_nhwc(x0, self._conv_w(c1, cpad1, precise), cpad1, bias=f32(c1.bias))
         ops.groupnorm_nhwc_(x1, gn1.num_groups, f32(gn1.weight), f32(gn1.bias), gn1.eps, True)
         cpad2 = ((D + 63) // 64) * 64
-        x2 = ops.conv3x3_nhwc(x1, self._conv_w(c2, cpad2), cpad2, bias=f32(c2.bias))
+        x2 = ops.conv3x3_nhwc(x1, self._conv_w(c2, cpad2, precise), cpad2, bias=f32(c2.bias))
         ops.groupnorm_nhwc_(x2, gn2.num_groups, f32(gn2.weight), f32(gn2.bias), gn2.eps, True)
         x = x2.view(b * Hh * Wh, D)
         # low-res tokens: Linear([feats | sine PE]) + LN, the PE part folded into a per-token constant
         ln = self.lr_input_proj[1]
-        lr = ops.gemm(feats, self._lr_feat_w(), residual=self._lr_pe_term(hs, ws, dev), res_mod_rows=N)
+        lr = ops.gemm(feats, self._lr_feat_w(precise), residual=self._lr_pe_term(hs, ws, dev, precise), res_mod_rows=N, out_dtype=act)
         lr = ops.layernorm(lr, f32(ln.weight), f32(ln.bias), ln.eps)
         H4, hd = self.num_heads, D // self.num_heads
+        P = Hh * Wh
         for blk in self.ca_transformer_blocks:
             ca = blk.cross_attn
             y_ = ops.layernorm(lr, f32(blk.norm_y.weight), f32(blk.norm_y.bias), 1e-5)
-            kv = ops.gemm(y_, cat_w16([ca.projk.weight, ca.projv.weight])).view(b, N, 2 * D)
-            q = ops.gemm(ops.layernorm(x, f32(blk.norm2.weight), f32(blk.norm2.bias), 1e-5), w16(ca.projq.weight))
-            o = ops.attention(q.view(b, Hh * Wh, H4, hd), kv[:, :, :D].unflatten(-1, (H4, hd)), kv[:, :, D:].unflatten(-1, (H4, hd)))
-            x = ops.gemm(o.view(b * Hh * Wh, D), w16(ca.proj.weight), bias=bias_of(ca.proj), residual=x, out=x)
+            qn = ops.layernorm(x, f32(blk.norm2.weight), f32(blk.norm2.bias), 1e-5)
+            if precise:
+                # unfused reference-precision cross-attention, one view at a time (49 152 high-res queries x 768 low-res
+                # keys x 4 heads: the score matrix of a view is what croco's CrossAttention materialises, blocks.py:29-35)
+                k = ops.gemm(y_, wsplit(ca.projk.weight), out_dtype="split")  # (b*N, D)
+                vT = ops.Split.empty((b, D, N), dev, align=8)
+                ops.gemm(y_, wsplit(ca.projv.weight), out=vT, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=N,
+                         batch_stride=vT.hi.stride(0), ldt=vT.hi.stride(1))
+                q = ops.gemm(qn, wsplit(ca.projq.weight), out_dtype="split")  # (b*P, D)
+                o = ops.Split.empty((b * P, D), dev)
+                for v in range(b):
+                    attention_precise(q[v * P:(v + 1) * P], k[v * N:(v + 1) * N].view(N, H4, hd).permute(1, 0, 2),
+                                      vT[v].view(H4, hd, N), hd ** -0.5, out=o[v * P:(v + 1) * P])
+            else:
+                kv = ops.gemm(y_, cat_w16([ca.projk.weight, ca.projv.weight])).view(b, N, 2 * D)
+                q = ops.gemm(qn, w16(ca.projq.weight))
+                o = ops.attention(q.view(b, P, H4, hd), kv[:, :, :D].unflatten(-1, (H4, hd)), kv[:, :, D:].unflatten(-1, (H4, hd)))
+                o = o.view(b * P, D)
+            x = ops.gemm(o, W(ca.proj.weight), bias=bias_of(ca.proj), residual=x, out=x)
             h = ops.layernorm(x, f32(blk.norm3.weight), f32(blk.norm3.bias), 1e-5)
-            h = ops.gemm(h, w16(blk.mlp.fc1.weight), bias=bias_of(blk.mlp.fc1), act=ops.ACT_GELU)
-            x = ops.gemm(h, w16(blk.mlp.fc2.weight), bias=bias_of(blk.mlp.fc2), residual=x, out=x)
+            h = ops.gemm(h, W(blk.mlp.fc1.weight), bias=bias_of(blk.mlp.fc1), act=ops.ACT_GELU, out_dtype=act)
+            x = ops.gemm(h, W(blk.mlp.fc2.weight), bias=bias_of(blk.mlp.fc2), residual=x, out=x)
         x = ops.layernorm(x, f32(self.ca_transformer_norm.weight), f32(self.ca_transformer_norm.bias), 1e-5)
-        if precise:  # hand split pairs to the reference-precision query decoder / mask einsum
-            return ops.Split.from_float(f16), ops.Split.from_float(x).view(b, Hh, Wh, D)
         return f16, x.view(b, Hh, Wh, D)
 
     @torch.no_grad()
-    def forward(self, inputs, img_shape):
+    def forward(self, inputs, img_shape, precise: bool = False):
         """Reference signature: ((lr_feats (b,N,C), img (b,3,H,W)), (H, W)) -> ([patch_feats (b,C,hs,ws)], (b,dim,H/2,W/2)) fp32."""
         lr, img = inputs
         H, W = img_shape
         hs, ws = H // self.patch_size, W // self.patch_size
         b = lr.shape[0]
-        x = lr if lr.dtype == torch.bfloat16 else ops.to_bf16(lr.float().contiguous())
-        f16, mf = self.forward_nhwc(x.reshape(b * hs * ws, -1), img, b, hs, ws)
+        x = _head_input(lr.reshape(b * hs * ws, -1), precise)
+        f16, mf = self.forward_nhwc(x, img, b, hs, ws, precise=precise)
         f16_nchw = ops.nhwc_to_nchw_f32(f16.view(b, hs * ws, -1)).view(b, -1, hs, ws)
-        mf_nchw = ops.nhwc_to_nchw_f32(mf.reshape(b, -1, self.dim)).view(b, self.dim, H // 2, W // 2)
+        mf_nchw = ops.nhwc_to_nchw_f32(mf.view(b, (H // 2) * (W // 2), self.dim)).view(b, self.dim, H // 2, W // 2)
         return [f16_nchw], mf_nchw

@@ -734,30 +734,38 @@ def panoptic_finalize(ids: torch.Tensor, win: torch.Tensor, lut: Optional[torch.
     return pan, conf
 
 
-def conv3x3_nhwc(x: torch.Tensor, w: torch.Tensor, cpad: int, *, bias: Optional[torch.Tensor] = None,
-                 act: int = ACT_NONE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def conv3x3_nhwc(x, w, cpad: int, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, out=None):
     """3x3 / stride 1 / zero-pad 1 convolution of a pixel-major bf16 map x [V, H, W, ld>=C] with tap-major weights
-    w bf16 [O, 9*cpad] as an implicit tcgen05 GEMM.  Returns bf16 [V, H, W, O]."""
+    w bf16 [O, 9*cpad] as an implicit tcgen05 GEMM.  Returns bf16 [V, H, W, O].  Reference-precision mode: x and w are
+    `Split`s (pixel rows [hi | lo]; weight rows [hi(9 cpad) | lo(9 cpad)]), the result a packed `Split`."""
     global launches
     lib = _l.load()
-    _need(x, torch.bfloat16, "conv3x3.x")
-    _need(w, torch.bfloat16, "conv3x3.w")
-    V, H, W, Cc = x.shape
-    if x.stride(-1) != 1 or x.stride(2) != x.stride(-2) or x.stride(1) != W * x.stride(2) or x.stride(0) != H * x.stride(1):
+    split = isinstance(w, Split)
+    if split != isinstance(x, Split):
+        raise _l.Pst3rError("conv3x3: x and w must both be Split or both plain bf16")
+    xb, wb = _base(x), _base(w)
+    _need(xb, torch.bfloat16, "conv3x3.x")
+    _need(wb, torch.bfloat16, "conv3x3.w")
+    V, H, W, Cc = xb.shape
+    if xb.stride(-1) != 1 or xb.stride(2) != xb.stride(-2) or xb.stride(1) != W * xb.stride(2) or xb.stride(0) != H * xb.stride(1):
         raise _l.Pst3rError("conv3x3.x: expected a dense pixel-major map")
-    O = w.shape[0]
-    if w.shape[1] != 9 * cpad or not w.is_contiguous():
-        raise _l.Pst3rError("conv3x3.w: expected contiguous [O, 9*cpad]")
+    O = wb.shape[0]
+    if wb.shape[1] != 9 * cpad or wb.stride(0) != (2 if split else 1) * 9 * cpad or (split and w.lo_off != 9 * cpad):
+        raise _l.Pst3rError("conv3x3.w: expected contiguous [O, 9*cpad] (split: rows [hi | lo])")
     if out is None:
-        out = torch.empty((V, H, W, O), device=x.device, dtype=torch.bfloat16)
+        out = Split.empty((V, H, W, O), xb.device) if split else torch.empty((V, H, W, O), device=xb.device, dtype=torch.bfloat16)
+    ob = _base(out)
     e = _l.GemmEpilogue()
-    e.out, e.ldo, e.out_kind, e.act, e.alpha = out.data_ptr(), out.stride(2), KIND_BF16, act, 1.0
+    e.out, e.ldo, e.out_kind, e.act, e.alpha = ob.data_ptr(), ob.stride(2), _kind(out), act, 1.0
+    if split:
+        e.split_terms, e.a_lo_off, e.b_lo_off, e.out_lo_off = 3, x.lo_off, w.lo_off, out.lo_off
     if bias is not None:
         _need(bias, torch.float32, "conv3x3.bias")
         e.bias = bias.data_ptr()
-    _l.check(lib.pst3r_conv3x3_nhwc(x.data_ptr(), x.stride(2), V, H, W, Cc, w.data_ptr(), cpad, O, C.byref(e), _stream()),
+    _l.check(lib.pst3r_conv3x3_nhwc(xb.data_ptr(), xb.stride(2), V, H, W, Cc, wb.data_ptr(), cpad, O, C.byref(e), _stream()),
              "pst3r_conv3x3_nhwc")
     launches += 1
+    flop_count["gemm"] = flop_count.get("gemm", 0.0) + 2.0 * V * H * W * O * 9 * Cc * (3 if split else 1)
     return out
 
 
@@ -781,8 +789,8 @@ def loftup_guidance(img: torch.Tensor):
     return half, minmax
 
 
-def loftup_fourier_gn(half, minmax, gy, gx, freqs, biases, gamma, beta, eps: float, ld: int) -> torch.Tensor:
-    """-> bf16 pixel-major [V, Hh, Wh, ld]: GroupNorm(1)(ImplicitFeaturizer(MinMaxScaler(half)))."""
+def loftup_fourier_gn(half, minmax, gy, gx, freqs, biases, gamma, beta, eps: float, ld: int, split: bool = False):
+    """-> pixel-major [V, Hh, Wh, ld]: GroupNorm(1)(ImplicitFeaturizer(MinMaxScaler(half))); bf16, or a packed `Split`."""
     global launches
     lib = _l.load()
     for t, n in ((half, "half"), (minmax, "minmax"), (gy, "gy"), (gx, "gx"), (freqs, "freqs"), (biases, "biases"),
@@ -790,26 +798,31 @@ def loftup_fourier_gn(half, minmax, gy, gx, freqs, biases, gamma, beta, eps: flo
         _need(t, torch.float32, f"loftup_fourier_gn.{n}")
     V, _, Hh, Wh = half.shape
     nf = freqs.numel()
-    out = torch.empty((V, Hh, Wh, ld), device=half.device, dtype=torch.bfloat16)
+    out = Split.empty((V, Hh, Wh, ld), half.device) if split else torch.empty((V, Hh, Wh, ld), device=half.device, dtype=torch.bfloat16)
     ws = _loftup_ws(V, 10 * nf + 3, 1, half.device)
     _l.check(lib.pst3r_loftup_fourier_gn(half.data_ptr(), minmax.data_ptr(), gy.data_ptr(), gx.data_ptr(), freqs.data_ptr(),
                                          biases.data_ptr(), V, Hh, Wh, nf, gamma.data_ptr(), beta.data_ptr(), eps,
-                                         out.data_ptr(), ld, ws.data_ptr(), _stream()), "pst3r_loftup_fourier_gn")
+                                         _base(out).data_ptr(), _kind(out), ld, ws.data_ptr(), _stream()), "pst3r_loftup_fourier_gn")
     launches += 3
     return out
 
 
-def groupnorm_nhwc_(x: torch.Tensor, groups: int, gamma, beta, eps: float, relu: bool) -> torch.Tensor:
-    """In-place GroupNorm(groups) (+ReLU) on a dense pixel-major bf16 map [V, ..., C]."""
+def groupnorm_nhwc_(x, groups: int, gamma, beta, eps: float, relu: bool):
+    """In-place GroupNorm(groups) (+ReLU) on a dense pixel-major map [V, ..., C]: bf16, or a packed `Split`."""
     global launches
     lib = _l.load()
-    _need(x, torch.bfloat16, "groupnorm.x")
-    if not x.is_contiguous():
+    xb = _base(x)
+    _need(xb, torch.bfloat16, "groupnorm.x")
+    _packed(x, "groupnorm.x")
+    V, Cc = xb.shape[0], xb.shape[-1]
+    npix = xb.numel() // (V * Cc)
+    if isinstance(x, Split):
+        if not x.full().is_contiguous():
+            raise _l.Pst3rError("groupnorm.x: expected a dense split map")
+    elif not xb.is_contiguous():
         raise _l.Pst3rError("groupnorm.x: expected contiguous")
-    V, Cc = x.shape[0], x.shape[-1]
-    npix = x.numel() // (V * Cc)
-    ws = _loftup_ws(V, Cc, groups, x.device)
-    _l.check(lib.pst3r_groupnorm_nhwc(x.data_ptr(), V, npix, Cc, groups, gamma.data_ptr(), beta.data_ptr(), eps, int(relu),
+    ws = _loftup_ws(V, Cc, groups, xb.device)
+    _l.check(lib.pst3r_groupnorm_nhwc(xb.data_ptr(), _kind(x), V, npix, Cc, groups, gamma.data_ptr(), beta.data_ptr(), eps, int(relu),
                                       ws.data_ptr(), _stream()), "pst3r_groupnorm_nhwc")
     launches += 3
     return x
