@@ -163,6 +163,10 @@ typedef struct pst3r_attn_args {
   const uint32_t* mask_bits; int64_t mask_sb, mask_sq; /* strides in words */
   int32_t kv_splits;     /* 0 = auto */
   void* workspace; int64_t workspace_bytes;
+  /* Optional int32 arrival counters, >= ceil(Nq / 256) * B * H entries, ZERO on entry (the kernel leaves them zero):
+   * with them the split-KV partials are merged by the last CTA of each query block inside the attention kernel
+   * (head_dim 64, no mask) instead of by a second launch.  NULL: separate combine kernel. */
+  void* counters; int64_t counters_len;
 } pst3r_attn_args;
 
 int64_t pst3r_attention_workspace_bytes(int32_t B, int32_t H, int32_t Nq, int32_t head_dim, int32_t kv_splits);

@@ -83,9 +83,10 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 }
 
 // PROMOTE: accumulator promotion for split-mode reductions (GemmEpi::promote): every epilogue thread then keeps 128 fp32
-// partial sums in registers, so that variant is compiled for 192 registers per thread (200 would fit 65536 / 320 but not the per-warp allocation granularity: the launch fails).
+// partial sums in registers.  320 threads put 3 warps on one SM sub-partition (16 K registers), which caps a thread at
+// 168 registers: ptxas spills 64 bytes of that variant's epilogue (a launch with more registers per thread is refused).
 template <bool PROMOTE>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(PROMOTE ? 192 : 168)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmOut, const GemmEpi ep, const int M, const int N, const int K) {
   constexpr int BN = G2_BN;

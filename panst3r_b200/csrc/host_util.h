@@ -36,6 +36,7 @@ const char* get_last_error();
     if (_e != cudaSuccess) {                                                                    \
       pst3r::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
                             __LINE__);                                                          \
+      (void)cudaGetLastError(); /* reported through our return code: do not leave it for the next caller */ \
       return pst3r::PST3R_ERR_CUDA;                                                             \
     }                                                                                           \
   } while (0)

@@ -67,6 +67,7 @@ class AttnArgs(C.Structure):
         ("mask_bits", C.c_void_p), ("mask_sb", C.c_int64), ("mask_sq", C.c_int64),
         ("kv_splits", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("counters", C.c_void_p), ("counters_len", C.c_int64),
     ]
 
 
