@@ -333,12 +333,15 @@ def run_ours(args):
     # ---- per-kernel breakdown of ONE timed-configuration step (CUPTI device durations via torch.profiler) ----
     # taken on ONE stream (DINOv2 not overlapped with the memory build): a kernel that shares the SMs with another stream's
     # kernels reports an inflated duration, and the sum would no longer compare with the step time
-    ov = model.overlap_dino
+    # ... and without programmatic dependent launch: a dependent kernel that starts early waits for its predecessor
+    # INSIDE its own measured duration
+    ov, pdl = model.overlap_dino, ops.set_pdl(False)
     model.overlap_dino = False
     try:
         breakdown = kernel_breakdown(torch, step_device, barrier)
     finally:
         model.overlap_dino = ov
+        ops.set_pdl(pdl)
     roofline = att_roof = gemm_class = None
     if rank == 0:
         peaks, peak_src = _peaks()
@@ -462,7 +465,7 @@ def kernel_breakdown(torch, run_step, barrier):
             d["ms"] = round(d["ms"], 4)
         out = dict(sorted(agg.items(), key=lambda kv: -kv[1]["ms"]))
         out["_total_ms"] = round(total, 3)
-        out["_source"] = "CUPTI kernel durations (torch.profiler) of one step, single stream, eager launches"
+        out["_source"] = "CUPTI kernel durations (torch.profiler) of one step: single stream, eager launches, no PDL"
         return out
     except Exception as e:  # noqa: BLE001
         barrier()

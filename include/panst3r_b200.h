@@ -60,6 +60,10 @@ int pst3r_num_sms(void);
  * (engine/must3r.py:40-54) and the throughput-bound DINOv2 encoder (model/dino.py:59-71) run side by side on
  * two streams, each on its own share of the 148 SMs. */
 int pst3r_set_sm_budget(int32_t n_sms);
+/* Programmatic dependent launch (every kernel is launched with the programmatic-stream-serialization attribute and
+ * executes griddepcontrol.wait before its first global access) on / off; returns the previous setting.  Off for
+ * per-kernel profiling: a dependent kernel that starts early spends the wait inside ITS measured duration. */
+int pst3r_set_pdl(int32_t on);
 
 /* ---- GEMM: C[M,N] = epilogue(A[M,K] * B[N,K]^T) ---------------------------------------------
  * A, B are bf16, K contiguous (row strides lda/ldb in elements, multiples of 8).  tcgen05 tensor cores,
@@ -163,10 +167,6 @@ typedef struct pst3r_attn_args {
   const uint32_t* mask_bits; int64_t mask_sb, mask_sq; /* strides in words */
   int32_t kv_splits;     /* 0 = auto */
   void* workspace; int64_t workspace_bytes;
-  /* Optional int32 arrival counters, >= ceil(Nq / 256) * B * H entries, ZERO on entry (the kernel leaves them zero):
-   * with them the split-KV partials are merged by the last CTA of each query block inside the attention kernel
-   * (head_dim 64, no mask) instead of by a second launch.  NULL: separate combine kernel. */
-  void* counters; int64_t counters_len;
 } pst3r_attn_args;
 
 int64_t pst3r_attention_workspace_bytes(int32_t B, int32_t H, int32_t Nq, int32_t head_dim, int32_t kv_splits);

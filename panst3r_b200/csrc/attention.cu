@@ -61,7 +61,6 @@ struct AttnParams {
   int splits;
   float* ws_o;   // [splits][B*H][Nq][HD] fp32 (unnormalised)
   float* ws_ml;  // [splits][B*H][Nq][2]   (m in raw-score units, l)
-  int* counters; // [q blocks][B*H] arrival counters of the fused split-KV combine (zero before and after the launch) or NULL
 };
 
 template <int HD, bool HAS_MASK>
@@ -408,10 +407,7 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
   p.mask_bits = a->mask_bits; p.mask_sb = a->mask_sb; p.mask_sq = a->mask_sq;
   p.kv_shared = kv_shared;
   p.splits = splits;
-  p.ws_o = nullptr; p.ws_ml = nullptr; p.counters = nullptr;
-  const bool fused_combine = splits > 1 && HD == 64 && !a->mask_bits && a->counters != nullptr &&
-                             a->counters_len >= (long long)((a->Nq + 255) / 256) * a->B * a->H;
-  if (fused_combine) p.counters = reinterpret_cast<int*>(a->counters);
+  p.ws_o = nullptr; p.ws_ml = nullptr;
   if (splits > 1) {
     const long long rows = (long long)a->B * a->H * a->Nq;
     p.ws_o = reinterpret_cast<float*>(a->workspace);
@@ -439,7 +435,7 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
     PST3R_CHECK_CUDA(launch_pdl(kern, grid, dim3(ATT_THREADS), C::DYN_BYTES, stream, tmQ, tmK, tmV, p));
   }
   PST3R_CHECK_CUDA(cudaGetLastError());
-  if (splits > 1 && !fused_combine) {
+  if (splits > 1) {
     const long long rows = (long long)a->B * a->H * a->Nq;
     const int wpb = 8;
     const unsigned blocks = (unsigned)((rows + wpb - 1) / wpb);

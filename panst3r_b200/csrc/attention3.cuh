@@ -288,56 +288,6 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         p.ws_ml[row * 2 + 1] = l_run;
       }
     }
-    if (p.splits > 1 && p.counters) {
-      // Fused split-KV combine: the LAST CTA of this (query block, batch, head) to finish merges all partials — no
-      // separate combine launch (4-5 us of the latency-bound memory-build chain per attention call).  Partials are made
-      // visible device-wide (fence) before the arrival counter is bumped; the counter is left at zero for the next launch.
-      __shared__ int s_ticket;
-      __threadfence();
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 softmax warps
-      if (threadIdx.x == 128) s_ticket = atomicAdd(&p.counters[bh * gridDim.x + q_blk], 1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (s_ticket == p.splits - 1) {
-        __threadfence();
-        if (q < p.Nq) {
-          const long long rows = (long long)p.B * p.H * p.Nq;
-          const long long row = (long long)bh * p.Nq + q;
-          float mmax = -CUDART_INF_F;
-          for (int sp = 0; sp < p.splits; ++sp) mmax = fmaxf(mmax, __ldcg(&p.ws_ml[(sp * rows + row) * 2]));
-          float lsum = 0.0f;
-#pragma unroll
-          for (int i = 0; i < HD; ++i) o_acc[i] = 0.0f;
-          for (int sp = 0; sp < p.splits; ++sp) {
-            const long long rr = sp * rows + row;
-            const float m = __ldcg(&p.ws_ml[rr * 2]);
-            const float l = __ldcg(&p.ws_ml[rr * 2 + 1]);
-            const float w = (m == -CUDART_INF_F) ? 0.0f : exp2f((m - mmax) * p.scale_log2);
-            lsum = fmaf(w, l, lsum);
-            const float4* src = reinterpret_cast<const float4*>(p.ws_o + rr * HD);
-#pragma unroll
-            for (int i = 0; i < HD / 4; ++i) {
-              const float4 f = __ldcg(src + i);
-              o_acc[4 * i + 0] = fmaf(w, f.x, o_acc[4 * i + 0]);
-              o_acc[4 * i + 1] = fmaf(w, f.y, o_acc[4 * i + 1]);
-              o_acc[4 * i + 2] = fmaf(w, f.z, o_acc[4 * i + 2]);
-              o_acc[4 * i + 3] = fmaf(w, f.w, o_acc[4 * i + 3]);
-            }
-          }
-          const float inv = lsum > 0.0f ? 1.0f / lsum : 0.0f;
-          bf16* o = p.o + (long long)b * p.o_sb + (long long)q * p.o_sn + h * HD;
-#pragma unroll
-          for (int i = 0; i < HD / 8; ++i) {
-            uint4 u;
-            u.x = pack_bf16x2(o_acc[8 * i + 0] * inv, o_acc[8 * i + 1] * inv);
-            u.y = pack_bf16x2(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
-            u.z = pack_bf16x2(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv);
-            u.w = pack_bf16x2(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv);
-            reinterpret_cast<uint4*>(o)[i] = u;
-          }
-        }
-        if (threadIdx.x == 128) p.counters[bh * gridDim.x + q_blk] = 0;
-      }
-    }
   }
 
   tc_fence_before();

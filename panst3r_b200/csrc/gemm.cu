@@ -144,6 +144,10 @@ struct GemmSmem {
 };
 
 // ---- epilogue for one 32-column chunk owned by one thread (one output row) --------------------
+// SPLIT_IO = false is the all-bf16 hot path (plain bf16 / fp32 outputs, bf16 residual): it compiles to exactly the
+// round-1 epilogue.  SPLIT_IO = true adds the split-bf16 / fp32 residual kinds and the split stores of the
+// reference-precision head; keeping them out of the common instantiation keeps its register allocation and unrolling.
+template <bool SPLIT_IO>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32], int row, int col0, int M, int N,
                                                int bidx = 0, float2 ln = make_float2(0.0f, 1.0f)) {
   if (row >= M || col0 >= N) return;
@@ -211,7 +215,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
   }
   if (ep.residual) {
     const int rrow = ep.res_mod_rows > 0 ? row % ep.res_mod_rows : row;
-    if (ep.res_kind == KIND_F32) {
+    if (SPLIT_IO && ep.res_kind == KIND_F32) {
       const float* r = reinterpret_cast<const float*>(ep.residual) + (long long)rrow * ep.ldr + col0;
       if (full && ((ep.ldr & 3) == 0)) {
         const float4* r4 = reinterpret_cast<const float4*>(r);
@@ -227,9 +231,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
       }
     } else {
       const bf16* r = reinterpret_cast<const bf16*>(ep.residual) + (long long)rrow * ep.ldr + col0;
-      const int nparts = ep.res_kind == KIND_SPLIT ? 2 : 1;
-      for (int part = 0; part < nparts; ++part, r += ep.res_lo_off) {
-        if (full && ((ep.ldr & 7) == 0) && ((ep.res_lo_off & 7) == 0)) {
+#pragma unroll
+      for (int part = 0; part < (SPLIT_IO ? 2 : 1); ++part) {
+        if (part == 1) {
+          if (ep.res_kind != KIND_SPLIT) break;
+          r += ep.res_lo_off;
+        }
+        if (full && ((ep.ldr & 7) == 0) && (!SPLIT_IO || (ep.res_lo_off & 7) == 0)) {
           const uint4* r4 = reinterpret_cast<const uint4*>(r);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -256,7 +264,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
         const long long bb = row / ep.rows_per_batch;
         roff = bb * ep.batch_stride + (row - bb * ep.rows_per_batch) * ep.ldo;
       }
-      if (ep.out_kind == KIND_SPLIT) {
+      if (SPLIT_IO && ep.out_kind == KIND_SPLIT) {
         bf16* o = reinterpret_cast<bf16*>(ep.out) + roff + col0;
         if (full && ((ep.ldo & 7) == 0) && ((ep.batch_stride & 7) == 0) && ((ep.out_lo_off & 7) == 0) && ((ep.out_bs & 7) == 0)) {
 #pragma unroll
@@ -323,7 +331,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (i < ncols) o[(long long)i * ep.ldt] = v[i];
-      } else if (ep.out_kind == KIND_SPLIT) {
+      } else if (SPLIT_IO && ep.out_kind == KIND_SPLIT) {
         bf16* o = reinterpret_cast<bf16*>(ep.out) + b * ep.batch_stride + (long long)col0 * ep.ldt + r;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -353,7 +361,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
         const int i = ij >> 1, j = ij & 1;
         const long long orow = ((long long)(b * 2 * gh + 2 * y + i)) * (2 * gw) + 2 * x + j;
         bf16* o = base + orow * ep.ldo + c0;
-        if (ep.out_kind == KIND_SPLIT) {
+        if (SPLIT_IO && ep.out_kind == KIND_SPLIT) {
           float t8[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) t8[c] = v[4 * c + ij];
@@ -411,11 +419,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
   }
 }
 
-template <int BN, int STAGES, bool PROMOTE>
+// MODE 0: all-bf16 hot path; 1: split-bf16 operands / outputs (reference-precision head), short reductions;
+// 2: split mode with accumulator promotion (GemmEpi::promote)
+template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const GemmEpi ep, const int M, const int N, const int K) {
   using L = GemmSmem<BN, STAGES>;
+  constexpr bool PROMOTE = MODE == 2;
+  constexpr bool SPLIT_IO = MODE != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -432,7 +444,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tiles_per_batch = num_m_blocks * num_n_blocks;
   const int num_tiles = tiles_per_batch * ep.batches;
   const int num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
-  const int terms = ep.split_terms > 1 ? ep.split_terms : 1;
+  const int terms = (SPLIT_IO && ep.split_terms > 1) ? ep.split_terms : 1;
   const int num_k_iters = num_k_blocks * terms;  // split mode: one pass over the k-blocks per product term
   // PROMOTE: the reduction is cut into chunks that alternate between the two accumulators (see GemmEpi::promote)
   const int chunk_iters = PROMOTE ? ep.promote : num_k_iters;
@@ -473,16 +485,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int trem = tile - bidx * tiles_per_batch;
         const int m_blk = trem % num_m_blocks;
         const int n_blk = trem / num_m_blocks;
-        for (int it = 0; it < num_k_iters; ++it) {
-          const int term = it / num_k_blocks;
-          const int kb = it - term * num_k_blocks;
+        for (int term = 0; term < terms; ++term) {
+        // hi / lo part of each operand for this product term: (hi,hi), (lo,hi), (hi,lo) | (A,hi), (A,lo)
+        const int pa = (terms == 3 && term == 1) ? 1 : 0;
+        const int pb = (terms > 1 && term == terms - 1) ? 1 : 0;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
           uint8_t* a_dst = smem + s * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + L::A_BYTES;
-          // hi / lo part of each operand for this product term: (hi,hi), (lo,hi), (hi,lo) | (A,hi), (A,lo)
-          const int pa = (terms == 3 && term == 1) ? 1 : 0;
-          const int pb = (terms > 1 && term == terms - 1) ? 1 : 0;
           if (ep.conv_cblocks > 0) {
             // k-block -> (tap, channel block); m-tile -> (view, y, 128-pixel segment of the row)
             const int tap = kb / ep.conv_cblocks, cb = kb - tap * ep.conv_cblocks;
@@ -514,6 +525,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_2d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
         }
       }
     }
@@ -606,7 +618,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
           const int c = cgrp + 2 * j;
-          if (c < BN / 32 && c * 32 < n_rem) epilogue_chunk(ep, accv[j], row, n_blk * BN + c * 32, m_lim, N, bidx, ln);
+          if (c < BN / 32 && c * 32 < n_rem) epilogue_chunk<true>(ep, accv[j], row, n_blk * BN + c * 32, m_lim, N, bidx, ln);
         }
       } else {
         const int acc = local & 1;
@@ -626,7 +638,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (ep.tma_store)
             epilogue_chunk_tma(ep, &tmOut, out_stage, v, m_blk * GEMM_BM + quad * 32, n_blk * BN + c * 32, lane);
           else
-            epilogue_chunk(ep, v, row, n_blk * BN + c * 32, m_lim, N, bidx, ln);
+            epilogue_chunk<SPLIT_IO>(ep, v, row, n_blk * BN + c * 32, m_lim, N, bidx, ln);
         }
         tc_fence_before();
         __syncwarp();
@@ -645,11 +657,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int STAGES, bool PROMOTE = false>
+template <int BN, int STAGES, int MODE = 0>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const GemmEpi& ep, int M,
                        int N, int K, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
-  auto kern = gemm_bf16_tn_kernel<BN, STAGES, PROMOTE>;
+  auto kern = gemm_bf16_tn_kernel<BN, STAGES, MODE>;
   static bool configured = false;
   if (!configured) {
     PST3R_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
@@ -872,8 +884,15 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
     if (r) return r;
   }
   if (ep.promote)
-    return BN == 128 ? launch_gemm<128, 6, true>(tmA, tmB, tmOut, ep, M, N, K, stream)
-                     : launch_gemm<64, 8, true>(tmA, tmB, tmOut, ep, M, N, K, stream);
+    return BN == 128 ? launch_gemm<128, 6, 2>(tmA, tmB, tmOut, ep, M, N, K, stream)
+                     : launch_gemm<64, 8, 2>(tmA, tmB, tmOut, ep, M, N, K, stream);
+  if (terms || e->out_kind == PST3R_KIND_SPLIT || (e->residual && e->res_kind != PST3R_KIND_BF16)) {
+    switch (BN) {
+      case 256: return launch_gemm<256, 4, 1>(tmA, tmB, tmOut, ep, M, N, K, stream);
+      case 128: return launch_gemm<128, 6, 1>(tmA, tmB, tmOut, ep, M, N, K, stream);
+      default: return launch_gemm<64, 8, 1>(tmA, tmB, tmOut, ep, M, N, K, stream);
+    }
+  }
   switch (BN) {
     case 256: return launch_gemm<256, 4>(tmA, tmB, tmOut, ep, M, N, K, stream);
     case 128: return launch_gemm<128, 6>(tmA, tmB, tmOut, ep, M, N, K, stream);

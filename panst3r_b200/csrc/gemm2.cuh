@@ -85,12 +85,14 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 // PROMOTE: accumulator promotion for split-mode reductions (GemmEpi::promote): every epilogue thread then keeps 128 fp32
 // partial sums in registers.  320 threads put 3 warps on one SM sub-partition (16 K registers), which caps a thread at
 // 168 registers: ptxas spills 64 bytes of that variant's epilogue (a launch with more registers per thread is refused).
-template <bool PROMOTE>
+template <int MODE>  // as for gemm_bf16_tn_kernel: 0 all-bf16 hot path, 1 split operands / outputs, 2 split + promotion
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmOut, const GemmEpi ep, const int M, const int N, const int K) {
   constexpr int BN = G2_BN;
   constexpr int STAGES = G2_STAGES;
+  constexpr bool PROMOTE = MODE == 2;
+  constexpr bool SPLIT_IO = MODE != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_BAR_OFFSET);
@@ -110,7 +112,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int num_n_blocks = N / BN;  // host guarantees N % 256 == 0
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
-  const int terms = ep.split_terms > 1 ? ep.split_terms : 1;  // split-bf16 mode: see GemmEpi::split_terms
+  const int terms = (SPLIT_IO && ep.split_terms > 1) ? ep.split_terms : 1;  // split-bf16 mode: see GemmEpi::split_terms
   const int num_k_iters = num_k_blocks * terms;
   const int chunk_iters = PROMOTE ? ep.promote : num_k_iters;
   const int num_chunks = (num_k_iters + chunk_iters - 1) / chunk_iters;
@@ -149,16 +151,15 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile % num_m_blocks;
         const int n_blk = tile / num_m_blocks;
-        for (int it = 0; it < num_k_iters; ++it) {
-          const int term = it / num_k_blocks;
-          const int kb = it - term * num_k_blocks;
+        for (int term = 0; term < terms; ++term) {
+        const int pa = (terms == 3 && term == 1) ? 1 : 0;
+        const int pb = (terms > 1 && term == terms - 1) ? 1 : 0;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (leader) mbar_expect_tx(&full_bar[s], 2 * G2_STAGE_BYTES);
           uint8_t* a_dst = smem + s * G2_STAGE_BYTES;
           uint8_t* b_dst = a_dst + G2_A_BYTES;
           if (terms > 1) {
-            const int pa = (terms == 3 && term == 1) ? 1 : 0;
-            const int pb = (term == terms - 1) ? 1 : 0;
             tma_load_3d_2sm(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * 256 + (int)rank * 128, pa);
             tma_load_3d_2sm(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)rank * (BN / 2), pb);
           } else {
@@ -166,6 +167,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tma_load_2d_2sm(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)rank * (BN / 2));
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
         }
       }
     }
@@ -239,7 +241,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
         }
 #pragma unroll
-        for (int j = 0; j < NCH; ++j) epilogue_chunk(ep, accv[j], row, n_blk * BN + (cgrp + 2 * j) * 32, M, N, 0, ln);
+        for (int j = 0; j < NCH; ++j) epilogue_chunk<true>(ep, accv[j], row, n_blk * BN + (cgrp + 2 * j) * 32, M, N, 0, ln);
       } else {
         const int acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
@@ -257,7 +259,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (ep.tma_store)
             epilogue_chunk_tma(ep, &tmOut, out_stage, v, m_blk * 256 + (int)rank * 128 + quad * 32, n_blk * BN + c * 32, lane);
           else
-            epilogue_chunk(ep, v, row, n_blk * BN + c * 32, M, N, 0, ln);
+            epilogue_chunk<SPLIT_IO>(ep, v, row, n_blk * BN + c * 32, M, N, 0, ln);
         }
         tc_fence_before();
         __syncwarp();
@@ -289,8 +291,9 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
                         int N, int K, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
-    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
+    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
+    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
+    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
     configured = true;
   }
   const int tiles = ((M + 255) / 256) * (N / G2_BN);
@@ -307,9 +310,11 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   if (ep.promote)
-    PST3R_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<true>, tmA, tmB, tmOut, ep, M, N, K));
+    PST3R_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<2>, tmA, tmB, tmOut, ep, M, N, K));
+  else if (ep.split_terms || ep.out_kind == KIND_SPLIT || (ep.residual && ep.res_kind != KIND_BF16))
+    PST3R_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<1>, tmA, tmB, tmOut, ep, M, N, K));
   else
-    PST3R_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<false>, tmA, tmB, tmOut, ep, M, N, K));
+    PST3R_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<0>, tmA, tmB, tmOut, ep, M, N, K));
   return PST3R_OK;
 }
 

@@ -83,13 +83,18 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
   return PST3R_OK;
 }
 
+static int g_pdl = -1;
 bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_pdl < 0) {
     const char* e = getenv("PST3R_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
   }
-  return v == 1;
+  return g_pdl == 1;
+}
+int set_pdl(int on) {
+  const int prev = pdl_enabled() ? 1 : 0;
+  g_pdl = on ? 1 : 0;
+  return prev;
 }
 
 int num_sms() {
@@ -119,3 +124,4 @@ extern "C" int pst3r_set_sm_budget(int32_t n) {
   return prev;
 }
 extern "C" int pst3r_num_sms(void) { return pst3r::num_sms(); }
+extern "C" int pst3r_set_pdl(int32_t on) { return pst3r::set_pdl(on); }

@@ -61,6 +61,7 @@ void set_sm_budget(int n);
 // launched this way executes griddepcontrol.wait (pdl_wait() in common.cuh) before touching global memory.
 // PST3R_PDL=0 in the environment disables the attribute (plain stream order).
 bool pdl_enabled();
+int set_pdl(int on);  // returns the previous setting
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

@@ -67,7 +67,6 @@ class AttnArgs(C.Structure):
         ("mask_bits", C.c_void_p), ("mask_sb", C.c_int64), ("mask_sq", C.c_int64),
         ("kv_splits", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
-        ("counters", C.c_void_p), ("counters_len", C.c_int64),
     ]
 
 
@@ -79,6 +78,7 @@ SIGNATURES = {
     "pst3r_check_device": (C.c_int, []),
     "pst3r_num_sms": (C.c_int, []),
     "pst3r_set_sm_budget": (C.c_int, [_i32]),
+    "pst3r_set_pdl": (C.c_int, [_i32]),
     "pst3r_gemm_bf16_batched": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, C.POINTER(GemmEpilogue),
                                           _i64, _i64, _p]),
     "pst3r_layernorm_batched": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _i64, _f, _p, _i64, _i64, _i32, _i32, _i32, _p]),

@@ -15,8 +15,6 @@ from . import lib as _l
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 STORE_PLAIN, STORE_TRANSPOSED, STORE_PIXSHUF2, STORE_D2S = 0, 1, 2, 3
 
-fused_combine = True  # split-KV partials merged inside the attention kernel (False: separate combine launch, for A/B runs)
-
 # launch counter (bench.py reports gpu_launches from this) and algorithmic FLOPs issued per kernel class
 launches = 0
 flop_count = {}
@@ -341,6 +339,11 @@ def set_sm_budget(n: int) -> int:
     return _l.load().pst3r_set_sm_budget(int(n))
 
 
+def set_pdl(on: bool) -> bool:
+    """Programmatic dependent launch on / off for the following launches; returns the previous setting."""
+    return bool(_l.load().pst3r_set_pdl(int(bool(on))))
+
+
 def num_sms() -> int:
     return _l.load().pst3r_num_sms()
 
@@ -382,19 +385,6 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return t
 
 
-_cnt_cache = {}
-
-
-def _counters(device) -> torch.Tensor:
-    """Zeroed int32 arrival counters of the current stream for the fused split-KV combine (kernels leave them zero)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
-    t = _cnt_cache.get(key)
-    if t is None:
-        t = torch.zeros(1 << 14, dtype=torch.int32, device=device)
-        _cnt_cache[key] = t
-    return t
-
-
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None,
               mask_bits: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
               kv_splits: int = 0) -> torch.Tensor:
@@ -432,16 +422,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optio
     splits = kv_splits if kv_splits > 0 else lib.pst3r_attention_auto_splits(B, H, Nq, Nk)
     a.kv_splits = splits
     need = lib.pst3r_attention_workspace_bytes(B, H, Nq, hd, splits)
-    fused = False
     if need > 0:
         ws = _workspace(need, q.device)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-        if hd == 64 and mask_bits is None and fused_combine:
-            cnt = _counters(q.device)
-            a.counters, a.counters_len = cnt.data_ptr(), cnt.numel()
-            fused = ((Nq + 255) // 256) * B * H <= cnt.numel()
     _l.check(lib.pst3r_attention(C.byref(a), _stream()), "pst3r_attention")
-    launches += 1 if (splits <= 1 or fused) else 2
+    launches += 1 if splits <= 1 else 2
     flop_count["attention"] = flop_count.get("attention", 0.0) + 4.0 * B * H * Nq * Nk * hd
     return out
 

@@ -31,6 +31,20 @@ PY
     memcheck) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_precise.py tests/test_gpu_kernels.py -m gpu -q -x -k "not full_size and not 12288 and not 4864" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" ;;
     racecheck) timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "layernorm or mask_helpers or patchify or rope" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" ;;
     launches) timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r02.csv python tools/profile_step.py step > gpurun_out/launches_r02.log 2>&1 ;;
+    ab)  # A/B on the same box, back to back: this tree (all-bf16 head; optional paths toggled) vs the round-1 tree (_r1/)
+      one() { python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['clocks']['sm_mhz'], d['gpu_launches'])"; }
+      for cfg in "" "PST3R_TMA_STORE=0" ""; do
+        echo "--- this tree, bf16 head [$cfg]" >> gpurun_out/ab.log
+        env $cfg timeout 300 python bench.py --head-precision bf16 --no-gpu-reference --no-cpu-baseline --no-bf16-head --steps 20 2>/dev/null | one >> gpurun_out/ab.log 2>&1
+      done
+      if [ -d _r1 ]; then
+        for i in 1 2; do
+          echo "--- round-1 tree" >> gpurun_out/ab.log
+          (cd _r1 && timeout 300 python bench.py --no-cpu-baseline --steps 20 2>/dev/null | one) >> gpurun_out/ab.log 2>&1
+        done
+      fi
+      echo "--- this tree, fp32-grade head" >> gpurun_out/ab.log
+      timeout 300 python bench.py --no-gpu-reference --no-cpu-baseline --no-bf16-head --steps 20 2>/dev/null | one >> gpurun_out/ab.log 2>&1 ;;
     *) echo "unknown step $s" ;;
   esac
 done
