@@ -143,7 +143,10 @@ def main():
     make_conditioned_golden(ref)
 
 
-COND = dict(variant="v1", V=3, H=64, W=96, input_seed=21, cls_logit_scale=3.0)
+# input seed 2416: the best of seeds 100..3099 by `min_decision_margin` (tools/seed_search.py): every one of the reference's
+# 6 x 200 x 48 sign(mask logit) decisions is at least 6.8e-5 of the largest logit away from zero, i.e. the fixture is well
+# conditioned for an implementation with 16 mantissa bits (measured logit error 2e-5 of the maximum) as well as for fp32.
+COND = dict(variant="v1", V=2, H=64, W=96, input_seed=2416, cls_logit_scale=3.0)
 
 
 def make_conditioned_golden(ref=None):
@@ -166,11 +169,13 @@ def make_conditioned_golden(ref=None):
                  "out_queries": out["out_queries"],
                  "aux_logits": [a["pred_logits"] for a in out["aux_outputs"]],
                  "pooled_logits": _pooled(rec),
+                 "min_decision_margin": min(float(p_.abs().min() / p_.abs().max()) for p_ in _pooled(rec)),
                  "ids": weighted.argmax(1).to(torch.int16), "margin": top2[:, 0] - top2[:, 1]})
     torch.save(blob, os.path.join(GOLDEN, "head_v1_conditioned.pt"))
     mg = blob["margin"]
-    print("wrote head_v1_conditioned.pt: |mask logit| max %.2f, |class logit| max %.2f, margin > 1e-4 on %.3f of the pixels"
-          % (out["pred_masks"].abs().max(), out["pred_logits"].abs().max(), (mg > 1e-4).float().mean()))
+    print("wrote head_v1_conditioned.pt: |mask logit| max %.2f, |class logit| max %.2f, margin > 1e-4 on %.3f of the pixels, "
+          "min decision margin %.2e" % (out["pred_masks"].abs().max(), out["pred_logits"].abs().max(),
+                                        (mg > 1e-4).float().mean(), blob["min_decision_margin"]))
 
 
 def make_postprocess_golden(ref=None):

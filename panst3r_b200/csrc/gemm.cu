@@ -136,11 +136,15 @@ struct GemmSmem {
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t OUT_OFFSET = STAGES * STAGE_BYTES;  // epilogue staging tiles for TMA stores
-  static constexpr uint32_t BAR_OFFSET = OUT_OFFSET + GEMM_OUT_STAGE_BYTES;
+  static constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr uint32_t TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
-  static_assert(TOTAL + 1024 <= 232448, "shared memory budget");
   static constexpr uint32_t DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
+  // epilogue staging tiles of the TMA-store mode live BEHIND everything else and are only requested by launches that use
+  // them: the common launches keep ~31 KB of the SM's shared memory free, which lets the CTAs of a dependent
+  // (programmatic dependent launch) kernel without shared memory — LayerNorm, split-KV combine — become resident early
+  static constexpr uint32_t OUT_OFFSET = (TOTAL + 127) & ~127u;
+  static constexpr uint32_t DYN_BYTES_TMA = OUT_OFFSET + GEMM_OUT_STAGE_BYTES + 1024;
+  static_assert(DYN_BYTES_TMA <= 232448, "shared memory budget");
 };
 
 // ---- epilogue for one 32-column chunk owned by one thread (one output row) --------------------
@@ -664,12 +668,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   auto kern = gemm_bf16_tn_kernel<BN, STAGES, MODE>;
   static bool configured = false;
   if (!configured) {
-    PST3R_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    PST3R_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES_TMA));
     configured = true;
   }
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN) * ep.batches;
   const int grid = tiles < sm_budget() ? tiles : sm_budget();
-  PST3R_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::DYN_BYTES, stream, tmA, tmB, tmOut, ep, M, N, K));
+  const size_t dyn = ep.tma_store ? L::DYN_BYTES_TMA : L::DYN_BYTES;
+  PST3R_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), dyn, stream, tmA, tmB, tmOut, ep, M, N, K));
   return PST3R_OK;
 }
 

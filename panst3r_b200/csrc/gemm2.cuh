@@ -16,9 +16,11 @@ constexpr int G2_STAGES = 6;
 constexpr uint32_t G2_A_BYTES = GEMM_BM * GEMM_BK * 2;          // 16 KB
 constexpr uint32_t G2_B_BYTES = (G2_BN / 2) * GEMM_BK * 2;      // 16 KB (half of the B tile)
 constexpr uint32_t G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr uint32_t G2_OUT_OFFSET = G2_STAGES * G2_STAGE_BYTES;  // epilogue staging tiles for TMA stores
-constexpr uint32_t G2_BAR_OFFSET = G2_OUT_OFFSET + GEMM_OUT_STAGE_BYTES;
-constexpr uint32_t G2_DYN_BYTES = G2_BAR_OFFSET + (2 * G2_STAGES + 4) * 8 + 16 + 1024;
+constexpr uint32_t G2_BAR_OFFSET = G2_STAGES * G2_STAGE_BYTES;
+constexpr uint32_t G2_TOTAL = G2_BAR_OFFSET + (2 * G2_STAGES + 4) * 8 + 16;
+constexpr uint32_t G2_DYN_BYTES = G2_TOTAL + 1024;
+constexpr uint32_t G2_OUT_OFFSET = (G2_TOTAL + 127) & ~127u;  // TMA-store staging tiles: requested only by launches using them
+constexpr uint32_t G2_DYN_BYTES_TMA = G2_OUT_OFFSET + GEMM_OUT_STAGE_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -291,9 +293,9 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
                         int N, int K, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
-    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
-    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
+    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES_TMA));
+    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES_TMA));
+    PST3R_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES_TMA));
     configured = true;
   }
   const int tiles = ((M + 255) / 256) * (N / G2_BN);
@@ -302,7 +304,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = G2_DYN_BYTES;
+  cfg.dynamicSmemBytes = ep.tma_store ? G2_DYN_BYTES_TMA : G2_DYN_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];  // the cluster shape (2,1,1) is compiled into the kernel (__cluster_dims__)
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

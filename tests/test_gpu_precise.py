@@ -303,11 +303,12 @@ def _ids(out, H, W):
 
 
 def test_argmax_ids_exact_on_conditioned_fixture():
-    """a well-conditioned fixture (class logits O(1), mask logits O(1)) and the post-processing front
-    half's score-weighted argmax (engine/postprocess.py:18-27, 63, 77).
-    With the reference's sign decisions: ids bit-exact on every decidable pixel, > 90 % of the pixels decidable.
-    Free-running: decisions differ only inside the rounding band; ids bit-exact on every pixel that is decidable at the
-    free run's own measured score error."""
+    """a well-conditioned fixture — class logits O(1), mask logits O(1), and every one of the
+    reference's 57 600 sign(mask logit) decisions at least 6.8e-5 of the largest logit away from zero (input seed chosen
+    by tools/seed_search.py) — and the post-processing front half's score-weighted argmax (engine/postprocess.py:18-27,
+    63, 77).  The FREE-RUNNING six-layer decoder takes exactly the reference's decisions, its final mask / class logits
+    agree to 1e-3, more than 90 % of the pixels are decidable and the instance ids are bit-exact on every one of them.
+    The same holds with the reference's decisions forced."""
     g = torch.load(os.path.join(GOLDEN, "head_v1_conditioned.pt"))
     o, m = _cuda_head("v1", cls_logit_scale=g["cls_logit_scale"])
     feats, imgs, pos, ts = head_inputs(g["V"], g["H"], g["W"], g["input_seed"])
@@ -328,10 +329,11 @@ def test_argmax_ids_exact_on_conditioned_fixture():
               f"{e['pred_logits']:.1e}; decidable pixels {frac:.4f}; ids equal on {(ids == g['ids'].long()).float().mean().item():.4f}")
         assert torch.equal(ids[safe], g["ids"].long()[safe])
         results[name] = (e, frac, flips, out, safe)
-    e, frac, _, out, safe = results["forced"]
-    assert e["pred_masks"] < TOL_HEAD and e["pred_logits"] < TOL_HEAD and frac > 0.9
-    if results["free"][2] == 0:
-        assert results["free"][0]["pred_masks"] < TOL_HEAD and results["free"][1] > 0.9
+    assert g["min_decision_margin"] > 5e-5
+    for name in ("forced", "free"):
+        e, frac, flips, out, safe = results[name]
+        assert flips == 0, f"{name}: {flips} sign decisions differ on the well-conditioned fixture"
+        assert e["pred_masks"] < TOL_HEAD and e["pred_logits"] < TOL_HEAD and frac > 0.9, (name, e, frac)
     # through the CUDA post-processing front half as well (fused sigmoid -> bilinear -> score-weighted argmax)
     from panst3r_b200 import ops
     sc, _ = ops.class_scores(out["pred_logits"][0].contiguous())

@@ -33,7 +33,7 @@ PY
     launches) timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r02.csv python tools/profile_step.py step > gpurun_out/launches_r02.log 2>&1 ;;
     ab)  # A/B on the same box, back to back: this tree (all-bf16 head; optional paths toggled) vs the round-1 tree (_r1/)
       one() { python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['clocks']['sm_mhz'], d['gpu_launches'])"; }
-      for cfg in "" "PST3R_TMA_STORE=0" ""; do
+      for cfg in "" "PST3R_SHALLOW=0" "" "PST3R_SHALLOW=0"; do
         echo "--- this tree, bf16 head [$cfg]" >> gpurun_out/ab.log
         env $cfg timeout 300 python bench.py --head-precision bf16 --no-gpu-reference --no-cpu-baseline --no-bf16-head --steps 20 2>/dev/null | one >> gpurun_out/ab.log 2>&1
       done
@@ -45,6 +45,7 @@ PY
       fi
       echo "--- this tree, fp32-grade head" >> gpurun_out/ab.log
       timeout 300 python bench.py --no-gpu-reference --no-cpu-baseline --no-bf16-head --steps 20 2>/dev/null | one >> gpurun_out/ab.log 2>&1 ;;
+    ksums) { python tools/kernel_sums.py . bf16; [ -d _r1 ] && python tools/kernel_sums.py _r1; python tools/kernel_sums.py . fp32; } > gpurun_out/kernel_sums.log 2>&1 ;;
     *) echo "unknown step $s" ;;
   esac
 done
