@@ -46,6 +46,10 @@ PY
       echo "--- this tree, fp32-grade head" >> gpurun_out/ab.log
       timeout 300 python bench.py --no-gpu-reference --no-cpu-baseline --no-bf16-head --steps 20 2>/dev/null | one >> gpurun_out/ab.log 2>&1 ;;
     ksums) { python tools/kernel_sums.py . bf16; [ -d _r1 ] && python tools/kernel_sums.py _r1; python tools/kernel_sums.py . fp32; } > gpurun_out/kernel_sums.log 2>&1 ;;
+    dist2) timeout 900 python -m pytest tests/test_gpu_dist.py -m gpu -q -x --timeout 800 > gpurun_out/pytest_dist.log 2>&1; echo "dist rc=$?" ;;
+    bench2|bench4|bench8) n=${s#bench}; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/bench_${n}gpu.json 2> gpurun_out/bench_${n}gpu.err; echo "bench$n rc=$?" ;;
+    ncufull) timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -f -o gpurun_out/r02_key_kernels python tools/profile_step.py kernels > gpurun_out/ncufull.log 2>&1
+             ncu -i gpurun_out/r02_key_kernels.ncu-rep --page raw --csv > gpurun_out/r02_key_kernels_raw.csv 2>/dev/null; echo "ncufull rc=$?" ;;
     *) echo "unknown step $s" ;;
   esac
 done

@@ -46,6 +46,10 @@ def main():
         mo = torch.empty(V, 200, 192, 256, device="cuda", dtype=torch.float32)
         x = r(V * 768, 1024)
         gam, bet = torch.ones(1024, device="cuda"), torch.zeros(1024, device="cuda")
+        # reference-precision head (split-bf16 operands): upscaler fc2 with accumulator promotion, mask einsum with TMA stores
+        ah, wh = ops.Split.from_float(torch.randn(V * 768, 11264, device="cuda")), ops.Split.from_float(torch.randn(2048, 11264, device="cuda") * 0.01)
+        oh = ops.Split.empty((V * 4 * 768, 512), "cuda")
+        fs, es = ops.Split.from_float(feats.float()), ops.Split.from_float(emb.float())
 
         def run():
             ops.attention(q, k, v)
@@ -54,6 +58,8 @@ def main():
             ops.gemm(a2, w2)
             ops.gemm(feats, emb, out=mo, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=192 * 256, batch_stride=200 * 192 * 256, ldt=192 * 256)
             ops.layernorm(x, gam, bet, 1e-6)
+            ops.gemm(ah, wh, out=oh, store_mode=ops.STORE_PIXSHUF2, grid=(24 * V, 32))
+            ops.gemm(fs, es, out=mo, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=192 * 256, batch_stride=200 * 192 * 256, ldt=192 * 256)
         for _ in range(2):
             run()
         torch.cuda.synchronize()
