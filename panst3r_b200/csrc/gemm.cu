@@ -207,7 +207,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, float (&v)[32]
   }
   if (ep.act == PST3R_ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 32; i += 2) {
+      const float2 g = gelu_erf2(make_float2(v[i], v[i + 1]));
+      v[i] = g.x; v[i + 1] = g.y;
+    }
   } else if (ep.act == PST3R_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);

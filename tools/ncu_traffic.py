@@ -38,7 +38,7 @@ def main():
         u = units[col[name]].lower()
         if scale_from_unit:
             v *= {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9,
-                  "second": 1.0}.get(u, 1.0)
+                  "second": 1.0, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1.0}.get(u, 1.0)
         return v
 
     out = {}
@@ -51,7 +51,8 @@ def main():
             "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes": None if rd is None or wr is None else rd + wr,
             "tensor_pipe_pct": get(r, "sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active", False)
             or get(r, "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", False),
-            "dram_throughput_pct": get(r, "dram__throughput.avg.pct_of_peak_sustained_elapsed", False),
+            "dram_gbs": None if rd is None or wr is None else (rd + wr) / 1e9 / max(get(r, "gpu__time_duration.sum") or 1e-9, 1e-9),
+            "sm_throughput_pct": get(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed", False),
             "registers": get(r, "launch__registers_per_thread", False),
             "source": f"ncu --set full --clock-control none, tools/profile_step.py kernels ({os.path.basename(src)})",
         }
