@@ -377,6 +377,84 @@ __global__ void attention_combine_kernel(const float* __restrict__ ws_o, const f
   }
 }
 
+// One query per (batch, head) on the CUDA cores: DINOv2's CLS token (model/dino.py:59-71 keeps it through all 24
+// layers and drops it at the end).  769 = 3 x 256 + 1 tokens would otherwise cost a fourth 256-query CTA per (batch, head)
+// for a single row — a quarter of the attention work of every DINOv2 layer.  One block per (b, h); thread per key for the
+// scores, then 4 key groups x 64 value columns.
+__global__ void __launch_bounds__(256)
+attention_q1_kernel(const bf16* __restrict__ q, long long q_sb, long long q_sh, const bf16* __restrict__ k, long long k_sb,
+                    long long k_sn, long long k_sh, const bf16* __restrict__ v, long long v_sb, long long v_sn, long long v_sh,
+                    bf16* __restrict__ o, long long o_sb, int H, int Nk, float scale_log2) {
+  constexpr int HD = 64;
+  extern __shared__ float sm[];  // [Nk] probabilities | [4][64] partial outputs | [16] reductions
+  float* prob = sm;
+  float* part = sm + ((Nk + 3) & ~3);
+  float* red = part + 4 * HD;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float qr[HD];
+  {
+    const uint4* q4 = reinterpret_cast<const uint4*>(q + b * q_sb + h * q_sh);
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      const uint4 u = __ldg(q4 + i);
+      float2 f;
+      f = unpack_bf16x2(u.x); qr[8 * i + 0] = f.x; qr[8 * i + 1] = f.y;
+      f = unpack_bf16x2(u.y); qr[8 * i + 2] = f.x; qr[8 * i + 3] = f.y;
+      f = unpack_bf16x2(u.z); qr[8 * i + 4] = f.x; qr[8 * i + 5] = f.y;
+      f = unpack_bf16x2(u.w); qr[8 * i + 6] = f.x; qr[8 * i + 7] = f.y;
+    }
+  }
+  float mx = -CUDART_INF_F;
+  for (int key = tid; key < Nk; key += 256) {
+    const uint4* k4 = reinterpret_cast<const uint4*>(k + b * k_sb + (long long)key * k_sn + h * k_sh);
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      const uint4 u = __ldg(k4 + i);
+      float2 f;
+      f = unpack_bf16x2(u.x); s = fmaf(qr[8 * i + 0], f.x, fmaf(qr[8 * i + 1], f.y, s));
+      f = unpack_bf16x2(u.y); s = fmaf(qr[8 * i + 2], f.x, fmaf(qr[8 * i + 3], f.y, s));
+      f = unpack_bf16x2(u.z); s = fmaf(qr[8 * i + 4], f.x, fmaf(qr[8 * i + 5], f.y, s));
+      f = unpack_bf16x2(u.w); s = fmaf(qr[8 * i + 6], f.x, fmaf(qr[8 * i + 7], f.y, s));
+    }
+    prob[key] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.0f;
+  for (int key = tid; key < Nk; key += 256) {
+    const float e = ex2_approx((prob[key] - mx) * scale_log2);
+    prob[key] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[8 + warp] = sum;
+  __syncthreads();
+  float tot = 0.0f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[8 + w];
+  // output: thread = (key group g, column d); 4 groups stride the keys
+  const int d = tid & 63, g = tid >> 6;
+  float acc = 0.0f;
+  const bf16* vb = v + b * v_sb + h * v_sh + d;
+  for (int key = g; key < Nk; key += 4) acc = fmaf(prob[key], __bfloat162float(vb[(long long)key * v_sn]), acc);
+  part[g * HD + d] = acc;
+  __syncthreads();
+  if (tid < HD) {
+    const float r = (part[tid] + part[HD + tid]) + (part[2 * HD + tid] + part[3 * HD + tid]);
+    o[b * o_sb + h * HD + tid] = __float2bfloat16(tot > 0.0f ? r / tot : 0.0f);
+  }
+}
+
 }  // namespace pst3r
 #include "attention3.cuh"
 namespace pst3r {
@@ -493,6 +571,17 @@ extern "C" int pst3r_attention(const pst3r_attn_args* a, pst3r_stream_t stream_)
     PST3R_CHECK_ARG(a->workspace && a->workspace_bytes >= need,
                     "attention: workspace too small (%lld < %lld bytes for %d splits)",
                     (long long)a->workspace_bytes, (long long)need, splits);
+  }
+  if (a->head_dim == 64 && a->Nq == 1 && !a->mask_bits && a->Nk <= 8192) {
+    // a single query per (batch, head): CUDA-core kernel (DINOv2's CLS token)
+    const size_t smem = (((size_t)a->Nk + 3) & ~(size_t)3) * 4 + (4 * 64 + 16) * 4;
+    PST3R_CHECK_CUDA(launch_pdl(attention_q1_kernel, dim3(a->B * a->H), dim3(256), smem, stream,
+                                reinterpret_cast<const bf16*>(a->q), (long long)a->q_sb, (long long)a->q_sh,
+                                reinterpret_cast<const bf16*>(a->k), (long long)a->k_sb, (long long)a->k_sn, (long long)a->k_sh,
+                                reinterpret_cast<const bf16*>(a->v), (long long)a->v_sb, (long long)a->v_sn, (long long)a->v_sh,
+                                reinterpret_cast<bf16*>(a->o), (long long)a->o_sb, (int)a->H, (int)a->Nk,
+                                a->scale * 1.4426950408889634f));
+    return PST3R_OK;
   }
   if (a->head_dim == 64) return launch_attention<64>(a, splits, stream);
   return launch_attention<96>(a, splits, stream);

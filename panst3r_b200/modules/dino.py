@@ -123,12 +123,16 @@ class DinoV2Encoder(nn.Module):
         # single producing GEMM.
         s1, s2 = fold_stats(b * T, D, dev, 2, enable=self.fold_ln)
         st = None
+        o = torch.empty((b, T, D), device=dev, dtype=torch.bfloat16)
         for lyr in self.dinov2.encoder.layer:
             a_ = lyr.attention.attention
             qkv = ln_linear(xr, st, lyr.norm1, [a_.query.weight, a_.key.weight, a_.value.weight],
                             [a_.query.bias, a_.key.bias, a_.value.bias], self.eps, plain_w=lyr.qkv_weight,
                             plain_b=lyr.qkv_bias).view(b, T, 3, Hh, D // Hh)
-            o = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2])
+            # 1 + N tokens: the N patch queries fill whole 256-query CTAs of the tensor-core kernel, the CLS query (one row
+            # per view and head) goes to the single-query kernel instead of occupying a fourth CTA per (view, head)
+            ops.attention(qkv[:, 1:, 0], qkv[:, :, 1], qkv[:, :, 2], out=o[:, 1:])
+            ops.attention(qkv[:, :1, 0], qkv[:, :, 1], qkv[:, :, 2], out=o[:, :1])
             dense = lyr.attention.output.dense
             ops.gemm(o.view(b * T, D), w16(dense.weight), bias=bias_of(dense), col_scale=f32(lyr.layer_scale1.lambda1),
                      residual=xr, out=xr, stats_out=s1)

@@ -229,6 +229,20 @@ def test_attention(ops, B, H, Nq, Nk, hd, splits):
     assert relmax(ops.attention(q, k, v, kv_splits=splits), attn_ref(q, k, v, hd ** -0.5)) < TOL_ATTN
 
 
+def test_attention_cls_row_split(ops):
+    """DINOv2 layout (1 + N tokens, packed QKV): patch queries through the tensor-core kernel, the CLS query through the
+    single-query kernel, both writing into one output — equals attention over all 1 + N queries."""
+    B, T, H, hd = 3, 1 + 192, 16, 64
+    qkv = rnd(B, T, 3, H, hd)
+    o = torch.zeros(B, T, H * hd, device="cuda", dtype=torch.bfloat16)
+    ops.attention(qkv[:, 1:, 0], qkv[:, :, 1], qkv[:, :, 2], out=o[:, 1:])
+    ops.attention(qkv[:, :1, 0], qkv[:, :, 1], qkv[:, :, 2], out=o[:, :1])
+    ref = attn_ref(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], hd ** -0.5)
+    assert relmax(o, ref) < TOL_ATTN and relmax(o[:, :1], ref[:, :1]) < TOL_ATTN
+    q1, k1, v1 = rnd(2, 1, 12, 64), rnd(1, 769, 12, 64), rnd(1, 769, 12, 64)  # K/V shared by the batch
+    assert relmax(ops.attention(q1, k1, v1), attn_ref(q1, k1.expand(2, -1, -1, -1), v1.expand(2, -1, -1, -1), 0.125)) < TOL_ATTN
+
+
 def test_attention_layouts(ops):
     B, N, H, hd = 2, 384, 12, 64
     qkv = rnd(B, N, 3, H, hd)  # packed QKV projection output
