@@ -229,6 +229,18 @@ def test_attention(ops, B, H, Nq, Nk, hd, splits):
     assert relmax(ops.attention(q, k, v, kv_splits=splits), attn_ref(q, k, v, hd ** -0.5)) < TOL_ATTN
 
 
+def test_attention_reference_maximum_raised_late(ops):
+    """Full tiles after the first are swept once against the running maximum (no max pass); keys that beat it by a wide
+    margin late in the sequence must send the tile through the two-pass route: results stay those of exact softmax."""
+    q, k, v = rnd(2, 512, 4, 64), rnd(2, 2048, 4, 64), rnd(2, 2048, 4, 64)
+    k[:, 1500:1510] *= 12.0   # scores ~12x larger than anything before: ex2 against the stale reference would overflow
+    k[:, 300:302] *= 3.0      # a moderate excess (inside the 2^12 headroom of the single sweep)
+    ref = attn_ref(q, k, v, 0.125)
+    assert relmax(ops.attention(q, k, v), ref) < TOL_ATTN
+    assert relmax(ops.attention(q, k, v, kv_splits=4), ref) < TOL_ATTN
+    assert torch.isfinite(ops.attention(q, k, v).float()).all()
+
+
 def test_attention_cls_row_split(ops):
     """DINOv2 layout (1 + N tokens, packed QKV): patch queries through the tensor-core kernel, the CLS query through the
     single-query kernel, both writing into one output — equals attention over all 1 + N queries."""

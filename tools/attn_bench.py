@@ -1,4 +1,5 @@
-"""Times the hd-64 attention kernel at the in-step shapes (development tool).  PST3R_ATT=2|3 selects the kernel generation."""
+"""Times the hd-64 attention kernel at the in-step shapes and checks it against torch SDPA, including a peaky-score case
+that forces the lazily kept reference maximum to be raised inside later tiles (development tool)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,7 +17,6 @@ def timed(fn, reps=10):
     return e0.elapsed_time(e1) / reps * 1e3
 
 r = lambda *s: torch.randn(*s, device="cuda").bfloat16()
-print("PST3R_ATT =", os.environ.get("PST3R_ATT", "(default 3)"), "PST3R_ATT_POLY =", os.environ.get("PST3R_ATT_POLY", "(default)"))
 for name, B, H, Nq, Nk, shared in [("render cross", 16, 12, 768, 12288, True), ("encoder self", 16, 16, 768, 768, False),
                                    ("dino self", 16, 16, 769, 769, False), ("membuild cross", 1, 12, 768, 11520, True),
                                    ("membuild self", 1, 12, 768, 768, False)]:

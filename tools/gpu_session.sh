@@ -50,6 +50,7 @@ PY
     bench2|bench4|bench8) n=${s#bench}; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/bench_${n}gpu.json 2> gpurun_out/bench_${n}gpu.err; echo "bench$n rc=$?" ;;
     ncufull) timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -f -o gpurun_out/r02_key_kernels python tools/profile_step.py kernels > gpurun_out/ncufull.log 2>&1
              ncu -i gpurun_out/r02_key_kernels.ncu-rep --page raw --csv > gpurun_out/r02_key_kernels_raw.csv 2>/dev/null; echo "ncufull rc=$?" ;;
+    attnb) timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.log 2>&1; [ -d _r1 ] && (cd _r1 && timeout 300 python ../tools/attn_bench.py) > gpurun_out/attn_bench_r1.log 2>&1 ;;
     *) echo "unknown step $s" ;;
   esac
 done
