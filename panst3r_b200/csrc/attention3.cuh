@@ -188,12 +188,37 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int kmax = p.Nk - (t0 + j) * ATT_BN;
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+      float mx = m_run;
+      if (kmax >= ATT_BN) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t rr[32];
+          tmem_ld32(s_addr + ch * 32, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
+        }
+      } else {
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t rr[32];
+          tmem_ld32(s_addr + ch * 32, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (ch * 32 + i < kmax) mx = fmaxf(mx, __uint_as_float(rr[i]));
+        }
+      }
+      const float m_use = (mx == -CUDART_INF_F) ? 0.0f : mx;
+      const float alpha = (m_run == -CUDART_INF_F) ? 0.0f : ex2_approx((m_run - m_use) * c);
+      const float neg_m = -m_use * c;
+      m_run = mx;
+      if (j > 0) consume_o(j - 1, a_prev);  // also guarantees P V of tile j-1 is done reading P_t from TMEM
+      a_prev = alpha;
       float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
       float2 sA = make_float2(0.0f, 0.0f), sB = make_float2(0.0f, 0.0f);
-      float alpha = 1.0f;
-      const float2 c2 = make_float2(c, c);
-      // exponentials of one full 128-key tile against the reference maximum encoded in nm2; bf16 P into TMEM, row sums
-      auto exp_pass = [&](const float2 nm2) {
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(neg_m, neg_m);
+      if (kmax >= ATT_BN) {
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           uint32_t rr[32];
@@ -216,73 +241,22 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           }
           tmem_st16(p_addr + ch * 16, pk);
         }
-      };
-      // Every full tile but the first takes ONE sweep over the scores with the running maximum as the reference — no
-      // separate max pass, no rescaling of O and l.  The probabilities may then exceed 1; if some row's sum passes 2^12 (a
-      // score beat the reference by more than ~12 in the log2 domain, or ex2 overflowed) the warp repeats the tile the
-      // two-pass way and overwrites its P before the tile is handed to the tensor core.
-      const bool full_tile = kmax >= ATT_BN;
-      bool need_max = !(j > 0 && full_tile);
-      bool consumed = false;
+      } else {
 #pragma unroll 1
-      for (;;) {
-        float neg_m = -m_run * c;
-        if (need_max) {
-          float mx = m_run;
-          if (full_tile) {
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t rr[32];
+          tmem_ld32(s_addr + ch * 32, rr);
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              uint32_t rr[32];
-              tmem_ld32(s_addr + ch * 32, rr);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
-            }
-          } else {
-#pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-              uint32_t rr[32];
-              tmem_ld32(s_addr + ch * 32, rr);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (ch * 32 + i < kmax) mx = fmaxf(mx, __uint_as_float(rr[i]));
-            }
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = (ch * 32 + i < kmax) ? ex2_approx(fmaf(__uint_as_float(rr[i]), c, neg_m)) : 0.0f;
+            const float e1 = (ch * 32 + i + 1 < kmax) ? ex2_approx(fmaf(__uint_as_float(rr[i + 1]), c, neg_m)) : 0.0f;
+            sum0 += e0; sum1 += e1;
+            pk[i >> 1] = pack_bf16x2(e0, e1);
           }
-          const float m_use = (mx == -CUDART_INF_F) ? 0.0f : mx;
-          alpha = (m_run == -CUDART_INF_F) ? 0.0f : ex2_approx((m_run - m_use) * c);
-          neg_m = -m_use * c;
-          m_run = mx;
+          tmem_st16(p_addr + ch * 16, pk);
         }
-        if (j > 0 && !consumed) {
-          consume_o(j - 1, a_prev);  // also guarantees P V of tile j-1 is done reading P_t from TMEM
-          consumed = true;
-        }
-        a_prev = alpha;
-        if (full_tile) {
-          exp_pass(make_float2(neg_m, neg_m));
-        } else {
-#pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t rr[32];
-            tmem_ld32(s_addr + ch * 32, rr);
-            tmem_ld_wait();
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float e0 = (ch * 32 + i < kmax) ? ex2_approx(fmaf(__uint_as_float(rr[i]), c, neg_m)) : 0.0f;
-              const float e1 = (ch * 32 + i + 1 < kmax) ? ex2_approx(fmaf(__uint_as_float(rr[i + 1]), c, neg_m)) : 0.0f;
-              sum0 += e0; sum1 += e1;
-              pk[i >> 1] = pack_bf16x2(e0, e1);
-            }
-            tmem_st16(p_addr + ch * 16, pk);
-          }
-        }
-        if (need_max) break;
-        const float rs = (sA.x + sA.y) + (sB.x + sB.y);
-        if (!__any_sync(0xffffffffu, !(rs <= 4096.0f))) break;
-        need_max = true;
-        sA = sB = make_float2(0.0f, 0.0f);
       }
       l_run = fmaf(l_run, alpha, ((sum0 + sum1) + (sum2 + sum3)) + ((sA.x + sA.y) + (sB.x + sB.y)));
       tmem_st_wait();
