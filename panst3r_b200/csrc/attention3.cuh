@@ -11,12 +11,17 @@
 // waiting on exactly that port (P V alone needs 162 B/clk against the 128 B/clk an SM can read).  With P in TMEM
 // the P V product reads only V (16 KB per step), the softmax warps issue 4 tcgen05.st instead of 16 st.shared,
 // and the freed 80 KB of smem deepen the K/V ring to 4 stages.  Row sums are accumulated by the softmax threads (fp32).
-// CTA: 384 threads = TMA warp, MMA warp, 2 idle warps, 4 + 4 softmax warps (one per TMEM lane quadrant and sub-tile).
+// CTA: 640 threads = TMA warp, MMA warp, 2 idle warps, 8 + 8 softmax warps: TWO threads per score row (one per 64-key half
+// of the tile; they exchange their half-row maxima through shared memory and a 64-thread named barrier once per tile, their
+// row sums once at the end) and each folds half of the output columns.  Round 1 ran one thread per row (4 + 4 warps): with a
+// single softmax warp of each sub-tile per SM sub-partition nobody filled the issue slots a warp left empty while it waited
+// for TMEM, a barrier or the MUFU (profiles/r02_attention_single_sweep.md: removing a quarter of the instructions changed
+// nothing); four independent warps per sub-partition do.
 #pragma once
 
 namespace pst3r {
 
-constexpr int AT3_THREADS = 384;
+constexpr int AT3_THREADS = 640;
 constexpr int AT3_STAGES = 4;
 constexpr uint32_t AT3_OFF_Q = 0;                                       // 2 x 16 KB
 constexpr uint32_t AT3_OFF_K = AT3_OFF_Q + 2 * ATT_ATOM_BYTES;          // 4 x 16 KB
@@ -24,7 +29,8 @@ constexpr uint32_t AT3_OFF_V = AT3_OFF_K + AT3_STAGES * ATT_ATOM_BYTES; // 4 x 1
 constexpr uint32_t AT3_OFF_BAR = AT3_OFF_V + AT3_STAGES * ATT_ATOM_BYTES;
 // barriers: q_full, k_full[ST], v_full[ST], kv_empty[ST], s_full[2], p_full[2], o_full[2]
 constexpr int AT3_NUM_BARS = 1 + 3 * AT3_STAGES + 6;
-constexpr uint32_t AT3_DYN_BYTES = AT3_OFF_BAR + AT3_NUM_BARS * 8 + 16 + 1024;
+constexpr uint32_t AT3_OFF_X = AT3_OFF_BAR + 256;  // fp32 exchange area [2 buffers][2 sub-tiles][2 halves][128 rows]
+constexpr uint32_t AT3_DYN_BYTES = AT3_OFF_X + 2 * 2 * 2 * 128 * 4 + 1024;
 constexpr uint32_t AT3_TMEM_S = 0;     // S_A at 0, S_B at 128 (fp32)
 constexpr uint32_t AT3_TMEM_O = 256;   // O_A at 256, O_B at 320 (fp32)
 constexpr uint32_t AT3_TMEM_P = 384;   // P_A at 384, P_B at 448 (bf16 pairs: column c of row r = keys 2c, 2c+1)
@@ -73,7 +79,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 256);
       mbar_init(&o_full[i], 1);
     }
     mbar_fence_init();
@@ -146,27 +152,29 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else if (warp >= 4) {
     // ------------------------------- softmax / accumulate -----------------------
-    const int t = (warp - 4) >> 2;  // sub-tile
-    const int quad = warp & 3;
+    const int t = (warp - 4) >> 3;         // sub-tile
+    const int quad = warp & 3;             // TMEM lane quadrant
+    const int half = ((warp - 4) >> 2) & 1;  // which 64 keys of a tile / which 32 output columns
     const int r = quad * 32 + lane;
     const int q = q_blk * 256 + t * 128 + r;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t s_addr = lane_addr + AT3_TMEM_S + t * ATT_BN;
-    const uint32_t o_addr = lane_addr + AT3_TMEM_O + t * HD;
-    const uint32_t p_addr = lane_addr + AT3_TMEM_P + t * (ATT_BN / 2);
-    float o_acc[HD];
+    const uint32_t s_addr = lane_addr + AT3_TMEM_S + t * ATT_BN + half * 64;
+    const uint32_t o_addr = lane_addr + AT3_TMEM_O + t * HD + half * 32;
+    const uint32_t p_addr = lane_addr + AT3_TMEM_P + t * (ATT_BN / 2) + half * 32;
+    float* xchg = reinterpret_cast<float*>(smem + AT3_OFF_X);
+    const int bar_id = 1 + t * 4 + quad;   // named barrier of the two warps that share these 32 rows
+    float o_acc[32];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) o_acc[i] = 0.0f;
+    for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
     float m_run = -CUDART_INF_F, l_run = 0.0f, a_prev = 0.0f;
     const float c = p.scale_log2;
 
-    auto consume_o = [&](int j, float alpha) {  // O_acc = O_acc * alpha + O_t(j)
+    auto consume_o = [&](int j, float alpha) {  // O_acc = O_acc * alpha + O_t(j), this thread's 32 columns
       mbar_wait(&o_full[t], j & 1);
       tc_fence_after();
       uint32_t rr[32];
       tmem_ld32(o_addr, rr);
       tmem_ld_wait();
-      // packed fp32x2 FMA (sm_100): half the issue slots of the fold
       const float2 al2 = make_float2(alpha, alpha);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
@@ -174,24 +182,16 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                                      make_float2(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])));
         o_acc[i] = r2.x; o_acc[i + 1] = r2.y;
       }
-      tmem_ld32(o_addr + 32, rr);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float2 r2 = __ffma2_rn(make_float2(o_acc[32 + i], o_acc[33 + i]), al2,
-                                     make_float2(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])));
-        o_acc[32 + i] = r2.x; o_acc[33 + i] = r2.y;
-      }
     };
 
     for (int j = 0; j < n_tiles; ++j) {
-      const int kmax = p.Nk - (t0 + j) * ATT_BN;
+      const int kv = p.Nk - (t0 + j) * ATT_BN - half * 64;  // valid keys among this thread's 64 (may exceed 64 / be <= 0)
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      float mx = m_run;
-      if (kmax >= ATT_BN) {
+      float mx = -CUDART_INF_F;
+      if (kv >= 64) {
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           uint32_t rr[32];
           tmem_ld32(s_addr + ch * 32, rr);
           tmem_ld_wait();
@@ -200,27 +200,32 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       } else {
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           uint32_t rr[32];
           tmem_ld32(s_addr + ch * 32, rr);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (ch * 32 + i < kmax) mx = fmaxf(mx, __uint_as_float(rr[i]));
+            if (ch * 32 + i < kv) mx = fmaxf(mx, __uint_as_float(rr[i]));
         }
       }
+      // the other half of the row: exchange the half-row maxima (double buffered across tiles)
+      float* xb = xchg + (((j & 1) * 2 + t) * 2) * 128;
+      xb[half * 128 + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      mx = fmaxf(fmaxf(mx, xb[(1 - half) * 128 + r]), m_run);
       const float m_use = (mx == -CUDART_INF_F) ? 0.0f : mx;
       const float alpha = (m_run == -CUDART_INF_F) ? 0.0f : ex2_approx((m_run - m_use) * c);
       const float neg_m = -m_use * c;
       m_run = mx;
       if (j > 0) consume_o(j - 1, a_prev);  // also guarantees P V of tile j-1 is done reading P_t from TMEM
       a_prev = alpha;
-      float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
+      float sum0 = 0.0f, sum1 = 0.0f;
       float2 sA = make_float2(0.0f, 0.0f), sB = make_float2(0.0f, 0.0f);
       const float2 c2 = make_float2(c, c), nm2 = make_float2(neg_m, neg_m);
-      if (kmax >= ATT_BN) {
+      if (kv >= 64) {
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           uint32_t rr[32];
           tmem_ld32(s_addr + ch * 32, rr);
           tmem_ld_wait();
@@ -243,34 +248,41 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       } else {
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           uint32_t rr[32];
           tmem_ld32(s_addr + ch * 32, rr);
           tmem_ld_wait();
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float e0 = (ch * 32 + i < kmax) ? ex2_approx(fmaf(__uint_as_float(rr[i]), c, neg_m)) : 0.0f;
-            const float e1 = (ch * 32 + i + 1 < kmax) ? ex2_approx(fmaf(__uint_as_float(rr[i + 1]), c, neg_m)) : 0.0f;
+            const float e0 = (ch * 32 + i < kv) ? ex2_approx(fmaf(__uint_as_float(rr[i]), c, neg_m)) : 0.0f;
+            const float e1 = (ch * 32 + i + 1 < kv) ? ex2_approx(fmaf(__uint_as_float(rr[i + 1]), c, neg_m)) : 0.0f;
             sum0 += e0; sum1 += e1;
             pk[i >> 1] = pack_bf16x2(e0, e1);
           }
           tmem_st16(p_addr + ch * 16, pk);
         }
       }
-      l_run = fmaf(l_run, alpha, ((sum0 + sum1) + (sum2 + sum3)) + ((sA.x + sA.y) + (sB.x + sB.y)));
+      l_run = fmaf(l_run, alpha, (sum0 + sum1) + ((sA.x + sA.y) + (sB.x + sB.y)));
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
     }
     if (n_tiles > 0) consume_o(n_tiles - 1, a_prev);
 
+    // row sum of both halves (same reference maximum on both sides)
+    {
+      float* xb = xchg + ((n_tiles & 1) * 2 + t) * 2 * 128;
+      xb[half * 128 + r] = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      l_run += xb[(1 - half) * 128 + r];
+    }
     if (q < p.Nq) {
       if (p.splits == 1) {
         const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
-        bf16* o = p.o + (long long)b * p.o_sb + (long long)q * p.o_sn + h * HD;
+        bf16* o = p.o + (long long)b * p.o_sb + (long long)q * p.o_sn + h * HD + half * 32;
 #pragma unroll
-        for (int i = 0; i < HD / 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           uint4 u;
           u.x = pack_bf16x2(o_acc[8 * i + 0] * inv, o_acc[8 * i + 1] * inv);
           u.y = pack_bf16x2(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
@@ -280,12 +292,14 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       } else {
         const long long row = ((long long)split * p.B * p.H + bh) * p.Nq + q;
-        float* wo = p.ws_o + row * HD;
+        float* wo = p.ws_o + row * HD + half * 32;
 #pragma unroll
-        for (int i = 0; i < HD / 4; ++i)
+        for (int i = 0; i < 8; ++i)
           reinterpret_cast<float4*>(wo)[i] = make_float4(o_acc[4 * i], o_acc[4 * i + 1], o_acc[4 * i + 2], o_acc[4 * i + 3]);
-        p.ws_ml[row * 2 + 0] = m_run;
-        p.ws_ml[row * 2 + 1] = l_run;
+        if (half == 0) {
+          p.ws_ml[row * 2 + 0] = m_run;
+          p.ws_ml[row * 2 + 1] = l_run;
+        }
       }
     }
   }
