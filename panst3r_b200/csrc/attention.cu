@@ -19,7 +19,9 @@
 #include "../../include/panst3r_b200.h"
 
 #include <math_constants.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <vector>
 
 namespace pst3r {
 
@@ -61,6 +63,8 @@ struct AttnParams {
   int splits;
   float* ws_o;   // [splits][B*H][Nq][HD] fp32 (unnormalised)
   float* ws_ml;  // [splits][B*H][Nq][2]   (m in raw-score units, l)
+  long long* trace;  // development aid (attention3.cuh), normally null
+  int trace_mode;    // timing experiments of the traced kernel (bit mask, attention3.cuh); results are wrong when non-zero
 };
 
 template <int HD, bool HAS_MASK>
@@ -486,6 +490,7 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
   p.kv_shared = kv_shared;
   p.splits = splits;
   p.ws_o = nullptr; p.ws_ml = nullptr;
+  p.trace = nullptr; p.trace_mode = 0;
   if (splits > 1) {
     const long long rows = (long long)a->B * a->H * a->Nq;
     p.ws_o = reinterpret_cast<float*>(a->workspace);
@@ -496,11 +501,36 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
     // 256 queries per CTA, probabilities in tensor memory (attention3.cuh)
     static bool cfg3 = false;
     if (!cfg3) {
-      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_DYN_BYTES));
+      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention3_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_DYN_BYTES));
+      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention3_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_DYN_BYTES));
       cfg3 = true;
     }
     dim3 grid2((a->Nq + 255) / 256, a->B * a->H, splits);
-    PST3R_CHECK_CUDA(launch_pdl(attention3_fwd_kernel, grid2, dim3(AT3_THREADS), AT3_DYN_BYTES, stream, tmQ, tmK, tmV, p));
+    static const char* trace_path = getenv("PST3R_ATT_TRACE");
+    if (trace_path && a->Nk >= 4096) {
+      // development aid: one traced launch, synchronous, timeline of CTA (0,0,0) written as text (tools/attn_trace.py reads it)
+      constexpr int TR_N = 5 * 16 * 128;
+      long long* dtr = nullptr;
+      PST3R_CHECK_CUDA(cudaMalloc(&dtr, TR_N * sizeof(long long)));
+      PST3R_CHECK_CUDA(cudaMemsetAsync(dtr, 0, TR_N * sizeof(long long), stream));
+      p.trace = dtr;
+      if (const char* m = getenv("PST3R_ATT_TRACE_MODE")) p.trace_mode = atoi(m);
+      PST3R_CHECK_CUDA(launch_pdl(attention3_fwd_kernel<true>, grid2, dim3(AT3_THREADS), AT3_DYN_BYTES, stream, tmQ, tmK, tmV, p));
+      PST3R_CHECK_CUDA(cudaStreamSynchronize(stream));
+      std::vector<long long> h(TR_N);
+      PST3R_CHECK_CUDA(cudaMemcpy(h.data(), dtr, TR_N * sizeof(long long), cudaMemcpyDeviceToHost));
+      PST3R_CHECK_CUDA(cudaFree(dtr));
+      if (FILE* f = fopen(trace_path, "w")) {
+        for (int sl = 0; sl < 5; ++sl)
+          for (int ev = 0; ev < 16; ++ev)
+            for (int j = 0; j < 128; ++j)
+              if (h[((sl * 16 + ev) << 7) + j]) fprintf(f, "%d %d %d %lld\n", sl, ev, j, h[((sl * 16 + ev) << 7) + j]);
+        fclose(f);
+      }
+      p.trace = nullptr;
+    } else {
+      PST3R_CHECK_CUDA(launch_pdl(attention3_fwd_kernel<false>, grid2, dim3(AT3_THREADS), AT3_DYN_BYTES, stream, tmQ, tmK, tmV, p));
+    }
   } else if (a->mask_bits) {
     auto kern = attention_fwd_kernel<HD, true>;
     static bool cfg = false;

@@ -35,6 +35,11 @@ constexpr uint32_t AT3_TMEM_S = 0;     // S_A at 0, S_B at 128 (fp32)
 constexpr uint32_t AT3_TMEM_O = 256;   // O_A at 256, O_B at 320 (fp32)
 constexpr uint32_t AT3_TMEM_P = 384;   // P_A at 384, P_B at 448 (bf16 pairs: column c of row r = keys 2c, 2c+1)
 
+// TRACE: development aid (PST3R_ATT_TRACE=<file>): CTA (0,0,0) records clock64() at the hand-over points of the MMA thread
+// and of one softmax thread per (sub-tile, half) into p.trace[(slot * 16 + event) * 128 + tile]
+#define AT3_TR(slot, ev, j) do { if (TRACE && tr_on && (j) < 128) p.trace[(((slot) * 16 + (ev)) << 7) + (j)] = clock64(); } while (0)
+
+template <bool TRACE>
 __global__ void __launch_bounds__(AT3_THREADS, 1)
 attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -60,6 +65,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int h = bh - b * p.H;
   const int split = blockIdx.z;
   const int kvb = p.kv_shared ? 0 : b;
+  const bool tr_on = TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
   const int total_tiles = (p.Nk + ATT_BN - 1) / ATT_BN;
   const int tiles_per_split = (total_tiles + p.splits - 1) / p.splits;
@@ -135,10 +141,12 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (j + 1 < n_tiles) mbar_wait(&k_full[(j + 1) % ST], ((j + 1) / ST) & 1);
         mbar_wait(&v_full[s], (j / ST) & 1);
         const uint32_t v_addr = smem_u32(smem + AT3_OFF_V + s * ATT_ATOM_BYTES);
+        AT3_TR(0, 0, j);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           // p_full(t, j): P_t(j) is in TMEM, S_t(j) has been fully read, O_t(j-1) has been consumed
           mbar_wait(&p_full[t], j & 1);
+          AT3_TR(0, 1 + 2 * t, j);
           tc_fence_after();
           if (j + 1 < n_tiles) issue_s(t, j + 1);  // next scores first: the softmax of t restarts soonest
 #pragma unroll
@@ -146,6 +154,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             umma_ts(tmem_base + AT3_TMEM_O + t * HD, tmem_base + AT3_TMEM_P + t * (ATT_BN / 2) + ks * 8,
                     make_smem_desc_sw128(v_addr + ks * 16 * 128, ATT_ATOM_BYTES, 1024), idesc_pv, ks != 0);
           umma_commit(&o_full[t]);
+          AT3_TR(0, 2 + 2 * t, j);
         }
         umma_commit(&kv_empty[s]);
       }
@@ -163,6 +172,9 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t p_addr = lane_addr + AT3_TMEM_P + t * (ATT_BN / 2) + half * 32;
     float* xchg = reinterpret_cast<float*>(smem + AT3_OFF_X);
     const int bar_id = 1 + t * 4 + quad;   // named barrier of the two warps that share these 32 rows
+    const int tr_slot = 1 + t + 2 * half;
+    const bool tr_me = quad == 0 && lane == 0;
+#define AT3_TRS(ev, j) do { if (tr_me) AT3_TR(tr_slot, ev, j); } while (0)
     float o_acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
@@ -171,7 +183,9 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
     auto consume_o = [&](int j, float alpha) {  // O_acc = O_acc * alpha + O_t(j), this thread's 32 columns
       mbar_wait(&o_full[t], j & 1);
+      AT3_TRS(3, j + 1);
       tc_fence_after();
+      if (TRACE && (p.trace_mode & 2)) return;
       uint32_t rr[32];
       tmem_ld32(o_addr, rr);
       tmem_ld_wait();
@@ -187,9 +201,12 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int j = 0; j < n_tiles; ++j) {
       const int kv = p.Nk - (t0 + j) * ATT_BN - half * 64;  // valid keys among this thread's 64 (may exceed 64 / be <= 0)
       mbar_wait(&s_full[t], j & 1);
+      AT3_TRS(0, j);
       tc_fence_after();
       float mx = -CUDART_INF_F;
-      if (kv >= 64) {
+      if (TRACE && (p.trace_mode & 1)) {
+        mx = 8.0f;
+      } else if (kv >= 64) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           uint32_t rr[32];
@@ -212,7 +229,9 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // the other half of the row: exchange the half-row maxima (double buffered across tiles)
       float* xb = xchg + (((j & 1) * 2 + t) * 2) * 128;
       xb[half * 128 + r] = mx;
+      AT3_TRS(1, j);
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      AT3_TRS(2, j);
       mx = fmaxf(fmaxf(mx, xb[(1 - half) * 128 + r]), m_run);
       const float m_use = (mx == -CUDART_INF_F) ? 0.0f : mx;
       const float alpha = (m_run == -CUDART_INF_F) ? 0.0f : ex2_approx((m_run - m_use) * c);
@@ -220,15 +239,33 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       m_run = mx;
       if (j > 0) consume_o(j - 1, a_prev);  // also guarantees P V of tile j-1 is done reading P_t from TMEM
       a_prev = alpha;
+      AT3_TRS(4, j);
       float sum0 = 0.0f, sum1 = 0.0f;
       float2 sA = make_float2(0.0f, 0.0f), sB = make_float2(0.0f, 0.0f);
       const float2 c2 = make_float2(c, c), nm2 = make_float2(neg_m, neg_m);
-      if (kv >= 64) {
+      if (TRACE && (p.trace_mode & 4)) {
+        // timing experiment: no sweep at all
+      } else if (TRACE && (p.trace_mode & 8)) {
+        // timing experiment: tensor-memory traffic of the sweep without its arithmetic
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           uint32_t rr[32];
           tmem_ld32(s_addr + ch * 32, rr);
           tmem_ld_wait();
+          tmem_st16(p_addr + ch * 16, rr);
+        }
+      } else if (kv >= 64) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t rr[32];
+          if (TRACE && (p.trace_mode & 16)) {
+            // timing experiment: the arithmetic of the sweep without reading the scores
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(o_acc[i] + (float)ch);
+          } else {
+            tmem_ld32(s_addr + ch * 32, rr);
+            tmem_ld_wait();
+          }
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -264,9 +301,11 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       }
       l_run = fmaf(l_run, alpha, (sum0 + sum1) + ((sA.x + sA.y) + (sB.x + sB.y)));
+      AT3_TRS(5, j);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      AT3_TRS(6, j);
     }
     if (n_tiles > 0) consume_o(n_tiles - 1, a_prev);
 
@@ -311,5 +350,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tmem_dealloc(tmem_base, 512);
   }
 }
+#undef AT3_TRS
+#undef AT3_TR
 
 }  // namespace pst3r

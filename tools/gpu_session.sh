@@ -33,7 +33,7 @@ PY
     launches) timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r02.csv python tools/profile_step.py step > gpurun_out/launches_r02.log 2>&1 ;;
     ab)  # A/B on the same box, back to back: this tree (all-bf16 head; optional paths toggled) vs the round-1 tree (_r1/)
       one() { python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['clocks']['sm_mhz'], d['gpu_launches'])"; }
-      for cfg in "" "PST3R_SHALLOW=0" "" "PST3R_SHALLOW=0"; do
+      for cfg in "" ""; do
         echo "--- this tree, bf16 head [$cfg]" >> gpurun_out/ab.log
         env $cfg timeout 300 python bench.py --head-precision bf16 --no-gpu-reference --no-cpu-baseline --no-bf16-head --steps 20 2>/dev/null | one >> gpurun_out/ab.log 2>&1
       done
@@ -51,6 +51,8 @@ PY
     ncufull) timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -f -o gpurun_out/r02_key_kernels python tools/profile_step.py kernels > gpurun_out/ncufull.log 2>&1
              ncu -i gpurun_out/r02_key_kernels.ncu-rep --page raw --csv > gpurun_out/r02_key_kernels_raw.csv 2>/dev/null; echo "ncufull rc=$?" ;;
     attnb) timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.log 2>&1; [ -d _r1 ] && (cd _r1 && timeout 300 python ../tools/attn_bench.py) > gpurun_out/attn_bench_r1.log 2>&1 ;;
+    attntr) timeout 300 python tools/attn_trace.py gpurun_out/attn_trace.md > gpurun_out/attn_trace.log 2>&1; echo "attntr rc=$?" ;;
+    mmarate) timeout 120 tools/_bin/mma_rate > gpurun_out/mma_rate.md 2>&1; echo "mmarate rc=$?" ;;
     *) echo "unknown step $s" ;;
   esac
 done
