@@ -486,7 +486,7 @@ def dominant_roofline(ops, torch, V, peaks, peak_src, breakdown):
     """The kernel with the largest share of the step (CUPTI breakdown), timed alone with CUDA events at its in-step shape
     AND with its in-step epilogue (bias + erf-GELU for the ViT-L fc1)."""
     names = [k for k in (breakdown or {}) if not k.startswith("_")]
-    dom = names[0] if names else "attention3_fwd_kernel"
+    dom = names[0] if names else "attention5_fwd_kernel"
     dev = "cuda"
     reps = 20
     traffic_tab = _load_traffic()
@@ -497,7 +497,7 @@ def dominant_roofline(ops, torch, V, peaks, peak_src, breakdown):
         v = torch.randn(1, Nk, Hh, hd, device=dev).bfloat16()
         fn = lambda: ops.attention(q, k, v)  # noqa: E731
         flops = 4.0 * B * Hh * Nq * Nk * hd
-        name = f"attention3_fwd_kernel B{B} H{Hh} Nq{Nq} Nk{Nk} hd64 (decoder render cross-attention)"
+        name = f"attention5_fwd_kernel B{B} H{Hh} Nq{Nq} Nk{Nk} hd64 (decoder render cross-attention)"
         tkey = "attention3_render"
     else:
         M, N, K = V * 768, 4096, 1024  # encoder / DINOv2 fc1 with its in-step epilogue
@@ -565,7 +565,7 @@ def attention_roofline(ops, torch, V, peaks, peak_src):
     ms = e0.elapsed_time(e1) / 10
     ach = 4.0 * B * Hh * Nq * Nk * hd / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops", 1590.0))
-    return {"kernel": f"attention3_fwd_kernel B{B} H{Hh} Nq{Nq} Nk{Nk} hd{hd} (render cross-attention over keyframe memory)",
+    return {"kernel": f"attention5_fwd_kernel B{B} H{Hh} Nq{Nq} Nk{Nk} hd{hd} (render cross-attention over keyframe memory)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "kernel_ms": ms,
             "bound": "MUFU ex2 (16/clk/SM) at head_dim 64: ceiling ~1150 TFLOP/s",
             "peak_source": peak_src}

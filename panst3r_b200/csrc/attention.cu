@@ -63,8 +63,7 @@ struct AttnParams {
   int splits;
   float* ws_o;   // [splits][B*H][Nq][HD] fp32 (unnormalised)
   float* ws_ml;  // [splits][B*H][Nq][2]   (m in raw-score units, l)
-  long long* trace;  // development aid (attention3.cuh), normally null
-  int trace_mode;    // timing experiments of the traced kernel (bit mask, attention3.cuh); results are wrong when non-zero
+  long long* trace;  // development aid (attention5.cuh, tools/attn_trace.py), normally null
 };
 
 template <int HD, bool HAS_MASK>
@@ -460,7 +459,7 @@ attention_q1_kernel(const bf16* __restrict__ q, long long q_sb, long long q_sh, 
 }
 
 }  // namespace pst3r
-#include "attention3.cuh"
+#include "attention5.cuh"
 namespace pst3r {
 
 static int make_qkv_map(CUtensorMap* m, const void* ptr, int hd, long long n, int H, int B, long long sn,
@@ -490,7 +489,7 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
   p.kv_shared = kv_shared;
   p.splits = splits;
   p.ws_o = nullptr; p.ws_ml = nullptr;
-  p.trace = nullptr; p.trace_mode = 0;
+  p.trace = nullptr;
   if (splits > 1) {
     const long long rows = (long long)a->B * a->H * a->Nq;
     p.ws_o = reinterpret_cast<float*>(a->workspace);
@@ -498,14 +497,14 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
   }
   dim3 grid((a->Nq + ATT_BM - 1) / ATT_BM, a->B * a->H, splits);
   if (HD == 64 && !a->mask_bits) {
-    // 256 queries per CTA, probabilities in tensor memory (attention3.cuh)
-    static bool cfg3 = false;
-    if (!cfg3) {
-      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention3_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_DYN_BYTES));
-      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention3_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_DYN_BYTES));
-      cfg3 = true;
+    // 256 queries per CTA, probabilities and output accumulator in tensor memory (attention5.cuh)
+    static bool cfg5 = false;
+    if (!cfg5) {
+      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention5_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_DYN_BYTES));
+      PST3R_CHECK_CUDA(cudaFuncSetAttribute(attention5_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_DYN_BYTES));
+      cfg5 = true;
     }
-    dim3 grid2((a->Nq + 255) / 256, a->B * a->H, splits);
+    const dim3 grid2((a->Nq + 255) / 256, a->B * a->H, splits);
     static const char* trace_path = getenv("PST3R_ATT_TRACE");
     if (trace_path && a->Nk >= 4096) {
       // development aid: one traced launch, synchronous, timeline of CTA (0,0,0) written as text (tools/attn_trace.py reads it)
@@ -514,8 +513,7 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
       PST3R_CHECK_CUDA(cudaMalloc(&dtr, TR_N * sizeof(long long)));
       PST3R_CHECK_CUDA(cudaMemsetAsync(dtr, 0, TR_N * sizeof(long long), stream));
       p.trace = dtr;
-      if (const char* m = getenv("PST3R_ATT_TRACE_MODE")) p.trace_mode = atoi(m);
-      PST3R_CHECK_CUDA(launch_pdl(attention3_fwd_kernel<true>, grid2, dim3(AT3_THREADS), AT3_DYN_BYTES, stream, tmQ, tmK, tmV, p));
+      PST3R_CHECK_CUDA(launch_pdl(attention5_fwd_kernel<true>, grid2, dim3(AT5_THREADS), AT5_DYN_BYTES, stream, tmQ, tmK, tmV, p));
       PST3R_CHECK_CUDA(cudaStreamSynchronize(stream));
       std::vector<long long> h(TR_N);
       PST3R_CHECK_CUDA(cudaMemcpy(h.data(), dtr, TR_N * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -529,7 +527,7 @@ static int launch_attention(const pst3r_attn_args* a, int splits, cudaStream_t s
       }
       p.trace = nullptr;
     } else {
-      PST3R_CHECK_CUDA(launch_pdl(attention3_fwd_kernel<false>, grid2, dim3(AT3_THREADS), AT3_DYN_BYTES, stream, tmQ, tmK, tmV, p));
+      PST3R_CHECK_CUDA(launch_pdl(attention5_fwd_kernel<false>, grid2, dim3(AT5_THREADS), AT5_DYN_BYTES, stream, tmQ, tmK, tmV, p));
     }
   } else if (a->mask_bits) {
     auto kern = attention_fwd_kernel<HD, true>;

@@ -52,6 +52,7 @@ PY
              ncu -i gpurun_out/r02_key_kernels.ncu-rep --page raw --csv > gpurun_out/r02_key_kernels_raw.csv 2>/dev/null; echo "ncufull rc=$?" ;;
     attnb) timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.log 2>&1; [ -d _r1 ] && (cd _r1 && timeout 300 python ../tools/attn_bench.py) > gpurun_out/attn_bench_r1.log 2>&1 ;;
     attntr) timeout 300 python tools/attn_trace.py gpurun_out/attn_trace.md > gpurun_out/attn_trace.log 2>&1; echo "attntr rc=$?" ;;
+    attnt) timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attention" --timeout 300 > gpurun_out/pytest_attn.log 2>&1; echo "attn tests rc=$?"; tail -5 gpurun_out/pytest_attn.log ;;
     mmarate) timeout 120 tools/_bin/mma_rate > gpurun_out/mma_rate.md 2>&1; echo "mmarate rc=$?" ;;
     *) echo "unknown step $s" ;;
   esac

@@ -170,6 +170,106 @@ __global__ void __launch_bounds__(128, 1) mma_two_issuers_kernel(Result* res, in
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tm, 512); }
 }
 
+// Softmax-sweep instruction mixes on register data: which pipe bounds the exp sweep?  `warps_per_smsp` warps per SM sub-partition
+// each run `iters` x 32 elements of: 0 = MUFU.EX2 only; 1 = FFMA2 + EX2; 2 = FFMA2 + EX2 + FADD2 (row sum);
+// 3 = the full sweep (+ F2FP bf16x2 pack); 4 = full sweep with a PRMT (truncating) pack instead of F2FP; 5 = F2FP only.
+template <int mix>
+__global__ void __launch_bounds__(512, 1) sweep_rate_kernel(long long* out, float* sink, int iters) {
+  float x[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[i] = -0.01f * (float)((threadIdx.x + i) & 63);
+  float2 sA = make_float2(0.f, 0.f), sB = make_float2(0.f, 0.f);
+  uint32_t acc = 0;
+  const float2 c2 = make_float2(0.999f, 0.999f), nm2 = make_float2(-0.001f, -0.001f);
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float2 x01 = make_float2(x[i], x[i + 1]), x23 = make_float2(x[i + 2], x[i + 3]);
+      if (mix >= 1 && mix <= 4) { x01 = __ffma2_rn(x01, c2, nm2); x23 = __ffma2_rn(x23, c2, nm2); }
+      float e0 = x01.x, e1 = x01.y, e2 = x23.x, e3 = x23.y;
+      if (mix != 5) { e0 = ex2_approx(e0); e1 = ex2_approx(e1); e2 = ex2_approx(e2); e3 = ex2_approx(e3); }
+      if (mix >= 2 && mix <= 4) { sA = __fadd2_rn(sA, make_float2(e0, e1)); sB = __fadd2_rn(sB, make_float2(e2, e3)); }
+      if (mix == 3 || mix == 5) { acc ^= pack_bf16x2(e0, e1); acc ^= pack_bf16x2(e2, e3); }
+      if (mix == 4) { acc ^= __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632); acc ^= __byte_perm(__float_as_uint(e2), __float_as_uint(e3), 0x7632); }
+      x[i] = e0 - 1.5f; x[i + 1] = e1 - 1.5f; x[i + 2] = e2 - 1.5f; x[i + 3] = e3 - 1.5f;  // keeps the chain data dependent, 1 FADD each
+    }
+  }
+  const long long t1 = clock64();
+  float r = sA.x + sA.y + sB.x + sB.y + __uint_as_float(acc & 0x3fffffffu);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r += x[i];
+  if (r == 123.456f) sink[0] = r;
+  if (threadIdx.x == 0) out[0] = t1 - t0;
+}
+
+// The exp sweep (full mix, register data) on 2 warps per SM sub-partition WHILE one or two threads keep the tensor core busy with
+// the attention kernel's MMA mix: does tensor-core activity slow the softmax warps down?
+__global__ void __launch_bounds__(384, 1) sweep_with_mma_kernel(long long* out, float* sink, int iters, int n_issuers) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+  volatile int* stop = reinterpret_cast<volatile int*>(bar + 4);
+  for (uint32_t i = threadIdx.x; i < OFF_BAR / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_fence_init(); *stop = 0; }
+  if (threadIdx.x < 32) { tmem_alloc(slot, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *slot;
+  const int w = threadIdx.x >> 5;
+  if (w < 2) {
+    if ((threadIdx.x & 31) == 0 && w < n_issuers) {
+      const uint32_t a_addr = smem_u32(smem + OFF_A), b_addr = smem_u32(smem + OFF_B), v_addr = smem_u32(smem + OFF_V);
+      constexpr uint32_t id128 = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t id64mn = make_idesc_bf16(128, 64, 0, 1);
+      long long n = 0;
+      while (!*stop) {
+        if (w == 0 || n_issuers == 1)
+          for (int k = 0; k < 4; ++k) umma_ss(tm, make_smem_desc_sw128(a_addr + k * 32, 0, 1024), make_smem_desc_sw128(b_addr + k * 32, 0, 1024), id128, 1);
+        if (w == 1 || n_issuers == 1)
+          for (int k = 0; k < 8; ++k) umma_ts(tm + 256, tm + 384 + k * 8, make_smem_desc_sw128(v_addr + k * 2048, 16384, 1024), id64mn, 1);
+        n += 12;
+      }
+      umma_commit(bar + w);
+      mbar_wait(bar + w, 0);
+      out[1 + w] = n;
+    }
+  } else if (w >= 4) {
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = -0.01f * (float)((threadIdx.x + i) & 63);
+    float2 sA = make_float2(0.f, 0.f), sB = make_float2(0.f, 0.f);
+    uint32_t acc = 0;
+    const float2 c2 = make_float2(0.999f, 0.999f), nm2 = make_float2(-0.001f, -0.001f);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float2 x01 = __ffma2_rn(make_float2(x[i], x[i + 1]), c2, nm2), x23 = __ffma2_rn(make_float2(x[i + 2], x[i + 3]), c2, nm2);
+        const float e0 = ex2_approx(x01.x), e1 = ex2_approx(x01.y), e2 = ex2_approx(x23.x), e3 = ex2_approx(x23.y);
+        sA = __fadd2_rn(sA, make_float2(e0, e1)); sB = __fadd2_rn(sB, make_float2(e2, e3));
+        acc ^= pack_bf16x2(e0, e1); acc ^= pack_bf16x2(e2, e3);
+        x[i] = e0 - 1.5f; x[i + 1] = e1 - 1.5f; x[i + 2] = e2 - 1.5f; x[i + 3] = e3 - 1.5f;
+      }
+    }
+    const long long t1 = clock64();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float r = sA.x + sA.y + sB.x + sB.y + __uint_as_float(acc & 0x3fffffffu);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r += x[i];
+    if (r == 123.456f) sink[0] = r;
+    if (threadIdx.x == 128) { out[0] = t1 - t0; *stop = 1; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tm, 512); }
+}
+
 int main() {
   const char* names[NCASE] = {
       "SS  N=256 K-major B, one accumulator",
@@ -226,5 +326,43 @@ int main() {
       for (int w = 0; w < ni; ++w) rate += 1000.0 * h[w].n / h[w].total;
       printf("| %d | %s | %.1f | %.1f |\n", ni, ts ? "TS N=64 MN-major B" : "SS N=128", (double)h[0].total / h[0].n, rate);
     }
+  {
+    long long* dt; float* sink;
+    cudaMalloc(&dt, 8); cudaMalloc(&sink, 4);
+    const char* mixes[6] = {"MUFU.EX2 only (+ 1 FADD per element to keep the data flowing)", "FFMA2 + EX2", "FFMA2 + EX2 + FADD2 row sums",
+                            "full sweep: FFMA2 + EX2 + FADD2 + F2FP bf16x2 pack", "full sweep with PRMT (truncating) pack", "F2FP pack only, no EX2"};
+    printf("\n| sweep mix | warps per SM sub-partition | clk per 32 elements per warp | clk per element-row of a sub-partition (x warps) |\n|---|---|---|---|\n");
+    for (int mix = 0; mix < 6; ++mix)
+      for (int wps = 1; wps <= 4; wps *= 2) {
+        const int iters = 64;
+        switch (mix) {
+          case 0: sweep_rate_kernel<0><<<1, 128 * wps>>>(dt, sink, iters); break;
+          case 1: sweep_rate_kernel<1><<<1, 128 * wps>>>(dt, sink, iters); break;
+          case 2: sweep_rate_kernel<2><<<1, 128 * wps>>>(dt, sink, iters); break;
+          case 3: sweep_rate_kernel<3><<<1, 128 * wps>>>(dt, sink, iters); break;
+          case 4: sweep_rate_kernel<4><<<1, 128 * wps>>>(dt, sink, iters); break;
+          default: sweep_rate_kernel<5><<<1, 128 * wps>>>(dt, sink, iters); break;
+        }
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+        long long c; cudaMemcpy(&c, dt, 8, cudaMemcpyDeviceToHost);
+        printf("| %s | %d | %.0f | %.1f per MUFU-or-pack group of 32 lanes |\n", mixes[mix], wps, (double)c / iters, (double)c / iters / 32.0 / wps);
+      }
+  }
+  {
+    long long* dt; float* sink;
+    cudaMalloc(&dt, 64); cudaMalloc(&sink, 4);
+    cudaFuncSetAttribute(sweep_with_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    printf("\n| MMA-issuing threads running next to the sweep | clk per 32 elements per warp (2 sweeping warps per sub-partition) | MMAs issued meanwhile |\n|---|---|---|\n");
+    for (int ni = 0; ni <= 2; ++ni) {
+      const int iters = 256;
+      cudaMemset(dt, 0, 64);
+      sweep_with_mma_kernel<<<1, 384, SMEM_BYTES>>>(dt, sink, iters, ni);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+      long long c[3]; cudaMemcpy(c, dt, 24, cudaMemcpyDeviceToHost);
+      printf("| %d | %.0f | %lld |\n", ni, (double)c[0] / iters, c[1] + c[2]);
+    }
+  }
   return 0;
 }
