@@ -8,11 +8,10 @@ pytestmark = pytest.mark.gpu
 
 TOL_F32 = 1e-3
 TOL_BF16 = 4e-3
-# attention: bf16 output (half an ulp is up to 2^-9 of the value) plus bf16 probabilities.  The hd-64 kernel raises its reference
-# maximum lazily (csrc/attention5.cuh), so the largest probability of a row is 2^x, x in [0, 8], rounded to bf16 like all others
-# (with the exact running maximum it is exactly 1): a row dominated by one key carries that key's 2^-9 rounding on top of the
-# output rounding.  Observed maxima on these tests: 3.1e-3 .. 5.5e-3 (exact-maximum kernel of round 1: 2.2e-3 .. 3.9e-3).
-TOL_ATTN = 6e-3
+# attention: bf16 output (half an ulp is up to 2^-9 of the value) plus bf16 probabilities; observed maxima 2.7e-3 .. 3.6e-3 on these
+# tests (the hd-64 kernel sums the probabilities as rounded, csrc/attention5.cuh; with unrounded row sums under its lazily raised
+# reference maximum the same tests reached 6.6e-3)
+TOL_ATTN = 5e-3
 
 
 def rnd(*shape, scale=1.0, dtype=torch.bfloat16):
