@@ -44,7 +44,12 @@ class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, None
+
+    def mark(self):
+        """The timed region starts now (the sampler is started a little earlier, during the last warm-up replays of the same
+        step, because nvidia-smi needs a few hundred ms to deliver its first line)."""
+        self.t_mark = time.monotonic()
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -59,7 +64,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -71,7 +76,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        timed = [r for t, r in self.rows if self.t_mark is None or t >= self.t_mark]
+        window = "timed region"
+        if not timed:  # region shorter than the sampling latency: the warm-up replays of the same step just before it
+            timed, window = [r for _, r in self.rows], "last warm-up replays + timed region"
+        for r in timed:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -81,7 +90,8 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def make_inputs(V, device, pinned=False):
@@ -266,14 +276,16 @@ def run_ours(args):
             return gout
         return step_device()
 
-    for _ in range(2):
-        run_step()
-    barrier()
-
-    # ---- timed region: `value` (inputs resident in HBM) ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(2 if world == 1 else 12):  # same step, untimed (a fixed count: the sharded step holds collectives);
+        run_step()                             # at N > 1 the steps are short and nvidia-smi needs ~0.3 s for its first line
+    torch.cuda.synchronize()
+    barrier()
+
+    # ---- timed region: `value` (inputs resident in HBM) ----
+    sampler.mark()
     ms_total = _timed(torch, dist, world, dev, run_step, args.steps)
     out = gout if graph is not None else out
     clocks = sampler.stop() if rank == 0 else None
@@ -628,10 +640,12 @@ def weak_scaling_leg(args, torch, dist, world, rank, local, dev, runner):
             runner(imgs, tsw, CLASSES)
         g, _ = _capture(torch, lambda: runner(imgs, tsw, CLASSES)) if args.graph else (None, None)
         fn = (lambda: g.replay()) if g is not None else (lambda: runner(imgs, tsw, CLASSES))
-        fn()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        fn()
+        fn()
+        sampler.mark()
         n = max(3, min(args.steps, 10))
         ms = _timed(torch, dist, world, dev, fn, n)
         clocks = sampler.stop() if rank == 0 else None
