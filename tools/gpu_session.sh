@@ -53,6 +53,7 @@ PY
     attnb) timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.log 2>&1; [ -d _r1 ] && (cd _r1 && timeout 300 python ../tools/attn_bench.py) > gpurun_out/attn_bench_r1.log 2>&1 ;;
     attntr) timeout 300 python tools/attn_trace.py gpurun_out/attn_trace.md > gpurun_out/attn_trace.log 2>&1; echo "attntr rc=$?" ;;
     attnt) timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attention" --timeout 300 > gpurun_out/pytest_attn.log 2>&1; echo "attn tests rc=$?"; tail -5 gpurun_out/pytest_attn.log ;;
+    memattn) timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attention and not 12288" > gpurun_out/sanitizer_memcheck_attention.log 2>&1; echo "memcheck attention rc=$?"; tail -4 gpurun_out/sanitizer_memcheck_attention.log ;;
     mmarate) timeout 120 tools/_bin/mma_rate > gpurun_out/mma_rate.md 2>&1; echo "mmarate rc=$?" ;;
     *) echo "unknown step $s" ;;
   esac
