@@ -684,6 +684,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 }  // namespace pst3r
 
 #include "gemm2.cuh"
+#include "gemm_splitk.cuh"
 
 using namespace pst3r;
 
@@ -829,6 +830,25 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
     r = encode_tmap(&tB2, B, 2, terms ? 3 : 2, dB, sB, bB);
     if (r) return r;
     return launch_gemm2(tA2, tB2, tmOut, ep, M, N, K, stream);
+  }
+
+  // Small all-bf16 problems whose 128 x 64 tiles fill at most half of the machine: split the reduction over a 2-CTA cluster
+  // (gemm_splitk.cuh) — the M = 768 projections and the K = 3072 fc2 of the sequential memory build.
+  {
+    static const bool splitk_on = !(getenv("PST3R_SPLITK") && getenv("PST3R_SPLITK")[0] == '0');
+    const long long tiles64 = (long long)mb * ((N + GSK_BN - 1) / GSK_BN);
+    if (splitk_on && !conv && nb == 1 && !terms && !ep.promote && !ep.tma_store && e->out_kind != PST3R_KIND_SPLIT &&
+        !(e->residual && e->res_kind != PST3R_KIND_BF16) && 2 * tiles64 <= sms && (K + GEMM_BK - 1) / GEMM_BK >= 8) {
+      CUtensorMap tA, tB;
+      uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[2] = {2, (uint64_t)lda * 2};
+      uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[2] = {2, (uint64_t)ldb * 2};
+      uint32_t bA[2] = {GEMM_BK, GEMM_BM}, bB[2] = {GEMM_BK, (uint32_t)GSK_BN};
+      int r = encode_tmap(&tA, A, 2, 2, dA, sA, bA);
+      if (r) return r;
+      r = encode_tmap(&tB, B, 2, 2, dB, sB, bB);
+      if (r) return r;
+      return launch_gemm_splitk(tA, tB, ep, M, N, K, stream);
+    }
   }
 
   CUtensorMap tmA, tmB;

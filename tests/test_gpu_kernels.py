@@ -31,8 +31,11 @@ def ops():
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (300, 200, 96), (1, 8, 8), (1000, 3072, 1024),
-                                   (768, 768, 3072), (200, 768, 768), (12288, 1024, 1024), (130, 72, 2816), (129, 264, 72)])
+                                   (768, 768, 3072), (200, 768, 768), (12288, 1024, 1024), (130, 72, 2816), (129, 264, 72),
+                                   (768, 768, 576), (700, 200, 1000), (768, 768, 768)])
 def test_gemm_shapes(ops, M, N, K):
+    # (768, 768, *), (200, 768, 768), (130, 72, 2816), (700, 200, 1000): at most 74 tiles of 128 x 64 and >= 8 k-blocks -> the
+    # split-K cluster kernel (csrc/gemm_splitk.cuh), incl. an odd k-block count (576 = 9 x 64) and K / N / M tails
     a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
     bias = torch.randn(N, device="cuda")
     ref = a.float() @ w.float().t() + bias

@@ -54,6 +54,10 @@ PY
     attntr) timeout 300 python tools/attn_trace.py gpurun_out/attn_trace.md > gpurun_out/attn_trace.log 2>&1; echo "attntr rc=$?" ;;
     attnt) timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attention" --timeout 300 > gpurun_out/pytest_attn.log 2>&1; echo "attn tests rc=$?"; tail -5 gpurun_out/pytest_attn.log ;;
     memattn) timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attention and not 12288" > gpurun_out/sanitizer_memcheck_attention.log 2>&1; echo "memcheck attention rc=$?"; tail -4 gpurun_out/sanitizer_memcheck_attention.log ;;
+    gemmt) timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "gemm" --timeout 300 > gpurun_out/pytest_gemm.log 2>&1; echo "gemm tests rc=$?"; tail -4 gpurun_out/pytest_gemm.log ;;
+    sk) one() { python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['clocks']['sm_mhz'], d['gpu_launches'])"; }
+        for v in 1 0 1 0; do echo "--- PST3R_SPLITK=$v" >> gpurun_out/sk.log
+          PST3R_SPLITK=$v timeout 300 python bench.py --head-precision bf16 --no-gpu-reference --no-cpu-baseline --no-bf16-head --steps 20 2>/dev/null | one >> gpurun_out/sk.log 2>&1; done ;;
     mmarate) timeout 120 tools/_bin/mma_rate > gpurun_out/mma_rate.md 2>&1; echo "mmarate rc=$?" ;;
     *) echo "unknown step $s" ;;
   esac
