@@ -64,6 +64,13 @@ int pst3r_set_sm_budget(int32_t n_sms);
  * executes griddepcontrol.wait before its first global access) on / off; returns the previous setting.  Off for
  * per-kernel profiling: a dependent kernel that starts early spends the wait inside ITS measured duration. */
 int pst3r_set_pdl(int32_t on);
+/* Split-K for small GEMMs on / off (default off); returns the previous setting.  While on, an all-bf16 pst3r_gemm_bf16 whose
+ * 128 x 64 output tiles fill at most half of the SMs and whose reduction has >= 8 k-blocks runs on two-CTA clusters, each CTA
+ * over half of K, the partial tile reduced through distributed shared memory (csrc/gemm_splitk.cuh).  The fp32 summation order
+ * differs from the unsplit kernel's, so results are equal to rounding, not bitwise; the decision depends on M.  The host side
+ * switches it on around the sequential memory build (engine/must3r.py:40-54: a chain of M = 768 nn.Linear calls), whose
+ * shapes are the same on every rank, and leaves the per-view stages on the unsplit kernels (bit-identical sharded runs). */
+int pst3r_set_split_k(int32_t on);
 
 /* ---- GEMM: C[M,N] = epilogue(A[M,K] * B[N,K]^T) ---------------------------------------------
  * A, B are bf16, K contiguous (row strides lda/ldb in elements, multiples of 8).  tcgen05 tensor cores,

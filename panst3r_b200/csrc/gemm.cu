@@ -835,7 +835,8 @@ static int gemm_run(const void* A, int64_t lda, const void* B, int64_t ldb, int3
   // Small all-bf16 problems whose 128 x 64 tiles fill at most half of the machine: split the reduction over a 2-CTA cluster
   // (gemm_splitk.cuh) — the M = 768 projections and the K = 3072 fc2 of the sequential memory build.
   {
-    static const bool splitk_on = !(getenv("PST3R_SPLITK") && getenv("PST3R_SPLITK")[0] == '0');
+    static const bool splitk_env = !(getenv("PST3R_SPLITK") && getenv("PST3R_SPLITK")[0] == '0');  // A/B measurements
+    const bool splitk_on = splitk_env && split_k_enabled();
     const long long tiles64 = (long long)mb * ((N + GSK_BN - 1) / GSK_BN);
     if (splitk_on && !conv && nb == 1 && !terms && !ep.promote && !ep.tma_store && e->out_kind != PST3R_KIND_SPLIT &&
         !(e->residual && e->res_kind != PST3R_KIND_BF16) && 2 * tiles64 <= sms && (K + GEMM_BK - 1) / GEMM_BK >= 8) {

@@ -97,6 +97,14 @@ int set_pdl(int on) {
   return prev;
 }
 
+static int g_split_k = 0;
+bool split_k_enabled() { return g_split_k == 1; }
+int set_split_k(int on) {
+  const int prev = g_split_k;
+  g_split_k = on ? 1 : 0;
+  return prev;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -125,3 +133,4 @@ extern "C" int pst3r_set_sm_budget(int32_t n) {
 }
 extern "C" int pst3r_num_sms(void) { return pst3r::num_sms(); }
 extern "C" int pst3r_set_pdl(int32_t on) { return pst3r::set_pdl(on); }
+extern "C" int pst3r_set_split_k(int32_t on) { return pst3r::set_split_k(on); }

@@ -62,6 +62,8 @@ void set_sm_budget(int n);
 // PST3R_PDL=0 in the environment disables the attribute (plain stream order).
 bool pdl_enabled();
 int set_pdl(int on);  // returns the previous setting
+bool split_k_enabled();
+int set_split_k(int on);  // returns the previous setting
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

@@ -79,6 +79,7 @@ SIGNATURES = {
     "pst3r_num_sms": (C.c_int, []),
     "pst3r_set_sm_budget": (C.c_int, [_i32]),
     "pst3r_set_pdl": (C.c_int, [_i32]),
+    "pst3r_set_split_k": (C.c_int, [_i32]),
     "pst3r_gemm_bf16_batched": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, C.POINTER(GemmEpilogue),
                                           _i64, _i64, _p]),
     "pst3r_layernorm_batched": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _i64, _f, _p, _i64, _i64, _i32, _i32, _i32, _p]),

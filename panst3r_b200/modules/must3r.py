@@ -306,6 +306,10 @@ class MUSt3R(nn.Module):
         else:
             layer_in = []
             mask_bits = self._own_view_mask(n, N, n_mem, dev) if n > 1 else None
+            # The memory update is a sequential chain of small (n * N rows) projections: split their reductions over two-CTA
+            # clusters (csrc/gemm_splitk.cuh).  Only here: the chain's shapes are the same on every rank of a sharded run,
+            # while the per-view stages stay on the unsplit kernels, whose results do not depend on how many views a rank holds.
+            prev_split_k = ops.set_split_k(True)
             for l, blk in enumerate(self.blocks_dec):
                 layer_in.append(cur)
                 nxt = self_attention(cur, blk, B * n, N, rope, in_place=False, stats=sa, stats_out=sb)
@@ -329,6 +333,7 @@ class MUSt3R(nn.Module):
             # feedback + memory write: stored_l = norm_y_l(layer_in_l + feedback(x_L)); K|V projected once, here
             fb = ops.gemm(cur, w16(self.feedback_layer.fc1.weight), bias=bias_of(self.feedback_layer.fc1), act=ops.ACT_GELU)
             fb = ops.gemm(fb, w16(self.feedback_layer.fc2.weight), bias=bias_of(self.feedback_layer.fc2))
+            ops.set_split_k(prev_split_k)
             if bank is None:
                 cap = max(self.reserve_views, mem_nimgs + n) * N
                 bank = MemoryBank(B, L, D, dev, cap)

@@ -344,6 +344,11 @@ def set_pdl(on: bool) -> bool:
     return bool(_l.load().pst3r_set_pdl(int(bool(on))))
 
 
+def set_split_k(on: bool) -> bool:
+    """Split-K cluster kernel for small all-bf16 GEMMs on / off for the following launches; returns the previous setting."""
+    return bool(_l.load().pst3r_set_split_k(int(bool(on))))
+
+
 def num_sms() -> int:
     return _l.load().pst3r_num_sms()
 

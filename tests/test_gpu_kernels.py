@@ -34,13 +34,38 @@ def ops():
                                    (768, 768, 3072), (200, 768, 768), (12288, 1024, 1024), (130, 72, 2816), (129, 264, 72),
                                    (768, 768, 576), (700, 200, 1000), (768, 768, 768)])
 def test_gemm_shapes(ops, M, N, K):
-    # (768, 768, *), (200, 768, 768), (130, 72, 2816), (700, 200, 1000): at most 74 tiles of 128 x 64 and >= 8 k-blocks -> the
-    # split-K cluster kernel (csrc/gemm_splitk.cuh), incl. an odd k-block count (576 = 9 x 64) and K / N / M tails
     a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
     bias = torch.randn(N, device="cuda")
     ref = a.float() @ w.float().t() + bias
     assert relmax(ops.gemm(a, w, bias=bias, out_dtype=torch.float32), ref) < TOL_F32
     assert relmax(ops.gemm(a, w, bias=bias), ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("M,N,K", [(768, 768, 3072), (768, 768, 768), (200, 768, 768), (130, 72, 2816), (768, 768, 576),
+                                   (700, 200, 1000), (512, 1024, 512)])
+def test_gemm_split_k(ops, M, N, K):
+    """Split-K cluster kernel (csrc/gemm_splitk.cuh, pst3r_set_split_k): at most 74 tiles of 128 x 64 and >= 8 k-blocks, incl. an odd
+    k-block count (576 = 9 x 64) and K / N / M tails; every fused epilogue the memory build uses; equal to the unsplit kernel up to
+    the fp32 summation order."""
+    a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    bias, ls, res = torch.randn(N, device="cuda"), torch.randn(N, device="cuda"), rnd(M, N)
+    y = a.float() @ w.float().t() + bias
+    unsplit = ops.gemm(a, w, bias=bias, out_dtype=torch.float32)
+    prev = ops.set_split_k(True)
+    try:
+        assert prev is False
+        got = ops.gemm(a, w, bias=bias, out_dtype=torch.float32)
+        assert relmax(got, y) < TOL_F32 and relmax(got, unsplit) < 1e-4
+        assert relmax(ops.gemm(a, w, bias=bias), y) < TOL_BF16
+        assert relmax(ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, out_dtype=torch.float32), torch.nn.functional.gelu(y)) < TOL_F32
+        assert relmax(ops.gemm(a, w, bias=bias, col_scale=ls, residual=res, out_dtype=torch.float32), y * ls + res.float()) < TOL_F32
+        x = rnd(M, N)
+        ref = y + x.float()
+        ops.gemm(a, w, bias=bias, residual=x, out=x)   # in-place residual stream update
+        assert relmax(x, ref) < TOL_BF16
+    finally:
+        assert ops.set_split_k(prev) is True
+    assert torch.equal(ops.gemm(a, w, bias=bias, out_dtype=torch.float32), unsplit)  # off again: the unsplit kernel, bitwise
 
 
 def test_gemm_epilogues(ops):
