@@ -13,7 +13,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # launch order of tools/profile_step.py kernels -> key used by bench.py
 ORDER = ["attention3_render", "attention3_encoder_self", "gemm2_fc1_gelu", "gemm_membuild_qkv", "gemm_mask_logits_tma",
-         "layernorm_12288x1024", "gemm2_split_fc2_promote", "gemm_mask_logits_split_tma"]
+         "layernorm_12288x1024", "gemm2_split_fc2_promote", "gemm_mask_logits_split_tma", "gemm_membuild_fc2_splitk",
+         "gemm_membuild_fc2_unsplit"]
 
 
 def num(x):

@@ -50,6 +50,7 @@ def main():
         ah, wh = ops.Split.from_float(torch.randn(V * 768, 11264, device="cuda")), ops.Split.from_float(torch.randn(2048, 11264, device="cuda") * 0.01)
         oh = ops.Split.empty((V * 4 * 768, 512), "cuda")
         fs, es = ops.Split.from_float(feats.float()), ops.Split.from_float(emb.float())
+        a3, w3, res3 = r(768, 3072), r(768, 3072), r(768, 768)                         # memory-build fc2: split-K cluster kernel / unsplit
 
         def run():
             ops.attention(q, k, v)
@@ -60,6 +61,10 @@ def main():
             ops.layernorm(x, gam, bet, 1e-6)
             ops.gemm(ah, wh, out=oh, store_mode=ops.STORE_PIXSHUF2, grid=(24 * V, 32))
             ops.gemm(fs, es, out=mo, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=192 * 256, batch_stride=200 * 192 * 256, ldt=192 * 256)
+            prev = ops.set_split_k(True)
+            ops.gemm(a3, w3, residual=res3)
+            ops.set_split_k(prev)
+            ops.gemm(a3, w3, residual=res3)
         for _ in range(2):
             run()
         torch.cuda.synchronize()
