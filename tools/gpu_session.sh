@@ -58,6 +58,7 @@ PY
     sk) one() { python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['clocks']['sm_mhz'], d['gpu_launches'])"; }
         for v in 1 0 1 0; do echo "--- PST3R_SPLITK=$v" >> gpurun_out/sk.log
           PST3R_SPLITK=$v timeout 300 python bench.py --head-precision bf16 --no-gpu-reference --no-cpu-baseline --no-bf16-head --steps 20 2>/dev/null | one >> gpurun_out/sk.log 2>&1; done ;;
+    stages) timeout 600 python tools/stage_times.py 16 v1 0 > gpurun_out/stages_r02_v1.json 2> gpurun_out/stages_r02.err; echo "stages rc=$?" ;;
     mmarate) timeout 120 tools/_bin/mma_rate > gpurun_out/mma_rate.md 2>&1; echo "mmarate rc=$?" ;;
     *) echo "unknown step $s" ;;
   esac
