@@ -7,6 +7,7 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_bin/mma_rate tools/mma_rate.cu -lcuda && tools/_bin/mma_rate
 #include <string>
+#include <cuda_fp16.h>
 
 #include "../panst3r_b200/csrc/common.cuh"
 
@@ -187,8 +188,26 @@ __global__ void __launch_bounds__(512, 1) sweep_rate_kernel(long long* out, floa
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       float2 x01 = make_float2(x[i], x[i + 1]), x23 = make_float2(x[i + 2], x[i + 3]);
-      if (mix >= 1 && mix <= 4) { x01 = __ffma2_rn(x01, c2, nm2); x23 = __ffma2_rn(x23, c2, nm2); }
+      if ((mix >= 1 && mix <= 4) || mix >= 6) { x01 = __ffma2_rn(x01, c2, nm2); x23 = __ffma2_rn(x23, c2, nm2); }
       float e0 = x01.x, e1 = x01.y, e2 = x23.x, e3 = x23.y;
+      if (mix == 6 || mix == 7) {
+        // packed half-precision exponentials: one MUFU instruction per PAIR
+        uint32_t p01, p23;
+        if (mix == 6) {
+          asm("{ .reg .b32 t; cvt.rn.f16x2.f32 t, %2, %1; ex2.approx.f16x2 %0, t; }" : "=r"(p01) : "f"(e0), "f"(e1));
+          asm("{ .reg .b32 t; cvt.rn.f16x2.f32 t, %2, %1; ex2.approx.f16x2 %0, t; }" : "=r"(p23) : "f"(e2), "f"(e3));
+          acc ^= p01 ^ p23;
+          e0 = __half2float(__ushort_as_half((unsigned short)(p01 & 0xffff))); e1 = __half2float(__ushort_as_half((unsigned short)(p01 >> 16)));
+          e2 = __half2float(__ushort_as_half((unsigned short)(p23 & 0xffff))); e3 = __half2float(__ushort_as_half((unsigned short)(p23 >> 16)));
+        } else {
+          asm("{ .reg .b32 t; cvt.rn.bf16x2.f32 t, %2, %1; ex2.approx.ftz.bf16x2 %0, t; }" : "=r"(p01) : "f"(e0), "f"(e1));
+          asm("{ .reg .b32 t; cvt.rn.bf16x2.f32 t, %2, %1; ex2.approx.ftz.bf16x2 %0, t; }" : "=r"(p23) : "f"(e2), "f"(e3));
+          acc ^= p01 ^ p23;
+          e0 = __uint_as_float(p01 << 16); e1 = __uint_as_float(p01 & 0xffff0000u);
+          e2 = __uint_as_float(p23 << 16); e3 = __uint_as_float(p23 & 0xffff0000u);
+        }
+        sA = __fadd2_rn(sA, make_float2(e0, e1)); sB = __fadd2_rn(sB, make_float2(e2, e3));
+      } else
       if (mix != 5) { e0 = ex2_approx(e0); e1 = ex2_approx(e1); e2 = ex2_approx(e2); e3 = ex2_approx(e3); }
       if (mix >= 2 && mix <= 4) { sA = __fadd2_rn(sA, make_float2(e0, e1)); sB = __fadd2_rn(sB, make_float2(e2, e3)); }
       if (mix == 3 || mix == 5) { acc ^= pack_bf16x2(e0, e1); acc ^= pack_bf16x2(e2, e3); }
@@ -329,10 +348,12 @@ int main() {
   {
     long long* dt; float* sink;
     cudaMalloc(&dt, 8); cudaMalloc(&sink, 4);
-    const char* mixes[6] = {"MUFU.EX2 only (+ 1 FADD per element to keep the data flowing)", "FFMA2 + EX2", "FFMA2 + EX2 + FADD2 row sums",
-                            "full sweep: FFMA2 + EX2 + FADD2 + F2FP bf16x2 pack", "full sweep with PRMT (truncating) pack", "F2FP pack only, no EX2"};
+    const char* mixes[8] = {"MUFU.EX2 only (+ 1 FADD per element to keep the data flowing)", "FFMA2 + EX2", "FFMA2 + EX2 + FADD2 row sums",
+                            "full sweep: FFMA2 + EX2 + FADD2 + F2FP bf16x2 pack", "full sweep with PRMT (truncating) pack", "F2FP pack only, no EX2",
+                            "FFMA2 + cvt.f16x2 + ex2.approx.ftz.f16x2 (one MUFU per pair) + unpack + FADD2 row sums of the rounded values",
+                            "FFMA2 + cvt.bf16x2 + ex2.approx.ftz.bf16x2 (one MUFU per pair) + unpack + FADD2 row sums of the rounded values"};
     printf("\n| sweep mix | warps per SM sub-partition | clk per 32 elements per warp | clk per element-row of a sub-partition (x warps) |\n|---|---|---|---|\n");
-    for (int mix = 0; mix < 6; ++mix)
+    for (int mix = 0; mix < 8; ++mix)
       for (int wps = 1; wps <= 4; wps *= 2) {
         const int iters = 64;
         switch (mix) {
@@ -341,7 +362,9 @@ int main() {
           case 2: sweep_rate_kernel<2><<<1, 128 * wps>>>(dt, sink, iters); break;
           case 3: sweep_rate_kernel<3><<<1, 128 * wps>>>(dt, sink, iters); break;
           case 4: sweep_rate_kernel<4><<<1, 128 * wps>>>(dt, sink, iters); break;
-          default: sweep_rate_kernel<5><<<1, 128 * wps>>>(dt, sink, iters); break;
+          case 5: sweep_rate_kernel<5><<<1, 128 * wps>>>(dt, sink, iters); break;
+          case 6: sweep_rate_kernel<6><<<1, 128 * wps>>>(dt, sink, iters); break;
+          default: sweep_rate_kernel<7><<<1, 128 * wps>>>(dt, sink, iters); break;
         }
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
