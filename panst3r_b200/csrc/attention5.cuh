@@ -66,9 +66,9 @@ __device__ __forceinline__ void at5_sweep16(const uint32_t (&sc)[16], int base, 
       // The row sum adds the probabilities AS ROUNDED to bf16 (what the P V product sees): numerator and denominator of O / l
       // carry the same rounding.  Under the lazy maximum the largest probability of a row is 2^x, x in [0, 8], not exactly 1: with
       // row sums of the unrounded values a row dominated by one key showed that key's 2^-9 rounding (errors up to 6.6e-3 of the
-      // largest output instead of 3.6e-3; costs 2 integer instructions per pair, 636 -> 692 us on the render cross-attention).
-      sA = __fadd2_rn(sA, make_float2(__uint_as_float(pa << 16), __uint_as_float(pa & 0xffff0000u)));
-      sB = __fadd2_rn(sB, make_float2(__uint_as_float(pb << 16), __uint_as_float(pb & 0xffff0000u)));
+      // largest output instead of 3.6e-3).  The halves of the packed register go straight into the fp32 sums (FHADD.BF16).
+      acc_bf16x2(pa, sA.x, sA.y);
+      acc_bf16x2(pb, sB.x, sB.y);
       pk[i >> 1] = pa;
       pk[(i >> 1) + 1] = pb;
     }
@@ -78,7 +78,7 @@ __device__ __forceinline__ void at5_sweep16(const uint32_t (&sc)[16], int base, 
       const float e0 = (base + i < kv) ? ex2_approx(fmaf(__uint_as_float(sc[i]), c, neg_m)) : 0.0f;
       const float e1 = (base + i + 1 < kv) ? ex2_approx(fmaf(__uint_as_float(sc[i + 1]), c, neg_m)) : 0.0f;
       const uint32_t pa = pack_bf16x2(e0, e1);
-      sA.x += __uint_as_float(pa << 16); sA.y += __uint_as_float(pa & 0xffff0000u);
+      acc_bf16x2(pa, sA.x, sA.y);
       pk[i >> 1] = pa;
     }
   }

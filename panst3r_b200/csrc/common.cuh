@@ -300,6 +300,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// a += float(low bf16 of p), b += float(high bf16 of p): the mixed-precision add of sm_100 (one FHADD.BF16 per half, reading
+// the packed register directly; no unpack instructions)
+__device__ __forceinline__ void acc_bf16x2(uint32_t p, float& a, float& b) {
+  asm("{\n"
+      ".reg .b16 lo, hi;\n"
+      "mov.b32 {lo, hi}, %2;\n"
+      "add.rn.f32.bf16 %0, lo, %0;\n"
+      "add.rn.f32.bf16 %1, hi, %1;\n"
+      "}\n"
+      : "+f"(a), "+f"(b)
+      : "r"(p));
+}
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
