@@ -1,5 +1,5 @@
 // tcgen05 flash attention for head_dim 64 without a block mask: 256 queries per CTA as two 128-row sub-tiles whose exp sweeps
-// alternate on the MUFU, probabilities AND the output accumulator in TENSOR MEMORY, scores read once.
+// alternate on the MUFU, probabilities AND the output accumulator in TENSOR MEMORY.
 //
 //   S_t = Q_t K_j^T       SS MMA (Q, K from swizzled smem)                    -> TMEM columns [t*128, +128)   fp32
 //   P_t = 2^((S_t - m) c) softmax warps: tcgen05.ld -> ex2 -> bf16x2 -> tcgen05.st -> TMEM [384 + t*64, +64)
@@ -17,15 +17,18 @@
 //     (16 columns each) fly during the exchange / hand-over waits and behind the exponentials of earlier chunks.  (Holding all
 //     64 scores of a thread across both passes does not fit the 96 registers a 640-thread CTA leaves: measured, it spills and
 //     runs at 900 instead of 700 us.)
-//   * the S buffer is handed back (s_free) as soon as the sweep's last load has landed, so S_t(j+1) is computed under the last
-//     chunk of sweep j and the other sub-tile's sweep, and the softmax warps hardly wait for the tensor core's S;
+//   * the S buffer is handed back (s_free) as soon as the sweep's last load has landed (after its second chunk), so S_t(j+1) is
+//     computed under the second half of sweep j and the other sub-tile's sweep, and the softmax warps hardly wait for S;
+//   * the row sums add the probabilities AS ROUNDED to bf16, one mixed-precision add (FHADD.BF16) per element reading the packed
+//     register that goes to tensor memory (12 instructions per four scores: 2 FFMA2, 4 MUFU, 2 F2FP, 4 FHADD);
 //   * O is never read per tile.  The reference maximum m is raised lazily: only when a tile's maximum exceeds it by more than 2^8
 //     are the row sums and the O rows rescaled in place (tcgen05.ld / st behind the P V of the previous tile); P <= 256 in bf16;
 //   * the two sub-tiles' sweeps alternate strictly (a sub-tile starts its exponentials when the other has handed its P over):
 //     left alone they fall into phase, sweep together at half the MUFU rate each and then wait together;
 //   * barrier arrivals are one elected lane per warp (8 per hand-over instead of 256 serialised shared-memory atomics).
-// CTA: 640 threads = TMA warp, two MMA-issuing warps (scores / P V), 1 idle warp, 8 + 8 softmax warps: two threads per score row (one per 64-key half of
-// the tile and 32 output columns; half-row maxima exchanged through shared memory and a 64-thread named barrier).
+// CTA: 640 threads = TMA warp, two MMA-issuing warps (scores / P V), 1 idle warp, 8 + 8 softmax warps: two threads per score
+// row (one per 64-key half of the tile and 32 output columns; half-row maxima exchanged through shared memory and a 64-thread
+// named barrier).  Measured: render cross-attention (B16 H12 Nq768 Nk12288) 642 us = 722 TFLOP/s (round-1 kernel: 719 us).
 #pragma once
 
 namespace pst3r {
