@@ -310,30 +310,32 @@ class MUSt3R(nn.Module):
             # clusters (csrc/gemm_splitk.cuh).  Only here: the chain's shapes are the same on every rank of a sharded run,
             # while the per-view stages stay on the unsplit kernels, whose results do not depend on how many views a rank holds.
             prev_split_k = ops.set_split_k(True)
-            for l, blk in enumerate(self.blocks_dec):
-                layer_in.append(cur)
-                nxt = self_attention(cur, blk, B * n, N, rope, in_place=False, stats=sa, stats_out=sb)
-                if n == 1:
-                    if n_mem == 0:
-                        raise ops._l.Pst3rError("a single first view has nothing to attend to (init needs >= 2 views)")
-                    kvs = stored_kv(l)
-                else:
-                    fresh = ops.layernorm(cur, f32(blk.norm_y.weight), f32(blk.norm_y.bias), 1e-6)
-                    kvf = ops.gemm(fresh, blk.kv_weight(), bias=blk.kv_bias()).view(B, n * N, 2 * D)
-                    kvs = []
-                    old = stored_kv(l) if n_mem > 0 else None
-                    for b in range(B):
-                        kvs.append(kvf[b:b + 1] if old is None else torch.cat([old[b], kvf[b:b + 1]], dim=1))
-                nxt = self._cross_attention(nxt, blk, B, n, N, kvs, mask_bits, stats=sb, stats_out=sc)
-                cur = mlp_residual(nxt, blk.norm3, blk.mlp, 1e-6,
-                                   out=stack[l + 1] if l < L - 1 else (feats_out if feats_out is not None else None),
-                                   stats=sc, stats_out=sa)
-                if keep_all:
-                    feats.append(cur.view(B, n, N, D) if cur.is_contiguous() else cur.unflatten(0, (B, n, N)))
-            # feedback + memory write: stored_l = norm_y_l(layer_in_l + feedback(x_L)); K|V projected once, here
-            fb = ops.gemm(cur, w16(self.feedback_layer.fc1.weight), bias=bias_of(self.feedback_layer.fc1), act=ops.ACT_GELU)
-            fb = ops.gemm(fb, w16(self.feedback_layer.fc2.weight), bias=bias_of(self.feedback_layer.fc2))
-            ops.set_split_k(prev_split_k)
+            try:
+                for l, blk in enumerate(self.blocks_dec):
+                    layer_in.append(cur)
+                    nxt = self_attention(cur, blk, B * n, N, rope, in_place=False, stats=sa, stats_out=sb)
+                    if n == 1:
+                        if n_mem == 0:
+                            raise ops._l.Pst3rError("a single first view has nothing to attend to (init needs >= 2 views)")
+                        kvs = stored_kv(l)
+                    else:
+                        fresh = ops.layernorm(cur, f32(blk.norm_y.weight), f32(blk.norm_y.bias), 1e-6)
+                        kvf = ops.gemm(fresh, blk.kv_weight(), bias=blk.kv_bias()).view(B, n * N, 2 * D)
+                        kvs = []
+                        old = stored_kv(l) if n_mem > 0 else None
+                        for b in range(B):
+                            kvs.append(kvf[b:b + 1] if old is None else torch.cat([old[b], kvf[b:b + 1]], dim=1))
+                    nxt = self._cross_attention(nxt, blk, B, n, N, kvs, mask_bits, stats=sb, stats_out=sc)
+                    cur = mlp_residual(nxt, blk.norm3, blk.mlp, 1e-6,
+                                       out=stack[l + 1] if l < L - 1 else (feats_out if feats_out is not None else None),
+                                       stats=sc, stats_out=sa)
+                    if keep_all:
+                        feats.append(cur.view(B, n, N, D) if cur.is_contiguous() else cur.unflatten(0, (B, n, N)))
+                # feedback + memory write: stored_l = norm_y_l(layer_in_l + feedback(x_L)); K|V projected once, here
+                fb = ops.gemm(cur, w16(self.feedback_layer.fc1.weight), bias=bias_of(self.feedback_layer.fc1), act=ops.ACT_GELU)
+                fb = ops.gemm(fb, w16(self.feedback_layer.fc2.weight), bias=bias_of(self.feedback_layer.fc2))
+            finally:
+                ops.set_split_k(prev_split_k)
             if bank is None:
                 cap = max(self.reserve_views, mem_nimgs + n) * N
                 bank = MemoryBank(B, L, D, dev, cap)
