@@ -38,7 +38,8 @@ const char* pst3r_last_error(void);
 /* ABI version of this header: bumped whenever a struct layout or an entry-point signature changes
  * (2: pst3r_gemm_epilogue grew the folded-LayerNorm fields; batched GEMM / LayerNorm, SM budget, post-processing;
  *  3: reference-precision "split bf16" operands (PST3R_KIND_SPLIT) through the GEMM and the row kernels, masked row
- *     softmax, TMA-store mask-logit planes). */
+ *     softmax, TMA-store mask-logit planes).  Entry points ADDED without touching existing ones keep the version
+ *     (pst3r_set_split_k); a library that lacks one fails at bind time, symbol by symbol (panst3r_b200/lib.py). */
 #define PST3R_ABI_VERSION 3
 
 /* Element kinds of a matrix argument.  PST3R_KIND_SPLIT is the reference-precision representation used for the

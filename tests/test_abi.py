@@ -66,6 +66,15 @@ def test_version_and_error_string(built):
     assert isinstance(lib.pst3r_last_error(), bytes)
 
 
+def test_host_side_switches_without_a_gpu(built):
+    """pst3r_set_pdl / pst3r_set_split_k / pst3r_set_sm_budget are host-side launch settings: they work, and return the previous
+    value, without a device (split-K is off by default: only the memory build switches it on around its own launches)."""
+    lib = built.load()
+    assert lib.pst3r_set_split_k(1) == 0 and lib.pst3r_set_split_k(0) == 1 and lib.pst3r_set_split_k(0) == 0
+    prev = lib.pst3r_set_pdl(0)
+    assert prev in (0, 1) and lib.pst3r_set_pdl(prev) == 0
+
+
 def test_bad_arguments_are_rejected_without_a_gpu(built):
     lib = built.load()
     e = built.GemmEpilogue()
