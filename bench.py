@@ -377,6 +377,9 @@ def run_ours(args):
                      "note": "same step with PanopticDecoder.precision='bf16' (plain bf16 operands in the head, ~1e-2 parity)"}
         model.panoptic_decoder.precision = "fp32"
         del g2
+    ids_only = None
+    if world == 1 and not keyframes and args.ids_only:
+        ids_only = ids_only_leg(args, torch, model, step_device, host_imgs, dev_imgs, ts, V, dev)
     if world == 1 and not keyframes and args.gpu_reference:
         gpu_ref = gpu_reference_leg(args, model, dev_imgs, ts, value)
 
@@ -422,6 +425,7 @@ def run_ours(args):
             "class_fractions": gemm_class,
             "total_views_per_s": V * args.steps / (ms_total / 1e3),
             "bf16_head": bf16_head,
+            "ids_only": ids_only,
             "gpu_reference": gpu_ref,
             "baseline_config5": weak,
             "scene_parallel": scene_parallel,
@@ -583,6 +587,73 @@ def attention_roofline(ops, torch, V, peaks, peak_src):
             "peak_source": peak_src}
 
 
+def ids_only_leg(args, torch, model, step_device, host_imgs, dev_imgs, ts, V, dev):
+    """The same scene for a caller that wants panoptic ids, not mask logits (tools/demo_panst3r.py:232-242 runs
+    `panoptic_inference_v2` on `pred_masks` right after the forward): `PanopticDecoder.lazy_masks` + the band-wise
+    post-processing (panst3r_b200/postprocess.py, LazyMasks).  The forward (without the mask einsums) is one CUDA graph,
+    the post-processing runs eagerly (its filtering rounds read two small counter arrays on the host).  Host images in,
+    segment ids / confidences / pointmaps / class logits out, every step; next to it the same post-processing on the
+    materialised `pred_masks` of the default step."""
+    from panst3r_b200 import postprocess as pp
+    pd = model.panoptic_decoder
+    size = tuple(int(v) for v in ts[0][0])
+    try:
+        def timed(fn, n):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        n = max(3, min(args.steps, 10))
+        host = {}
+
+        def to_host(name, t):
+            if name not in host:
+                host[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            host[name].copy_(t, non_blocking=True)
+
+        def make_step(lazy):
+            pd.lazy_masks = lazy
+            for _ in range(2):
+                step_device()
+            g, out = _capture(torch, step_device) if args.graph else (None, None)
+
+            def step():
+                dev_imgs.copy_(host_imgs, non_blocking=True)
+                if g is not None:
+                    g.replay()
+                    pan, pm = out
+                else:
+                    pan, pm = step_device()
+                res = pp.panoptic_inference_v2(pan["pred_logits"], pan["pred_masks"], size)[0]
+                to_host("pan", res["pan"]); to_host("conf", res["conf"]); to_host("pm", pm); to_host("cls", pan["pred_logits"])
+                return res
+            return step
+
+        lazy_step = make_step(True)
+        ms_lazy = timed(lazy_step, n)
+        res = lazy_step()
+        torch.cuda.synchronize()
+        d2h = sum(h.numel() * h.element_size() for h in host.values())
+        mat_step = make_step(False)
+        ms_mat = timed(mat_step, n)
+        return {"value": V / (ms_lazy / 1e3), "unit": UNIT, "ms_per_step": ms_lazy, "segments": len(res["segments_info"]),
+                "h2d_bytes_per_step": host_imgs.numel() * host_imgs.element_size(), "d2h_bytes_per_step": d2h,
+                "materialised": {"value": V / (ms_mat / 1e3), "ms_per_step": ms_mat,
+                                 "note": "default forward (all seven mask einsums materialised) + the same post-processing"},
+                "what": "PanSt3R forward with lazy masks (CUDA graph) + panoptic_inference_v2 on the GPU, host images in, "
+                        "ids / confidences / pointmaps / class logits to pinned host memory; no (V, Q, H/2, W/2) tensor"}
+    except Exception as e:  # noqa: BLE001  (a secondary leg must never take the headline line down)
+        torch.cuda.synchronize()
+        return {"error": repr(e)}
+    finally:
+        pd.lazy_masks = False
+
+
 def gpu_reference_leg(args, model, dev_imgs, ts, our_value):
     """The reference's OWN single-GPU path on this box, as the denominator of the north star's '>= 8x the reference's
     single-GPU forward': the oracle modules (the reference's panoptic-head code restated + restated MUSt3R, same weights
@@ -696,6 +767,7 @@ def main():
     ap.add_argument("--head-precision", default="fp32", choices=["fp32", "bf16"],
                     help="panoptic head arithmetic: fp32 = the reference's policy (split-bf16 operands), bf16 = plain bf16")
     ap.add_argument("--no-bf16-head", dest="bf16_head", action="store_false", help="skip the secondary all-bf16-head timing")
+    ap.add_argument("--no-ids-only", dest="ids_only", action="store_false", help="skip the lazy-masks + post-processing timing")
     ap.add_argument("--no-gpu-reference", dest="gpu_reference", action="store_false",
                     help="skip timing the reference's own PyTorch path on the GPU (N = 1)")
     ap.add_argument("--no-weak", dest="weak", action="store_false", help="N > 1: skip the 8-views-per-GPU (config 5) leg")

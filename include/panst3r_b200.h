@@ -273,6 +273,17 @@ int pst3r_panoptic_argmax(const float* masks, int64_t view_stride, int64_t query
                           const int32_t* keep_idx, const float* keep_scores, int32_t nkeep, int32_t H, int32_t W,
                           float mask_threshold, int32_t* ids, float* win, int64_t out_view_stride, int32_t out_row_stride,
                           int32_t* area_half, int32_t* area_won, pst3r_stream_t stream);
+/* The same kernel on a BAND of the map: output rows [y0, y0 + rows) of every view, with `masks` holding only the source
+ * rows [src_row0, src_row0 + src_rows) of every plane (plane pitch query_stride >= src_rows * wm; hm stays the height of
+ * the whole mask grid, ids / win still point at row 0 of the whole output map).  The band must contain every source row
+ * the bilinear resize reads for its output rows (checked).  This is what lets a caller produce the mask logits chunk by
+ * chunk into a scratch buffer that stays in the 126 MB L2 and never materialise the (V, Q, h, w) tensor the reference
+ * builds at postprocess.py:18-27 (panst3r_b200/postprocess.py, LazyMasks); counters accumulate across bands. */
+int pst3r_panoptic_argmax_band(const float* masks, int64_t view_stride, int64_t query_stride, int32_t V, int32_t hm, int32_t wm,
+                               int32_t src_row0, int32_t src_rows, const int32_t* keep_idx, const float* keep_scores,
+                               int32_t nkeep, int32_t H, int32_t W, int32_t y0, int32_t rows, float mask_threshold,
+                               int32_t* ids, float* win, int64_t out_view_stride, int32_t out_row_stride,
+                               int32_t* area_half, int32_t* area_won, pst3r_stream_t stream);
 /* pan[i] = lut[ids[i]] if win[i] >= mask_threshold else 0; conf[i] = win[i] where pan[i] != 0 else void_confidence
  * (:103-105); lut[k] = segment id of kept query k or 0 if it was filtered out. */
 int pst3r_panoptic_finalize(const int32_t* ids, const float* win, const int32_t* lut, int32_t nkeep, float mask_threshold,

@@ -67,6 +67,9 @@ struct PanArgmaxParams {
   int out_row_stride;
   int* area_half;                // [nkeep] += #pixels with probability >= 0.5
   int* area_won;                 // [nkeep] += #pixels won with probability >= mask_threshold
+  // band launches (pst3r_panoptic_argmax_band): this launch covers output rows [y0, y0 + rows) and `masks` holds the
+  // source rows [src_row0, src_row0 + src_rows) of every plane (plane pitch = query_stride); whole-map launches: 0, H, 0
+  int y0, rows, src_row0;
 };
 
 __global__ void __launch_bounds__(256) panoptic_argmax_kernel(const PanArgmaxParams p) {
@@ -77,7 +80,8 @@ __global__ void __launch_bounds__(256) panoptic_argmax_kernel(const PanArgmaxPar
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int v = blockIdx.z;
   const int x = blockIdx.x * PA_TW + tx;
-  const int y_base = blockIdx.y * PA_TH;
+  const int y_base = p.y0 + blockIdx.y * PA_TH;
+  const int y_end = min(p.y0 + p.rows, p.H);
   for (int i = tid; i < 2 * p.nkeep; i += 256) smem_i[i] = 0;
 
   // source window of this output tile
@@ -86,7 +90,7 @@ __global__ void __launch_bounds__(256) panoptic_argmax_kernel(const PanArgmaxPar
   src_index(blockIdx.x * PA_TW, p.scale_w, p.wm, sx0, d1, dl);
   src_index(min(blockIdx.x * PA_TW + PA_TW - 1, p.W - 1), p.scale_w, p.wm, d0, sx1, dl);
   src_index(y_base, p.scale_h, p.hm, sy0, d1, dl);
-  src_index(min(y_base + PA_TH - 1, p.H - 1), p.scale_h, p.hm, d0, sy1, dl);
+  src_index(min(y_base + PA_TH - 1, y_end - 1), p.scale_h, p.hm, d0, sy1, dl);
   const int sw = sx1 - sx0 + 1, sh = sy1 - sy0 + 1;
 
   // this thread's pixels: column x, rows y_base + ty + 8 * i
@@ -101,9 +105,9 @@ __global__ void __launch_bounds__(256) panoptic_argmax_kernel(const PanArgmaxPar
 #pragma unroll
   for (int i = 0; i < PA_ROWS; ++i) {
     const int y = y_base + ty + 8 * i;
-    valid[i] = (x < p.W) && (y < p.H);
+    valid[i] = (x < p.W) && (y < y_end);
     int a, b;
-    src_index(min(y, p.H - 1), p.scale_h, p.hm, a, b, yl1[i]);
+    src_index(min(y, y_end - 1), p.scale_h, p.hm, a, b, yl1[i]);
     yo0[i] = (a - sy0) * sw;
     yo1[i] = (b - sy0) * sw;
   }
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(256) panoptic_argmax_kernel(const PanArgmaxPar
 #pragma unroll
   for (int i = 0; i < PA_ROWS; ++i) { best[i] = -CUDART_INF_F; bestv[i] = 0.0f; bestk[i] = 0; }
 
-  const float* vbase = p.masks + (long long)v * p.view_stride + (long long)sy0 * p.wm + sx0;
+  const float* vbase = p.masks + (long long)v * p.view_stride + (long long)(sy0 - p.src_row0) * p.wm + sx0;
   auto load_tile = [&](int k, float* dst) {
     const float* src = vbase + (long long)p.keep_idx[k] * p.query_stride;
     for (int i = tid; i < sh * sw; i += 256) {
@@ -180,11 +184,20 @@ extern "C" int pst3r_class_scores(const float* logits, int64_t ldl, int32_t Q, i
   return PST3R_OK;
 }
 
-extern "C" int pst3r_panoptic_argmax(const float* masks, int64_t view_stride, int64_t query_stride, int32_t V, int32_t hm,
-                                     int32_t wm, const int32_t* keep_idx, const float* keep_scores, int32_t nkeep,
-                                     int32_t H, int32_t W, float mask_threshold, int32_t* ids, float* win,
-                                     int64_t out_view_stride, int32_t out_row_stride, int32_t* area_half,
-                                     int32_t* area_won, pst3r_stream_t s_) {
+// the kernel's source-row arithmetic on the host (same fp32 operations): first / last source row read for an output row
+static void host_src_rows(int dst, float scale, int in_size, int* i0, int* i1) {
+  float s = scale * ((float)dst + 0.5f) - 0.5f;
+  s = s < 0.0f ? 0.0f : s;
+  *i0 = (int)s < in_size - 1 ? (int)s : in_size - 1;
+  *i1 = *i0 + 1 < in_size - 1 ? *i0 + 1 : in_size - 1;
+}
+
+extern "C" int pst3r_panoptic_argmax_band(const float* masks, int64_t view_stride, int64_t query_stride, int32_t V, int32_t hm,
+                                          int32_t wm, int32_t src_row0, int32_t src_rows, const int32_t* keep_idx,
+                                          const float* keep_scores, int32_t nkeep, int32_t H, int32_t W, int32_t y0,
+                                          int32_t rows, float mask_threshold, int32_t* ids, float* win,
+                                          int64_t out_view_stride, int32_t out_row_stride, int32_t* area_half,
+                                          int32_t* area_won, pst3r_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
   PST3R_CHECK_ARG(masks && ids && win && V > 0 && hm > 0 && wm > 0 && H > 0 && W > 0 && nkeep >= 0,
                   "panoptic_argmax: bad args");
@@ -193,20 +206,44 @@ extern "C" int pst3r_panoptic_argmax(const float* masks, int64_t view_stride, in
                   hm, wm, H, W);
   PST3R_CHECK_ARG(out_row_stride >= W && out_view_stride >= (int64_t)out_row_stride * H, "panoptic_argmax: bad output strides");
   PST3R_CHECK_ARG(nkeep <= 4096, "panoptic_argmax: at most 4096 kept queries");
+  PST3R_CHECK_ARG(y0 >= 0 && rows > 0 && y0 + rows <= H && src_row0 >= 0 && src_rows > 0 && src_row0 + src_rows <= hm,
+                  "panoptic_argmax: bad band (rows [%d, %d) of %d, source rows [%d, %d) of %d)", y0, y0 + rows, H, src_row0,
+                  src_row0 + src_rows, hm);
+  PST3R_CHECK_ARG(query_stride >= (int64_t)src_rows * wm, "panoptic_argmax: plane pitch smaller than the band");
+  const float scale_h = (float)hm / (float)H, scale_w = (float)wm / (float)W;
+  {
+    int lo, hi, d;
+    host_src_rows(y0, scale_h, hm, &lo, &d);
+    host_src_rows(y0 + rows - 1, scale_h, hm, &d, &hi);
+    PST3R_CHECK_ARG(lo >= src_row0 && hi < src_row0 + src_rows,
+                    "panoptic_argmax: output rows [%d, %d) read source rows [%d, %d], the band holds [%d, %d)", y0, y0 + rows, lo,
+                    hi, src_row0, src_row0 + src_rows);
+  }
   PanArgmaxParams p;
   p.masks = masks; p.view_stride = view_stride; p.query_stride = query_stride;
   p.hm = hm; p.wm = wm; p.V = V;
   p.keep_idx = keep_idx; p.keep_scores = keep_scores; p.nkeep = nkeep;
   p.H = H; p.W = W;
-  p.scale_h = (float)hm / (float)H; p.scale_w = (float)wm / (float)W;
+  p.scale_h = scale_h; p.scale_w = scale_w;
   p.mask_threshold = mask_threshold;
   p.ids = ids; p.win = win; p.out_view_stride = out_view_stride; p.out_row_stride = out_row_stride;
   p.area_half = area_half; p.area_won = area_won;
+  p.y0 = y0; p.rows = rows; p.src_row0 = src_row0;
   const size_t smem = (size_t)2 * nkeep * sizeof(int) + 2 * PA_SMAX * PA_SMAX * sizeof(float);
-  dim3 grid((W + PA_TW - 1) / PA_TW, (H + PA_TH - 1) / PA_TH, V);
+  dim3 grid((W + PA_TW - 1) / PA_TW, (rows + PA_TH - 1) / PA_TH, V);
   panoptic_argmax_kernel<<<grid, 256, smem, s>>>(p);
   PST3R_CHECK_CUDA(cudaGetLastError());
   return PST3R_OK;
+}
+
+extern "C" int pst3r_panoptic_argmax(const float* masks, int64_t view_stride, int64_t query_stride, int32_t V, int32_t hm,
+                                     int32_t wm, const int32_t* keep_idx, const float* keep_scores, int32_t nkeep,
+                                     int32_t H, int32_t W, float mask_threshold, int32_t* ids, float* win,
+                                     int64_t out_view_stride, int32_t out_row_stride, int32_t* area_half,
+                                     int32_t* area_won, pst3r_stream_t s_) {
+  PST3R_CHECK_ARG(H > 0 && hm > 0, "panoptic_argmax: bad args");
+  return pst3r_panoptic_argmax_band(masks, view_stride, query_stride, V, hm, wm, 0, hm, keep_idx, keep_scores, nkeep, H, W, 0, H,
+                                    mask_threshold, ids, win, out_view_stride, out_row_stride, area_half, area_won, s_);
 }
 
 extern "C" int pst3r_panoptic_finalize(const int32_t* ids, const float* win, const int32_t* lut, int32_t nkeep,

@@ -109,6 +109,8 @@ SIGNATURES = {
     "pst3r_class_scores": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p]),
     "pst3r_panoptic_argmax": (C.c_int, [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _i32, _i32, _i32, _f, _p, _p, _i64, _i32,
                                         _p, _p, _p]),
+    "pst3r_panoptic_argmax_band": (C.c_int, [_p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32,
+                                             _f, _p, _p, _i64, _i32, _p, _p, _p]),
     "pst3r_panoptic_finalize": (C.c_int, [_p, _p, _p, _i32, _f, _f, _p, _p, _i64, _p]),
 }
 

@@ -247,10 +247,13 @@ class MaskTransformer(nn.Module):
 
     # ---- prediction heads (mask_transformer.py:215-288) -----------------------------------------------
     @torch.no_grad()
-    def prediction_heads(self, output, mask_feats, pooled, cls_emb, want_masks: bool, precise: bool = False):
+    def prediction_heads(self, output, mask_feats, pooled, cls_emb, want_masks: bool, precise: bool = False,
+                         lazy: bool = False):
         """output (Q, C) [batch 1]; mask_feats (V, Hm, Wm, Cm) pixel-major; pooled (V*h*w, Cm) or None — bf16 tensors,
         or ops.Split pairs when `precise`.
-        Returns (class logits fp32 (Q, K), mask logits fp32 (V, Q, Hm, Wm) | None, mask bits int32 (1, Q, W) | None)."""
+        Returns (class logits fp32 (Q, K), mask logits fp32 (V, Q, Hm, Wm) | None, mask bits int32 (1, Q, W) | None).
+        lazy: the mask logits come back as a `postprocess.LazyMasks` (embeddings + features; the einsum is left to the
+        post-processing, which evaluates it band by band through the L2)."""
         Q = output.shape[0]
         W = wsplit if precise else w16
         act = "split" if precise else torch.bfloat16
@@ -267,6 +270,9 @@ class MaskTransformer(nn.Module):
         masks = None
         if want_masks:
             def plane_major(mf):
+                if lazy:
+                    from ..postprocess import LazyMasks
+                    return LazyMasks(mf, e)
                 V, Hm, Wm, Cm = mf.shape
                 mk = torch.empty((V, Q, Hm, Wm), device=dev, dtype=torch.float32)
                 ops.gemm(mf.view(V * Hm * Wm, Cm), e, out=mk, store_mode=ops.STORE_TRANSPOSED,
@@ -301,7 +307,8 @@ class MaskTransformer(nn.Module):
     @torch.no_grad()
     def forward_nhwc(self, src, mask_feats, hw, cls_emb,
                      deep_supervision: bool = True, pooled=None,
-                     mask_override: Optional[List[torch.Tensor]] = None, portrait=False, precise: bool = False):
+                     mask_override: Optional[List[torch.Tensor]] = None, portrait=False, precise: bool = False,
+                     lazy_masks: bool = False):
         """src (V*h*w, C) = stride-16 features + level_embed, views flattened view-major (batch 1);
         mask_feats (V', Hm, Wm, Cm) — the views whose full-resolution masks this call produces (all V, or this
         rank's shard); pooled (V*h*w, Cm): centre-pooled mask features of ALL views (computed from mask_feats
@@ -309,7 +316,11 @@ class MaskTransformer(nn.Module):
         Returns the reference's output dict (batch dim 1).
         Multi aspect ratio (mask_transformer.py:126-146 with multi_ar=True): src / mask_feats / hw / portrait are
         LISTS with one entry per stack of equally shaped views; the memory tokens of all stacks are concatenated in
-        stack order (each with the PE of its own grid) and `pred_masks` comes back as a list with one tensor per stack."""
+        stack order (each with the PE of its own grid) and `pred_masks` comes back as a list with one tensor per stack.
+        lazy_masks: `pred_masks` is a `postprocess.LazyMasks` (the final einsum is left to the post-processing) and the
+        auxiliary heads are not evaluated (`aux_outputs` is empty): the layers only need the pooled attention masks."""
+        if lazy_masks:
+            deep_supervision = False
         if mask_override is None:
             mask_override = self.mask_override
         multi = isinstance(src, (list, tuple))
@@ -382,7 +393,7 @@ class MaskTransformer(nn.Module):
             output = ops.layernorm(t, f32(ff.norm.weight), f32(ff.norm.bias), 1e-5)
             last = i == L - 1
             cls, msk, bits = self.prediction_heads(output, mask_feats, None if last else pooled, cls_emb,
-                                                   want_masks=deep_supervision or last, precise=precise)
+                                                   want_masks=deep_supervision or last, precise=precise, lazy=lazy_masks)
             if deep_supervision or last:
                 pred_cls.append(cls)
                 pred_msk.append(msk)
@@ -421,7 +432,8 @@ def _cat_rows(parts):
 class PanopticDecoder(nn.Module):
     def __init__(self, input_mixer=None, upscaler=None, fpn_dim=[768], hidden_dim=768, mask_dim=256, ff_dim=2048,
                  num_queries=200, num_heads=8, dec_layers=6, text_encoder="siglip", fixed_vocab=True,
-                 label_mode="sigmoid", two_stage=False, landscape_only=True, deep_supervision=True, precision="fp32"):
+                 label_mode="sigmoid", two_stage=False, landscape_only=True, deep_supervision=True, precision="fp32",
+                 lazy_masks=False):
         super().__init__()
         assert upscaler is not None, "Upscaler module must be provided"
         assert label_mode == "sigmoid" and not two_stage
@@ -437,6 +449,9 @@ class PanopticDecoder(nn.Module):
         # "bf16": plain bf16 operands + fused flash attention (see the module docstring)
         assert precision in ("fp32", "bf16")
         self.precision = precision
+        # True: `pred_masks` comes back as a `postprocess.LazyMasks` — the full-resolution mask einsum is evaluated by
+        # `panoptic_inference_v1/_v2` band by band and never materialised (no auxiliary masks; one scene per call)
+        self.lazy_masks = bool(lazy_masks)
 
     @property
     def precise(self) -> bool:
@@ -452,6 +467,8 @@ class PanopticDecoder(nn.Module):
             return self._forward_multi_ar(in_feats, in_imgs, pos, true_shape, classes, outdevice, memory_queries, cat_feats)
         B = cat_feats.shape[0] if cat_feats is not None else in_feats[0].shape[0]
         if B > 1:  # scenes are independent: one pass per scene, outputs concatenated along the batch dimension
+            if self.lazy_masks:
+                raise ops._l.Pst3rError("lazy_masks: one scene per call (a batch of lazy mask handles cannot be concatenated)")
             from ..panst3r import merge_panouts
             ts = true_shape.cpu() if torch.is_tensor(true_shape) and true_shape.is_cuda else true_shape
             outs = []
@@ -468,10 +485,10 @@ class PanopticDecoder(nn.Module):
         cls_emb = self.text_encoder(classes, device=dev, precise=pr)
         if memory_queries is None:
             out = mt.forward_nhwc(src, mask_f, grid, cls_emb, deep_supervision=self.deep_supervision, portrait=portrait,
-                                  precise=pr)
+                                  precise=pr, lazy_masks=self.lazy_masks)
         else:
             logits, masks, _ = mt.prediction_heads(self._queries(memory_queries), mask_f, None, cls_emb, want_masks=True,
-                                                   precise=pr)
+                                                   precise=pr, lazy=self.lazy_masks)
             out = {"pred_logits": logits[None], "pred_masks": masks[None]}
         return self._to_device(out, outdevice, dev)
 
@@ -488,7 +505,7 @@ class PanopticDecoder(nn.Module):
             return out
 
         def mv(v):
-            if torch.is_tensor(v):
+            if torch.is_tensor(v) or hasattr(v, "materialize"):  # a LazyMasks handle materialises when it leaves the GPU
                 return v.to(outdevice)
             if isinstance(v, dict):
                 return {k: mv(x) for k, x in v.items()}
@@ -545,10 +562,11 @@ class PanopticDecoder(nn.Module):
         cls_emb = self.text_encoder(classes, device=dev, precise=pr)
         if memory_queries is None:
             out = mt.forward_nhwc([s_[0] for s_ in st], [s_[1] for s_ in st], [s_[2] for s_ in st], cls_emb,
-                                  deep_supervision=self.deep_supervision, portrait=[s_[3] for s_ in st], precise=pr)
+                                  deep_supervision=self.deep_supervision, portrait=[s_[3] for s_ in st], precise=pr,
+                                  lazy_masks=self.lazy_masks)
         else:
             logits, masks, _ = mt.prediction_heads(self._queries(memory_queries), [s_[1] for s_ in st], None, cls_emb,
-                                                   want_masks=True, precise=pr)
+                                                   want_masks=True, precise=pr, lazy=self.lazy_masks)
             out = {"pred_logits": logits[None], "pred_masks": [m_[None] for m_ in masks]}
         return self._to_device(out, outdevice, dev)
 

@@ -698,28 +698,40 @@ def class_scores(logits: torch.Tensor):
 
 
 def panoptic_argmax(masks: torch.Tensor, keep_idx: torch.Tensor, keep_scores: torch.Tensor, size: Tuple[int, int],
-                    mask_threshold: float, area_half: torch.Tensor, area_won: torch.Tensor):
+                    mask_threshold: float, area_half: torch.Tensor, area_won: torch.Tensor, *, out=None, band=None):
     """masks fp32 [V, Q, hm, wm] mask logits -> (ids int32 [V, H, W], win fp32 [V, H, W]); accumulates the per-query
-    pixel counts into area_half / area_won (int32 [nkeep], zeroed by the caller)."""
+    pixel counts into area_half / area_won (int32 [nkeep], zeroed by the caller).
+    out = (ids, win): write into these maps instead of fresh ones.
+    band = (y0, rows, src_row0, hm): only output rows [y0, y0 + rows); `masks` is then [V, Q, src_rows, wm], the source rows
+    [src_row0, src_row0 + src_rows) of a mask grid of height hm (pst3r_panoptic_argmax_band)."""
     global launches
     lib = _l.load()
     _need(masks, torch.float32, "panoptic_argmax.masks")
     if masks.dim() != 4 or masks.stride(-1) != 1 or masks.stride(-2) != masks.shape[-1]:
         raise _l.Pst3rError("panoptic_argmax.masks: expected [V, Q, hm, wm] with dense planes")
-    V, Q, hm, wm = masks.shape
+    V, Q, src_rows, wm = masks.shape
     H, W = int(size[0]), int(size[1])
+    y0, rows, src_row0, hm = (0, H, 0, src_rows) if band is None else (int(b) for b in band)
     nkeep = keep_idx.numel()
     if nkeep:
         _need(keep_idx, torch.int32, "panoptic_argmax.keep_idx")
         _need(keep_scores, torch.float32, "panoptic_argmax.keep_scores")
         _need(area_half, torch.int32, "panoptic_argmax.area_half")
         _need(area_won, torch.int32, "panoptic_argmax.area_won")
-    ids = torch.empty((V, H, W), device=masks.device, dtype=torch.int32)
-    win = torch.empty((V, H, W), device=masks.device, dtype=torch.float32)
-    _l.check(lib.pst3r_panoptic_argmax(masks.data_ptr(), masks.stride(0), masks.stride(1), V, hm, wm, _ptr(keep_idx) if nkeep else None,
-                                       _ptr(keep_scores) if nkeep else None, nkeep, H, W, float(mask_threshold), ids.data_ptr(),
-                                       win.data_ptr(), H * W, W, _ptr(area_half) if nkeep else None,
-                                       _ptr(area_won) if nkeep else None, _stream()), "pst3r_panoptic_argmax")
+    if out is None:
+        ids = torch.empty((V, H, W), device=masks.device, dtype=torch.int32)
+        win = torch.empty((V, H, W), device=masks.device, dtype=torch.float32)
+    else:
+        ids, win = out
+        _need(ids, torch.int32, "panoptic_argmax.ids")
+        _need(win, torch.float32, "panoptic_argmax.win")
+        if tuple(ids.shape) != (V, H, W) or tuple(win.shape) != (V, H, W) or not (ids.is_contiguous() and win.is_contiguous()):
+            raise _l.Pst3rError(f"panoptic_argmax: out maps must be contiguous [{V}, {H}, {W}]")
+    _l.check(lib.pst3r_panoptic_argmax_band(masks.data_ptr(), masks.stride(0), masks.stride(1), V, hm, wm, src_row0, src_rows,
+                                            _ptr(keep_idx) if nkeep else None, _ptr(keep_scores) if nkeep else None, nkeep, H, W,
+                                            y0, rows, float(mask_threshold), ids.data_ptr(), win.data_ptr(), H * W, W,
+                                            _ptr(area_half) if nkeep else None, _ptr(area_won) if nkeep else None, _stream()),
+             "pst3r_panoptic_argmax_band")
     launches += 1
     return ids, win
 

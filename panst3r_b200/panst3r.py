@@ -180,6 +180,32 @@ class PanSt3R(nn.Module):
         return panout, pointmaps
 
     @torch.no_grad()
+    def forward_panoptic(self, imgs, true_shape, classes, postprocess: Optional[str] = None, max_bs=None, **pp_kwargs):
+        """`forward()` followed by the reference's standard post-processing (tools/demo_panst3r.py:232-242:
+        `panoptic_inference_v1/_v2(pan_out['pred_logits'], pan_out['pred_masks'], size)`) for callers that want segment
+        ids, not mask logits: the head leaves its final mask einsum to the post-processing (`PanopticDecoder.lazy_masks`),
+        which evaluates it band by band through the L2 (panst3r_b200/postprocess.py, LazyMasks) — the (V, Q, H/2, W/2)
+        fp32 tensor (629 MB at 16 views of 512x384) is never written, re-read or copied to the host.
+        Returns (pan_preds, panout, pointmaps); pan_preds[b] = {'pan', 'segments_info', 'conf'} as the reference's
+        functions return it, panout['pred_masks'] is the LazyMasks handle (`.materialize()` gives the tensor)."""
+        from . import postprocess as pp
+        which = postprocess or self.postprocess_default
+        fns = {"standard_v1": pp.panoptic_inference_v1, "standard_v2": pp.panoptic_inference_v2}
+        if which not in fns:
+            raise NotImplementedError(f"postprocess={which!r}: only 'standard_v1' / 'standard_v2' run on the GPU "
+                                      "(panoptic_inference_qubo is out of scope)")
+        pd = self.panoptic_decoder
+        prev, pd.lazy_masks = pd.lazy_masks, True
+        try:
+            panout, pointmaps = self.forward(imgs, true_shape, classes, max_bs=max_bs)
+        finally:
+            pd.lazy_masks = prev
+        ts = true_shape.cpu() if torch.is_tensor(true_shape) and true_shape.is_cuda else true_shape
+        size = tuple(int(v) for v in ts[0][0])
+        pan_preds = fns[which](panout["pred_logits"], panout["pred_masks"], size, label_mode=pd.label_mode, **pp_kwargs)
+        return pan_preds, panout, pointmaps
+
+    @torch.no_grad()
     def forward_inference_multi_ar(self, imgs: List[torch.Tensor], true_shape, classes, num_keyframes=None,
                                    use_retrieval=False, max_bs=None, outdevice=None, amp=False):
         """Keyframes build the memory and run the full panoptic head; the remaining frames are rendered against the

@@ -11,6 +11,13 @@ the two per-query pixel counts of the filtering rule, the final id / confidence 
 libpanst3r_b200.so (csrc/postprocess.cu); the host only walks the <= Q surviving queries of each round over two small
 counter arrays, exactly the reference's loop (:77-113) without its per-query `.item()` reductions over full-size maps.
 Only label_mode='sigmoid' without temperature (configs/base.yaml, tools/demo_panst3r.py) is implemented.
+
+`LazyMasks` (what `PanopticDecoder.lazy_masks = True` puts into `pred_masks`): the mask einsum
+"bqc,bnchw->bnqhw" (mask_transformer.py:279-280) is NOT evaluated by the head; `mask_pred` then holds the final
+mask embeddings and the pixel features, and every post-processing round produces the logits chunk by chunk (one band of
+one view per tcgen05 GEMM launch) into ONE scratch buffer small enough to stay in the 126 MB L2, consumed at once by
+the band form of the argmax kernel.  The (V, Q, h, w) fp32 tensor the reference writes, copies and re-reads
+(629 MB at 16 views of 512x384) never exists; ids, segments and confidences are those of the materialised path.
 """
 from __future__ import annotations
 
@@ -20,6 +27,160 @@ import numpy as np
 import torch
 
 from . import ops
+
+
+class LazyMasks:
+    """Mask logits of one stack of equally shaped views in factored form: logits[v, q, y, x] = <feats[v, y, x, :], embed[q, :]>.
+    feats: (V, hm, wm, C) pixel-major, embed: (Q, C); both bf16 tensors, or both ops.Split pairs (reference-precision head).
+    Stands where the reference's `pred_masks` tensor stands: `shape` / `dim()` / indexing by batch and view follow a
+    (1, V, Q, hm, wm) tensor (ndim 5: leading batch of one; 4: a stack; 3: one view), `.to(cuda device)` is the identity and
+    `.to('cpu')` / `materialize()` evaluate the full tensor with the same GEMM the eager head uses."""
+
+    # bytes of fp32 logits produced per GEMM launch: 200 queries x 96 rows x 256 pixels = 19.7 MB, half a 512x384 view
+    # (measured: profiles/r02_lazy_masks.md)
+    scratch_bytes = 20 << 20
+    _scratch = {}
+
+    def __init__(self, feats, embed, ndim: int = 4):
+        if feats.shape[-1] != embed.shape[-1] or len(feats.shape) != 4 or len(embed.shape) != 2:
+            raise ops._l.Pst3rError(f"LazyMasks: feats (V, hm, wm, C) / embed (Q, C) expected, got {tuple(feats.shape)} / {tuple(embed.shape)}")
+        if isinstance(feats, ops.Split) != isinstance(embed, ops.Split):
+            raise ops._l.Pst3rError("LazyMasks: features and embeddings must be both bf16 or both split pairs")
+        if ndim == 3 and feats.shape[0] != 1:
+            raise ops._l.Pst3rError("LazyMasks: a single-view handle needs exactly one view")
+        self.feats, self.embed, self._ndim = feats, embed, ndim
+
+    # ---- tensor-like surface -------------------------------------------------------------------------
+    @property
+    def shape(self):
+        V, hm, wm, _ = self.feats.shape
+        core = (self.embed.shape[0], hm, wm)
+        return torch.Size({3: core, 4: (V, *core), 5: (1, V, *core)}[self._ndim])
+
+    def dim(self) -> int:
+        return self._ndim
+
+    def __len__(self) -> int:
+        return self.shape[0]
+
+    @property
+    def device(self):
+        return self.feats.device
+
+    dtype = torch.float32
+    is_cuda = True
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple):
+            out = self
+            for i in idx:
+                out = out[i]
+            return out
+        if idx is None:
+            if self._ndim == 5:
+                raise ops._l.Pst3rError("LazyMasks: already has a batch dimension")
+            return LazyMasks(self.feats, self.embed, self._ndim + 1)
+        if self._ndim == 5:
+            if isinstance(idx, slice):
+                if idx.indices(1) != (0, 1, 1):
+                    raise IndexError("LazyMasks: the batch dimension has one entry")
+                return self
+            if int(idx) not in (0, -1):
+                raise IndexError("LazyMasks: the batch dimension has one entry")
+            return LazyMasks(self.feats, self.embed, 4)
+        if self._ndim == 4:
+            V = self.feats.shape[0]
+            if isinstance(idx, slice):
+                a, b, st = idx.indices(V)
+                if st != 1 or b <= a:
+                    raise IndexError("LazyMasks: contiguous, non-empty view ranges only")
+                return LazyMasks(self.feats[a:b], self.embed, 4)
+            i = int(idx) + (V if int(idx) < 0 else 0)
+            if not 0 <= i < V:
+                raise IndexError(f"LazyMasks: view {idx} of {V}")
+            return LazyMasks(self.feats[i:i + 1], self.embed, 3)
+        raise IndexError("LazyMasks: a single view is indexed by materialising it")
+
+    def to(self, device=None, *a, **k):
+        if device is None or torch.device(device).type == "cuda":
+            return self
+        return self.materialize().to(device, *a, **k)
+
+    def float(self):
+        return self
+
+    def contiguous(self):
+        return self
+
+    # ---- evaluation ----------------------------------------------------------------------------------
+    def logits(self, v: int, r0: int, r1: int, out: torch.Tensor = None) -> torch.Tensor:
+        """fp32 [Q, r1 - r0, wm]: source rows [r0, r1) of view v — one GEMM launch with a plane-major store."""
+        V, hm, wm, C = self.feats.shape
+        Q = self.embed.shape[0]
+        n = (r1 - r0) * wm
+        if out is None:
+            out = torch.empty((Q, r1 - r0, wm), device=self.device, dtype=torch.float32)
+        rows = self.feats.view(V * hm * wm, C)[(v * hm + r0) * wm:(v * hm + r1) * wm]
+        ops.gemm(rows, self.embed, out=out, store_mode=ops.STORE_TRANSPOSED, rows_per_batch=n, batch_stride=0, ldt=n)
+        return out
+
+    def materialize(self) -> torch.Tensor:
+        """The tensor this object stands for, (…, Q, hm, wm) fp32 with this handle's leading dims (one GEMM launch)."""
+        V, hm, wm, C = self.feats.shape
+        Q = self.embed.shape[0]
+        mk = torch.empty((V, Q, hm, wm), device=self.device, dtype=torch.float32)
+        ops.gemm(self.feats.view(V * hm * wm, C), self.embed, out=mk, store_mode=ops.STORE_TRANSPOSED,
+                 rows_per_batch=hm * wm, batch_stride=Q * hm * wm, ldt=hm * wm)
+        return {3: mk[0], 4: mk, 5: mk[None]}[self._ndim]
+
+    def band_plan(self, H: int, scratch_bytes: int = None):
+        """[(y0, rows, src_row0, src_rows)]: output-row bands (multiples of the kernel's 32-row tiles) whose source rows fit
+        the scratch budget, each with the source rows its bilinear resize reads (one spare row on either side: the
+        kernel's fp32 index arithmetic is re-checked by the library)."""
+        _, hm, wm, _ = self.feats.shape
+        Q = self.embed.shape[0]
+        budget = self.scratch_bytes if scratch_bytes is None else int(scratch_bytes)
+        max_src = max(4, budget // (Q * wm * 4))
+        scale = hm / H
+
+        def src_range(y0, rows):
+            lo = int(np.floor(scale * (y0 + 0.5) - 0.5)) - 1
+            hi = int(np.floor(scale * (y0 + rows - 1 + 0.5) - 0.5)) + 2
+            return max(lo, 0), min(hi, hm - 1)
+
+        step = max(32, int((max_src - 4) / scale) // 32 * 32)
+        plan, y0 = [], 0
+        while y0 < H:
+            rows = min(step, H - y0)
+            lo, hi = src_range(y0, rows)
+            plan.append((y0, rows, lo, hi - lo + 1))
+            y0 += rows
+        return plan
+
+    def panoptic_argmax(self, keep_idx, keep_scores, size, mask_threshold, area_half, area_won, scratch_bytes: int = None):
+        """`ops.panoptic_argmax` without the logits tensor: per view and band, GEMM into the scratch -> band argmax."""
+        V, hm, wm, _ = self.feats.shape
+        Q = self.embed.shape[0]
+        H, W = int(size[0]), int(size[1])
+        dev = self.device
+        ids = torch.empty((V, H, W), device=dev, dtype=torch.int32)
+        win = torch.empty((V, H, W), device=dev, dtype=torch.float32)
+        plan = self.band_plan(H, scratch_bytes)
+        need = max(p_[3] for p_ in plan) * Q * wm
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+        buf = LazyMasks._scratch.get(key)
+        if buf is None or buf.numel() < need:
+            buf = LazyMasks._scratch[key] = torch.empty(need, device=dev, dtype=torch.float32)
+        for v in range(V):
+            for y0, rows, s0, sr in plan:
+                chunk = self.logits(v, s0, s0 + sr, out=buf[:Q * sr * wm].view(Q, sr, wm))
+                ops.panoptic_argmax(chunk[None], keep_idx, keep_scores, (H, W), mask_threshold, area_half, area_won,
+                                    out=(ids[v:v + 1], win[v:v + 1]), band=(y0, rows, s0, hm))
+        return ids, win
+
+
+def _argmax(g, *args):
+    return g.panoptic_argmax(*args) if isinstance(g, LazyMasks) else ops.panoptic_argmax(g, *args)
 
 
 def _views(mask_pred, true_shape, multi_ar: bool):
@@ -47,7 +208,8 @@ def panoptic_inference_v2(mask_cls, mask_pred, true_shape, label_mode="sigmoid",
         dev = groups[0][0].device
         if dev.type != "cuda":
             raise ops._l.Pst3rError("panoptic_inference (panst3r_b200) runs on CUDA tensors only (no CPU fallback)")
-        groups = [(g.float().contiguous() if g.dtype != torch.float32 or not g.is_contiguous() else g, s) for g, s in groups]
+        groups = [(g if isinstance(g, LazyMasks) or (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous(), s)
+                  for g, s in groups]
         scores_d, labels_d = ops.class_scores(mask_cls[b].to(dev).float().contiguous())
         scores, labels = scores_d.cpu().numpy(), labels_d.cpu().numpy()
         keep = np.nonzero(scores > np.float32(cls_threshold))[0].astype(np.int32)
@@ -62,7 +224,7 @@ def panoptic_inference_v2(mask_cls, mask_pred, true_shape, label_mode="sigmoid",
             keep_d = torch.from_numpy(keep).to(dev)
             sc_d = scores_d[keep_d.long()].contiguous()
             areas = torch.zeros((2, keep.size), device=dev, dtype=torch.int32)
-            maps = [ops.panoptic_argmax(g, keep_d, sc_d, size, mask_threshold, areas[0], areas[1]) for g, size in groups]
+            maps = [_argmax(g, keep_d, sc_d, size, mask_threshold, areas[0], areas[1]) for g, size in groups]
             area_half, area_won = areas.cpu().numpy()
             lut = np.zeros(keep.size, dtype=np.int32)
             selected = []
