@@ -347,12 +347,13 @@ def run_ours(args):
     # kernels reports an inflated duration, and the sum would no longer compare with the step time
     # ... and without programmatic dependent launch: a dependent kernel that starts early waits for its predecessor
     # INSIDE its own measured duration
-    ov, pdl = model.overlap_dino, ops.set_pdl(False)
-    model.overlap_dino = False
+    mt_ = model.panoptic_decoder.mask_transformer
+    ov, ova, pdl = model.overlap_dino, mt_.overlap_aux_masks, ops.set_pdl(False)
+    model.overlap_dino = mt_.overlap_aux_masks = False
     try:
         breakdown = kernel_breakdown(torch, step_device, barrier)
     finally:
-        model.overlap_dino = ov
+        model.overlap_dino, mt_.overlap_aux_masks = ov, ova
         ops.set_pdl(pdl)
     roofline = att_roof = gemm_class = None
     if rank == 0:

@@ -22,6 +22,7 @@ of the query decoder is evaluated unfused (QK^T GEMM -> masked row softmax -> PV
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -213,6 +214,17 @@ class MaskTransformer(nn.Module):
         # block mask each layer actually used.  Both None in normal operation.
         self.mask_override: Optional[List[torch.Tensor]] = None
         self.bits_record: Optional[list] = None
+        # The masks of the auxiliary heads (deep supervision: the initial prediction and layers 0 .. L-2) feed nothing but the
+        # output dict, while the decoder layer that follows them is a chain of small, latency-bound launches on 200 query rows:
+        # their HBM-bound full-resolution GEMMs run on a side stream, on `aux_mask_sms` SMs, next to that layer, and are
+        # joined before forward_nhwc returns.  Bit-identical to the in-line run (tests/test_lazy_masks.py).  Measured at 16 views
+        # of 512x384 (profiles/r02_lazy_masks.md): the bf16 head gains 0.4 of 6.0 ms; the fp32-grade head, whose decoder
+        # layers are real tensor work on split operands, gains nothing (15.84 -> 15.79 ms).  None = on for the bf16 head
+        # only; True / False (or PST3R_AUX_OVERLAP=1 / 0) force it.
+        env = os.environ.get("PST3R_AUX_OVERLAP")
+        self.overlap_aux_masks: Optional[bool] = None if env is None else env != "0"
+        self.aux_mask_sms = 64
+        self._aux_stream = None
 
     # ---- prepared -------------------------------------------------------------------------------
     def _kv_weights(self, precise: bool = False):
@@ -248,12 +260,15 @@ class MaskTransformer(nn.Module):
     # ---- prediction heads (mask_transformer.py:215-288) -----------------------------------------------
     @torch.no_grad()
     def prediction_heads(self, output, mask_feats, pooled, cls_emb, want_masks: bool, precise: bool = False,
-                         lazy: bool = False):
+                         lazy: bool = False, side=None):
         """output (Q, C) [batch 1]; mask_feats (V, Hm, Wm, Cm) pixel-major; pooled (V*h*w, Cm) or None — bf16 tensors,
         or ops.Split pairs when `precise`.
         Returns (class logits fp32 (Q, K), mask logits fp32 (V, Q, Hm, Wm) | None, mask bits int32 (1, Q, W) | None).
         lazy: the mask logits come back as a `postprocess.LazyMasks` (embeddings + features; the einsum is left to the
-        post-processing, which evaluates it band by band through the L2)."""
+        post-processing, which evaluates it band by band through the L2).
+        side = (stream, keep_alive list): the full-resolution mask GEMM is launched on that stream, on `aux_mask_sms` SMs,
+        so that it runs next to the following decoder layer (whose launches are small and latency bound); the caller joins
+        the stream before it returns and keeps `keep_alive` until then."""
         Q = output.shape[0]
         W = wsplit if precise else w16
         act = "split" if precise else torch.bfloat16
@@ -279,7 +294,16 @@ class MaskTransformer(nn.Module):
                          rows_per_batch=Hm * Wm, batch_stride=Q * Hm * Wm, ldt=Hm * Wm)
                 return mk
             # several aspect-ratio stacks (multi_ar): one mask tensor per stack, as the reference returns them
-            masks = [plane_major(mf) for mf in mask_feats] if isinstance(mask_feats, (list, tuple)) else plane_major(mask_feats)
+            def all_planes():
+                return [plane_major(mf) for mf in mask_feats] if isinstance(mask_feats, (list, tuple)) else plane_major(mask_feats)
+            if side is not None and not lazy:
+                stream, keep_alive = side
+                stream.wait_stream(torch.cuda.current_stream())  # fork: the embeddings (and the features) are complete
+                keep_alive.append(e)                             # read by the side stream: not to be recycled before the join
+                with torch.cuda.stream(stream), ops.sm_budget(self.aux_mask_sms):
+                    masks = all_planes()
+            else:
+                masks = all_planes()
         bits = None
         if pooled is not None:
             nk = pooled.shape[0]
@@ -357,7 +381,14 @@ class MaskTransformer(nn.Module):
         qe = psplit(self.query_embed.weight) if precise else b16(self.query_embed.weight)
         output = psplit(self.query_feat.weight) if precise else b16(self.query_feat.weight)
         pred_cls, pred_msk = [], []
-        cls, msk, bits = self.prediction_heads(output, mask_feats, pooled, cls_emb, want_masks=deep_supervision, precise=precise)
+        side = None
+        overlap = (not precise) if self.overlap_aux_masks is None else self.overlap_aux_masks
+        if deep_supervision and overlap and not lazy_masks:
+            if self._aux_stream is None:
+                self._aux_stream = torch.cuda.Stream()
+            side = (self._aux_stream, [])
+        cls, msk, bits = self.prediction_heads(output, mask_feats, pooled, cls_emb, want_masks=deep_supervision, precise=precise,
+                                               side=side)
         if deep_supervision:
             pred_cls.append(cls)
             pred_msk.append(msk)
@@ -393,10 +424,14 @@ class MaskTransformer(nn.Module):
             output = ops.layernorm(t, f32(ff.norm.weight), f32(ff.norm.bias), 1e-5)
             last = i == L - 1
             cls, msk, bits = self.prediction_heads(output, mask_feats, None if last else pooled, cls_emb,
-                                                   want_masks=deep_supervision or last, precise=precise, lazy=lazy_masks)
+                                                   want_masks=deep_supervision or last, precise=precise, lazy=lazy_masks,
+                                                   side=None if last else side)
             if deep_supervision or last:
                 pred_cls.append(cls)
                 pred_msk.append(msk)
+        if side is not None:  # join: the auxiliary mask planes are complete before anything downstream reads them
+            torch.cuda.current_stream().wait_stream(side[0])
+            side[1].clear()
         b1 = (lambda t: [x[None] for x in t]) if multi else (lambda t: t[None])  # batch dim 1 (per stack when multi_ar)
         return {
             "pred_logits": pred_cls[-1][None],

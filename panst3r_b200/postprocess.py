@@ -39,7 +39,8 @@ class LazyMasks:
     # bytes of fp32 logits produced per GEMM launch: 200 queries x 96 rows x 256 pixels = 19.7 MB, half a 512x384 view
     # (measured: profiles/r02_lazy_masks.md)
     scratch_bytes = 20 << 20
-    _scratch = {}
+    streams = 2          # chunks in flight (scratch_bytes each: together well inside the L2)
+    _lanes = {}          # (device, launching stream) -> [[side stream, scratch buffer], ...]
 
     def __init__(self, feats, embed, ndim: int = 4):
         if feats.shape[-1] != embed.shape[-1] or len(feats.shape) != 4 or len(embed.shape) != 2:
@@ -157,8 +158,13 @@ class LazyMasks:
             y0 += rows
         return plan
 
-    def panoptic_argmax(self, keep_idx, keep_scores, size, mask_threshold, area_half, area_won, scratch_bytes: int = None):
-        """`ops.panoptic_argmax` without the logits tensor: per view and band, GEMM into the scratch -> band argmax."""
+    def panoptic_argmax(self, keep_idx, keep_scores, size, mask_threshold, area_half, area_won, scratch_bytes: int = None,
+                        streams: int = None):
+        """`ops.panoptic_argmax` without the logits tensor: per view and band, GEMM into a scratch buffer -> band argmax.
+        A band's argmax is a short grid of latency-bound CTAs (one 32 x 32 tile each, walking the kept queries), so the
+        (view, band) chunks are dealt round-robin to `streams` side streams with one scratch buffer each: the GEMM of
+        one chunk runs next to the argmax of another.  Forked from / joined to the current stream; the counters are
+        integer atomics, so the result does not depend on the interleaving."""
         V, hm, wm, _ = self.feats.shape
         Q = self.embed.shape[0]
         H, W = int(size[0]), int(size[1])
@@ -167,15 +173,33 @@ class LazyMasks:
         win = torch.empty((V, H, W), device=dev, dtype=torch.float32)
         plan = self.band_plan(H, scratch_bytes)
         need = max(p_[3] for p_ in plan) * Q * wm
-        key = (dev, torch.cuda.current_stream(dev).cuda_stream)
-        buf = LazyMasks._scratch.get(key)
-        if buf is None or buf.numel() < need:
-            buf = LazyMasks._scratch[key] = torch.empty(need, device=dev, dtype=torch.float32)
+        n_str = max(1, min(int(self.streams if streams is None else streams), V * len(plan)))
+        cur = torch.cuda.current_stream(dev)
+        if n_str == 1:  # everything on the launching stream
+            lanes = LazyMasks._lanes.setdefault((dev, cur.cuda_stream, "solo"), [[cur, None]])
+            lanes[0][0] = cur
+        else:           # side streams of this (device, launching stream), created once
+            lanes = LazyMasks._lanes.setdefault((dev, cur.cuda_stream), [])
+            while len(lanes) < n_str:
+                lanes.append([torch.cuda.Stream(dev), None])
+        for lane in lanes[:n_str]:
+            if lane[0] is not cur:
+                lane[0].wait_stream(cur)  # fork: ids / win / counters / keep lists are ready
+            with torch.cuda.stream(lane[0]):
+                if lane[1] is None or lane[1].numel() < need:
+                    lane[1] = torch.empty(need, device=dev, dtype=torch.float32)
+        c = 0
         for v in range(V):
             for y0, rows, s0, sr in plan:
-                chunk = self.logits(v, s0, s0 + sr, out=buf[:Q * sr * wm].view(Q, sr, wm))
-                ops.panoptic_argmax(chunk[None], keep_idx, keep_scores, (H, W), mask_threshold, area_half, area_won,
-                                    out=(ids[v:v + 1], win[v:v + 1]), band=(y0, rows, s0, hm))
+                st, buf = lanes[c % n_str]
+                c += 1
+                with torch.cuda.stream(st):
+                    chunk = self.logits(v, s0, s0 + sr, out=buf[:Q * sr * wm].view(Q, sr, wm))
+                    ops.panoptic_argmax(chunk[None], keep_idx, keep_scores, (H, W), mask_threshold, area_half, area_won,
+                                        out=(ids[v:v + 1], win[v:v + 1]), band=(y0, rows, s0, hm))
+        for lane in lanes[:n_str]:
+            if lane[0] is not cur:
+                cur.wait_stream(lane[0])  # join
         return ids, win
 
 

@@ -244,6 +244,85 @@ def test_forward_panoptic_equals_forward_plus_postprocess(precision):
 
 
 @pytest.mark.gpu
+def test_lazy_masks_through_forward_inference_multi_ar():
+    """Mixed shapes / a portrait view, 4 keyframes + 2 render-only frames (the memory-query path): with
+    `PanopticDecoder.lazy_masks` every entry of `pred_masks` is a one-view handle whose logits are the eager path's, and the
+    reference-style call `panoptic_inference_v2(..., size, multi_ar=True)` (tools/demo_panst3r.py:236-242) returns the same
+    segments and ids as on the materialised list."""
+    import bench
+    from panst3r_b200 import postprocess as pp
+    from panst3r_b200.panst3r import build_panst3r
+    with torch.device("cuda"):
+        m = build_panst3r("v1", 2, 2, 2)
+    bench.init_weights_(m)
+    classes = [f"c{i}" for i in range(6)]
+    g = torch.Generator().manual_seed(11)
+    m.panoptic_decoder.text_encoder.class_embeddings = {c: torch.randn(768, generator=g) for c in classes}
+    shapes = [(64, 96), (64, 96), (64, 64), (64, 96), (64, 96), (64, 64)]
+    ts = torch.tensor([[64, 96], [64, 96], [64, 64], [96, 64], [64, 96], [64, 64]])  # view 3: portrait, stored transposed
+    imgs = [(torch.rand(3, *sh, generator=g) * 2 - 1).cuda() for sh in shapes]
+    pms, pan = m.forward_inference_multi_ar(imgs, ts, classes, num_keyframes=4)
+    m.panoptic_decoder.lazy_masks = True
+    pms_l, pan_l = m.forward_inference_multi_ar(imgs, ts, classes, num_keyframes=4)
+    m.panoptic_decoder.lazy_masks = False
+    assert all(torch.equal(a, b) for a, b in zip(pms, pms_l)) and torch.equal(pan["pred_logits"], pan_l["pred_logits"])
+    for a, b in zip(pan["pred_masks"], pan_l["pred_masks"]):
+        assert isinstance(b, pp.LazyMasks) and b.shape == a.shape
+        assert (b.materialize() - a).abs().max() <= 1e-6 * a.abs().max()
+    kw = dict(cls_threshold=0.0)
+    size = ts.numpy()
+    r0 = pp.panoptic_inference_v2(pan["pred_logits"], pan["pred_masks"], size, multi_ar=True, **kw)[0]
+    r1 = pp.panoptic_inference_v2(pan_l["pred_logits"], pan_l["pred_masks"], size, multi_ar=True, **kw)[0]
+    assert r0["segments_info"] == r1["segments_info"]
+    for a, b, t in zip(r0["pan"], r1["pan"], ts.tolist()):
+        assert tuple(a.shape) == tuple(t) and (a == b).float().mean() > 0.999
+    # leaving the GPU materialises the handle (outdevice='cpu', the reference demo's pattern)
+    m.panoptic_decoder.lazy_masks = True
+    _, pan_c = m.forward_inference_multi_ar(imgs[:3], ts[:3], classes, outdevice="cpu")
+    m.panoptic_decoder.lazy_masks = False
+    assert all(torch.is_tensor(x) and x.device.type == "cpu" for x in pan_c["pred_masks"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_aux_masks_on_the_side_stream_are_bit_identical(precision):
+    """MaskTransformer.overlap_aux_masks: the auxiliary heads' full-resolution mask GEMMs run on a side stream (64 SMs)
+    next to the following decoder layer.  Same kernels, same operands: every output equals the in-line run bit for bit,
+    eagerly and from a replayed CUDA graph, at 512x384 (the GEMMs are long enough to overlap the whole next layer)."""
+    import bench
+    from panst3r_b200.panst3r import build_panst3r
+    with torch.device("cuda"):
+        m = build_panst3r("v1", 2, 2, 2, head_precision=precision)
+    bench.init_weights_(m)
+    classes = bench.CLASSES[:12]
+    g = torch.Generator().manual_seed(3)
+    m.panoptic_decoder.text_encoder.class_embeddings = {c: torch.randn(768, generator=g) for c in classes}
+    imgs, ts = bench.make_inputs(4, "cuda")
+    imgs = imgs.cuda()
+    mt = m.panoptic_decoder.mask_transformer
+
+    def flat(o):
+        pan, pm = o
+        return [pm, pan["pred_logits"], pan["pred_masks"], pan["out_queries"]] + \
+            [a[k] for a in pan["aux_outputs"] for k in ("pred_logits", "pred_masks")]
+    mt.overlap_aux_masks = False
+    ref = [t.clone() for t in flat(m(imgs, ts, classes))]
+    assert len(ref) == 4 + 2 * 6
+    mt.overlap_aux_masks = True
+    for _ in range(3):
+        out = flat(m(imgs, ts, classes))
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(out, ref))
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        gout = m(imgs, ts, classes)
+    for _ in range(3):
+        gr.replay()
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(flat(gout), ref))
+
+
+@pytest.mark.gpu
 def test_lazy_postprocess_full_size():
     """16 views x 200 queries at 512x384 (BASELINE config 2): lazy == materialised on every pixel; prints both timings."""
     from panst3r_b200 import postprocess as pp

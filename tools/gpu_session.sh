@@ -60,6 +60,17 @@ PY
           PST3R_SPLITK=$v timeout 300 python bench.py --head-precision bf16 --no-gpu-reference --no-cpu-baseline --no-bf16-head --steps 20 2>/dev/null | one >> gpurun_out/sk.log 2>&1; done ;;
     stages) timeout 600 python tools/stage_times.py 16 v1 0 > gpurun_out/stages_r02_v1.json 2> gpurun_out/stages_r02.err; echo "stages rc=$?" ;;
     mmarate) timeout 120 tools/_bin/mma_rate > gpurun_out/mma_rate.md 2>&1; echo "mmarate rc=$?" ;;
+    lazy) timeout 240 python -m pytest tests/test_lazy_masks.py -m gpu -q -s --timeout 200 > gpurun_out/pytest_lazy.log 2>&1; echo "lazy tests rc=$?"; tail -25 gpurun_out/pytest_lazy.log
+          timeout 150 python tools/lazy_masks_bench.py time > gpurun_out/lazy_time.json 2> gpurun_out/lazy_time.err; echo "lazy time rc=$?"; cat gpurun_out/lazy_time.json
+          timeout 240 ncu --profile-from-start off --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv --log-file gpurun_out/lazy_ncu.csv python tools/lazy_masks_bench.py ncu > gpurun_out/lazy_ncu.log 2>&1; echo "lazy ncu rc=$?"
+          python tools/lazy_masks_bench.py parse gpurun_out/lazy_ncu.csv gpurun_out/lazy_ncu_segments.json > gpurun_out/lazy_ncu.md 2>&1; cat gpurun_out/lazy_ncu.md ;;
+    benchq) timeout 600 python bench.py --no-gpu-reference --no-cpu-baseline --steps 10 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "benchq rc=$?"; python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/bench_quick.json").read().strip().splitlines()[-1])
+print({k: d.get(k) for k in ("value", "ms_per_step", "e2e", "bf16_head", "ids_only", "clocks")})
+PY
+      ;;
+    headab) timeout 300 python tools/stage_times.py 16 v1 head > gpurun_out/head_ab.json 2> gpurun_out/head_ab.err; echo "headab rc=$?"; cat gpurun_out/head_ab.json; tail -3 gpurun_out/head_ab.err ;;
     *) echo "unknown step $s" ;;
   esac
 done

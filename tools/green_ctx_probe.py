@@ -47,6 +47,7 @@ def main():
         m = build_panst3r("v1")
     bench.init_weights_(m)
     m.overlap_dino = False
+    m.panoptic_decoder.mask_transformer.overlap_aux_masks = False
     imgs, ts = bench.make_inputs(V, "cuda")
     imgs = imgs.cuda()
     cat, rows, x, pos, _ = m._features(imgs, ts)

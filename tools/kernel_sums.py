@@ -21,6 +21,7 @@ bench.init_weights_(m)
 g = torch.Generator().manual_seed(7)
 m.panoptic_decoder.text_encoder.class_embeddings = {c: torch.randn(768, generator=g) for c in bench.CLASSES}
 m.overlap_dino = False
+m.panoptic_decoder.mask_transformer.overlap_aux_masks = False
 imgs, ts = bench.make_inputs(16, "cuda")
 imgs = imgs.cuda()
 for _ in range(3):

@@ -20,7 +20,8 @@ sys.path.insert(0, ROOT)
 
 V, HM, WM, C, Q, K = 16, 192, 256, 256, 200, 20
 SIZE = (384, 512)
-BUDGETS_MB = [8, 20, 40]  # 6 / 2 / 1 band(s) per view
+# (scratch MB per chunk, chunks in flight): 8 / 20 / 40 MB = 6 / 2 / 1 band(s) per view
+CONFIGS = [(8, 1), (20, 1), (40, 1), (20, 2), (20, 3), (10, 3), (40, 2)]
 
 
 def setup(split: bool):
@@ -40,9 +41,10 @@ def variants(lz, keep, sc, areas):
     """name -> (callable running ONE argmax round incl. the mask GEMM(s), number of kernel launches)"""
     from panst3r_b200 import ops
     out = {"materialised": (lambda: ops.panoptic_argmax(lz.materialize(), keep, sc, SIZE, 0.25, areas[0], areas[1]), 2)}
-    for mb in BUDGETS_MB:
+    for mb, ns in CONFIGS:
         n = 2 * V * len(lz.band_plan(SIZE[0], mb << 20))
-        out[f"lazy_{mb}MB"] = (lambda mb=mb: lz.panoptic_argmax(keep, sc, SIZE, 0.25, areas[0], areas[1], scratch_bytes=mb << 20), n)
+        out[f"lazy_{mb}MB_x{ns}"] = (lambda mb=mb, ns=ns: lz.panoptic_argmax(keep, sc, SIZE, 0.25, areas[0], areas[1],
+                                                                           scratch_bytes=mb << 20, streams=ns), n)
     return out
 
 

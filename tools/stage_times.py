@@ -1,5 +1,5 @@
 """In-graph time of every stage of one PanSt3R.forward (development tool; each stage captured in its own CUDA graph,
-timed with CUDA events over several replays).  Usage:  python tools/stage_times.py [V] [variant]"""
+timed with CUDA events over several replays).  Usage:  python tools/stage_times.py [V] [variant] [dino SM list | head]"""
 import json
 import os
 import sys
@@ -46,6 +46,23 @@ def main():
     imgs = imgs.cuda()
     cat, rows, x, pos, _ = m._features(imgs, ts)
     out = {}
+    if len(sys.argv) > 3 and sys.argv[3] == "head":
+        # panoptic head only: auxiliary mask GEMMs on the side stream (MaskTransformer.overlap_aux_masks) vs in line
+        m(imgs, ts, bench.CLASSES)  # fills `cat` through the whole trunk
+        mt = m.panoptic_decoder.mask_transformer
+        for prec in ("fp32", "bf16"):
+            m.panoptic_decoder.precision = prec
+            mt.overlap_aux_masks = False
+            out[f"head_{prec}_in_line"] = timed_graph(lambda: m.panoptic_decoder(None, imgs, pos, ts, bench.CLASSES, cat_feats=cat), 10)
+            mt.overlap_aux_masks = True
+            for sms in (32, 64, 96):
+                mt.aux_mask_sms = sms
+                out[f"head_{prec}_aux_side_{sms}sm"] = timed_graph(lambda: m.panoptic_decoder(None, imgs, pos, ts, bench.CLASSES, cat_feats=cat), 10)
+            m.panoptic_decoder.lazy_masks = True
+            out[f"head_{prec}_lazy_masks"] = timed_graph(lambda: m.panoptic_decoder(None, imgs, pos, ts, bench.CLASSES, cat_feats=cat), 10)
+            m.panoptic_decoder.lazy_masks = False
+        print(json.dumps({"views": V, "variant": variant, "stages": {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in out.items()}}))
+        return
     out["dino"] = timed_graph(lambda: m.forward_dino(imgs, ts, out=rows[:, ENC_DIM + DEC_DIM:]))
     out["encoder"] = timed_graph(lambda: m.forward_must3r_encoder(imgs, ts, out=rows[:, :ENC_DIM]))
     out["memory_build"] = timed_graph(lambda: m.build_memory(x, pos, ts))
