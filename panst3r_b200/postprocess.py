@@ -39,7 +39,9 @@ class LazyMasks:
     # bytes of fp32 logits produced per GEMM launch: 200 queries x 96 rows x 256 pixels = 19.7 MB, half a 512x384 view
     # (measured: profiles/r02_lazy_masks.md)
     scratch_bytes = 20 << 20
-    streams = 2          # chunks in flight (scratch_bytes each: together well inside the L2)
+    # chunks in flight, each with its own scratch.  1: the logits stay in the L2 (DRAM traffic = features + maps + 10 %);
+    # 2 with 40 MB chunks halves the time of a round but writes most of the logits to DRAM once (profiles/r02_lazy_masks.md)
+    streams = 1
     _lanes = {}          # (device, launching stream) -> [[side stream, scratch buffer], ...]
 
     def __init__(self, feats, embed, ndim: int = 4):
