@@ -70,6 +70,8 @@ d = json.loads(open("gpurun_out/bench_quick.json").read().strip().splitlines()[-
 print({k: d.get(k) for k in ("value", "ms_per_step", "e2e", "bf16_head", "ids_only", "clocks")})
 PY
       ;;
+    lazyfull) timeout 300 ncu --profile-from-start off --set full --cache-control none --clock-control none --import-source on -c 4 -f -o gpurun_out/r02_lazy_kernels python tools/lazy_masks_bench.py ncufull > gpurun_out/lazyfull.log 2>&1; echo "lazyfull rc=$?"
+              ncu -i gpurun_out/r02_lazy_kernels.ncu-rep --page raw --csv > gpurun_out/r02_lazy_kernels_raw.csv 2>/dev/null; ls -la gpurun_out/r02_lazy_kernels* ;;
     headab) timeout 300 python tools/stage_times.py 16 v1 head > gpurun_out/head_ab.json 2> gpurun_out/head_ab.err; echo "headab rc=$?"; cat gpurun_out/head_ab.json; tail -3 gpurun_out/head_ab.err ;;
     *) echo "unknown step $s" ;;
   esac

@@ -81,11 +81,14 @@ def main():
 
     import torch
     cudart = torch.cuda.cudart()
-    if mode == "ncu":
+    if mode in ("ncu", "ncufull"):
+        # ncufull: `ncu --set full` of four launches — the whole-map mask GEMM + argmax, then one band GEMM + band argmax
         segs = []
-        for split in (True, False):
+        for split in ((True,) if mode == "ncufull" else (True, False)):
             lz, keep, sc, areas = setup(split)
             for name, (fn, n) in variants(lz, keep, sc, areas).items():
+                if mode == "ncufull" and name not in ("materialised", "lazy_20MB_x1"):
+                    continue
                 fn()
                 fn()
                 flush()
