@@ -105,7 +105,11 @@ class LazyMasks:
         raise IndexError("LazyMasks: a single view is indexed by materialising it")
 
     def to(self, device=None, *a, **k):
-        if device is None or torch.device(device).type == "cuda":
+        """Same CUDA device / fp32: the handle itself.  Anything else (another device, another dtype) needs the values:
+        the tensor is evaluated and converted."""
+        if device is None or device == torch.float32:
+            return self
+        if not isinstance(device, torch.dtype) and torch.device(device).type == "cuda":
             return self
         return self.materialize().to(device, *a, **k)
 
