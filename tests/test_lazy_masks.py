@@ -89,6 +89,25 @@ def test_band_entry_point_rejects_bad_bands_without_a_gpu():
     assert call(0, 48, 0, 64, qs=47 * 128) == -1 and b"pitch" in lib.pst3r_last_error()
 
 
+def test_forward_panoptic_host_logic_without_a_gpu():
+    """Unknown post-processing names are refused before any work; on a CPU module the forward refuses (no CPU fallback) and
+    the `lazy_masks` switch is restored; a batch of lazy handles is refused by the head."""
+    from panst3r_b200.lib import Pst3rError
+    from panst3r_b200.panst3r import build_panst3r
+    m = build_panst3r("v1", 1, 1, 1)
+    imgs, ts = torch.zeros(1, 2, 3, 32, 48), torch.tensor([[[32, 48]] * 2])
+    with pytest.raises(NotImplementedError):
+        m.forward_panoptic(imgs, ts, ["a"], postprocess="qubo")
+    assert m.postprocess_default == "standard_v2" and m.panoptic_decoder.lazy_masks is False
+    with pytest.raises(Pst3rError):
+        m.forward_panoptic(imgs, ts, ["a"])
+    assert m.panoptic_decoder.lazy_masks is False
+    m.panoptic_decoder.lazy_masks = True
+    with pytest.raises(Pst3rError, match="one scene per call"):
+        m.panoptic_decoder(None, torch.zeros(2, 2, 3, 32, 48), None, torch.tensor([[[32, 48]] * 2] * 2), ["a"],
+                           cat_feats=torch.zeros(2, 2, 6, 2816, dtype=torch.bfloat16))
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("H,W,hm,wm", [(192, 256, 96, 128), (90, 140, 48, 64), (64, 96, 64, 96)])
